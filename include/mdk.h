@@ -1,0 +1,175 @@
+/*
+ * mdk.h -- C ABI of libmdk.so, the B200 (sm_100a) kernels behind the MDSuite
+ * calculator API (SamTov/LAMMPS-Analysis).
+ *
+ * The reference is pure Python on TensorFlow and has no FFI of its own
+ * (SURVEY.md section 8b); this is the boundary introduced *below* its calculator
+ * classes.  Every entry point names the reference code whose arithmetic it
+ * replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - All array pointers are DEVICE pointers owned by the caller unless the
+ *     parameter is documented as HOST.
+ *   - The library never allocates or frees caller-visible memory, never
+ *     synchronises the stream and keeps no global mutable state except a
+ *     thread-local last-error string.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - Return 0 on success, a negative MDK_E* code otherwise; mdk_last_error()
+ *     then describes the failure.
+ *   - Accumulating outputs (histograms, sums) are `+=`: zero them first.
+ */
+#ifndef MDK_H_
+#define MDK_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDK_VERSION 100
+
+#define MDK_OK 0
+#define MDK_EINVAL -1      /* bad argument */
+#define MDK_ECUDA -2       /* CUDA runtime / launch failure */
+#define MDK_EUNSUPPORTED -3 /* valid request outside what the kernels support */
+
+#define MDK_MAX_SPECIES 8
+
+/* flags for mdk_rdf_hist */
+#define MDK_RDF_EXACT_DIV 1 /* true fp32 division + separate mul/sub in the minimum image
+                               (required when cutoff >= min(box)/2 or coordinates span
+                               more than 2.5 box lengths); default is the fast path that
+                               is bit-identical under those preconditions */
+
+typedef void* mdk_stream_t;
+
+int mdk_version(void);
+const char* mdk_last_error(void);
+/* Number of SMs of the current device (used by hosts to size batches). */
+int mdk_sm_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * RDF  (mdsuite/calculators/radial_distribution_function.py)
+ * ------------------------------------------------------------------------- */
+
+/* Rows of one RDF row tile; species blocks in the packed frame array must start
+ * at multiples of this and be padded with NaN up to the next multiple. */
+int mdk_rdf_tile(void);
+
+/* HOST helper.  Fills thr_host[0..nbins] with the fp32 thresholds on the squared
+ * distance that reproduce tf.histogram_fixed_width exactly:
+ *   bin(d2) = #{ m in 1..nbins-1 : d2 >= thr[m] },  thr[0] = 0, thr[nbins] = +inf
+ * and *cut2_host with the smallest fp32 d2 whose correctly rounded sqrt is
+ * >= (float)cutoff, so that `d < cutoff` <=> `d2 < cut2`.
+ * Replaces: radial_distribution_function.py:616-645 (bin_minibatch),
+ *           utils/linalg.py:125-136 (apply_system_cutoff),
+ *           tensorflow/core/kernels/histogram_op.cc (CPU functor). */
+int mdk_rdf_thresholds(float cutoff, int nbins, float* thr_host, float* cut2_host);
+
+/* Gather + transpose atom-major trajectory rows into the frame-major SoA layout
+ * the pair kernel streams:  out[k][d][dst_first + a] = traj[(atom_first + a)][frames[k]][d]
+ * for a < atom_count, and NaN for dst_first + atom_count <= idx < dst_first + dst_span.
+ *   traj   : [A_total][T][3] fp32 (MDSuite store layout, simulation_database.py:364-368)
+ *   frames : device int32 [n_frames]
+ *   out    : [n_frames][3][n_pad] fp32
+ * Replaces: data_manager.py:195-201 (frame fancy-index load) and
+ *           radial_distribution_function.py:535-563 (_format_data concat). */
+int mdk_rdf_pack(const float* traj, long long A_total, long long T, long long atom_first,
+                 long long atom_count, const int* frames, int n_frames, float* out,
+                 long long n_pad, long long dst_first, long long dst_span, mdk_stream_t stream);
+
+/* Per-dimension min / max of a packed frame array (NaN padding ignored).
+ * minmax: device float[6] = {minx,miny,minz,maxx,maxy,maxz}, caller-initialised to
+ * {+inf x3, -inf x3}.  Used by the host to decide whether the fast minimum-image
+ * path is bit-exact (coordinate extent < 2.5 box lengths). */
+int mdk_coord_extent(const float* pos_soa, int n_frames, long long n_pad, float* minmax,
+                     mdk_stream_t stream);
+
+/* All-pairs minimum-image distance histogram for every species pair a <= b.
+ *   pos_soa : [n_frames][3][n_pad] fp32, species blocks [sp_lo[s], sp_hi[s]) (HOST
+ *             arrays, multiples of mdk_rdf_tile()), NaN-padded
+ *   box     : HOST float[3]
+ *   thr     : device float[nbins+1] from mdk_rdf_thresholds; cut2 likewise
+ *   hist    : device u64 [n_pairs][nbins], pair order = combinations_with_replacement
+ *             (0,0),(0,1),...,(1,1),... ; accumulated (+=)
+ *   work_counter : device scratch, 8 bytes, 8-byte aligned; zeroed by the call
+ * Pairs counted: i < j within a species block, all (i, j) across blocks, for each
+ * frame: r = p_j - p_i; r -= rint(r / L) * L; d2 = (x*x + y*y) + z*z (fp32, each op
+ * rounded); counted iff sqrt(d2) < cutoff.
+ * Replaces: utils/linalg.py:84-122 (min image, triu indices),
+ *           radial_distribution_function.py:422-524, 616-689, 846-885. */
+int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad, const int* sp_lo,
+                 const int* sp_hi, int n_species, const float* box, float cut2, float cutoff,
+                 int nbins, const float* thr, unsigned long long* hist,
+                 unsigned int* work_counter, int flags, mdk_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * Einstein MSD / Green-Kubo ACF
+ * ------------------------------------------------------------------------- */
+
+/* Windowed single-origin mean-square displacement.
+ *   traj : [A][T][3] fp32 (atom-major), atoms [a_lo, a_hi), frames [t0, t0 + B)
+ *   windows start at t0 + e*ct, e < W;  lags tau[k] (device int32 [n_tau], all < span;
+ *   span = data_range, the window length in frames)
+ *   msd_sum[k] += sum_w sum_a sum_d (x[a, s_w + tau_k, d] - x[a, s_w, d])^2   (fp64)
+ * Replaces: einstein_diffusion_coefficients.py:168-190 (ensemble_operation) and the
+ *           window loop :230-244 / data_manager.py:309-339. */
+int mdk_msd_windowed(const float* traj, long long A, long long T, long long a_lo, long long a_hi,
+                     long long t0, int W, int ct, const int* tau, int n_tau, int span,
+                     double* msd_sum, mdk_stream_t stream);
+
+/* Lag products for the windowed unbiased autocorrelation.
+ *   P[t - t0][m] += sum_{a in [a_lo,a_hi)} sum_d v[a,t,d] * v[a,t+m,d]
+ *   for t0 <= t < t0 + B, 0 <= m < N, t + m < t0 + B          (P: device f64 [B][N])
+ * Replaces the per-window FFT of tfp.stats.auto_correlation in
+ * green_kubo_self_diffusion_coefficients.py:191-199 and
+ * green_kubo_ionic_conductivity.py:201-203 (see mdk_acf_windows). */
+int mdk_acf_lagprod(const float* traj, long long A, long long T, long long a_lo, long long a_hi,
+                    long long t0, int B, int N, double* P, mdk_stream_t stream);
+
+/* Window sums from the lag products:
+ *   S_w[m] = (1/(N-m)) * sum_{t = w*ct}^{w*ct + N-1-m} P[t][m],  w < W
+ *   acf_sum[m] += sum_w S_w[m];  if acf_win != NULL: acf_win[w][m] = S_w[m]
+ * which equals sum over atoms and dims of tfp.stats.auto_correlation(window,
+ * axis=1, normalize=False, center=False).  P is overwritten by its prefix sum in t. */
+int mdk_acf_windows(double* P, int B, int N, int W, int ct, double* acf_sum, double* acf_win,
+                    mdk_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * Transformations
+ * ------------------------------------------------------------------------- */
+
+/* Box-jump unwrapping along time, per (atom, dim):
+ *   jump_t = round_half_even((p_t - p_{t-1}) / L)   (fp64, p_{-1} = carry_pos or p_0)
+ *   img_t  = carry_img - sum_{u<=t} jump_u
+ *   out_t  = (float)((double)p_t + img_t * L)
+ *   pos/out : [A][T][3] fp32; box HOST double[3]
+ *   carry_pos : device float [A][3] or NULL (first batch); updated to p_{T-1}
+ *   carry_img : device double [A][3], in/out (zero it for the first batch)
+ * Replaces: transformations/unwrap_coordinates.py:51-81. */
+int mdk_unwrap(const float* pos, long long A, long long T, const double* box,
+               float* carry_pos, int have_carry, double* carry_img, float* out,
+               mdk_stream_t stream);
+
+/* out = (float)((double)pos + (double)img * L).  img: [A][T][3] fp32.
+ * Replaces: transformations/unwrap_via_indices.py:49-57. */
+int mdk_unwrap_indices(const float* pos, const float* img, long long n_atom_frames,
+                       const double* box, float* out, mdk_stream_t stream);
+
+/* J[t][d] += sum_a q_a * v[a][t][d]   (fp64 accumulation)
+ *   q_mode 0: scalar *q (HOST double), 1: q device float [A], 2: q device float [A][T]
+ * Replaces: transformations/ionic_current.py:48-58. */
+int mdk_ionic_current(const float* vel, long long A, long long T, const void* q, int q_mode,
+                      double* J, mdk_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * Measurement helpers (bench.py / tests only)
+ * ------------------------------------------------------------------------- */
+
+/* Runs an FP32 FMA throughput kernel (packed FFMA2 if packed != 0) and returns the
+ * measured TFLOP/s in *tflops (2 flop per FMA).  Synchronises the device. */
+int mdk_peak_fp32(int packed, int iters, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDK_H_ */

@@ -1,0 +1,646 @@
+// rdf_pair_hist: minimum-image all-pairs distance histogram, one launch for every
+// species pair and every frame of a batch.
+//
+// Replaces the TF op chain of the reference
+//   utils/linalg.py:102-122   get_partial_triu_indices  (never materialised here)
+//   utils/linalg.py:84-99     apply_minimum_image
+//   radial_distribution_function.py:647-689  get_dij   (gather, sub, min-image, norm)
+//   radial_distribution_function.py:616-645  bin_minibatch (species mask, cutoff, histogram)
+// with a tiled pair pass:
+//   * persistent CTAs pull work items (species pair, frame, row tile, column chunk) from an
+//     atomic counter;
+//   * each thread keeps R row atoms in registers (negated, duplicated into f32x2 pairs);
+//   * column tiles (x[], y[], z[] of TJ atoms) are staged into shared memory by the TMA
+//     engine (cp.async.bulk + mbarrier, double buffered);
+//   * the geometry runs on packed FFMA2/FADD2/FMUL2 (two column atoms per instruction) and
+//     reproduces the reference's fp32 rounding sequence exactly:
+//         r = p_j - p_i ; r -= rint(r/L)*L ; d2 = (x*x + y*y) + z*z
+//   * binning is exact: a fast fp32 guess g = rint(sqrt.approx(d2)/step) is corrected
+//     against a table of fp32 thresholds on d2 (mdk_rdf_thresholds) held in shared memory;
+//   * counts go to a CTA-private u32 histogram in shared memory and are flushed to the
+//     global u64 histogram when the species pair changes / the CTA retires.
+#include "mdk_common.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace mdk {
+
+constexpr int TJ = 256;  // column tile (atoms) == padding granule of species blocks
+constexpr int MAX_PAIRS = MDK_MAX_SPECIES * (MDK_MAX_SPECIES + 1) / 2;
+constexpr float RINT_MAGIC = 12582912.0f;         // 1.5 * 2^23: ulp == 1, even
+constexpr unsigned RINT_MAGIC_BITS = 0x4B400000u; // __float_as_uint(RINT_MAGIC)
+
+struct RdfParams {
+  const float* pos;            // [F][3][n_pad]
+  long long n_pad;
+  int n_frames;
+  int n_species;
+  int n_pairs;
+  int sp_lo[MDK_MAX_SPECIES];
+  int sp_hi[MDK_MAX_SPECIES];
+  // per species pair p = (a, b)
+  int pair_a[MAX_PAIRS];
+  int pair_b[MAX_PAIRS];
+  int row_tiles[MAX_PAIRS];      // ceil(len_a / TI)
+  int col_tiles[MAX_PAIRS];      // len_b / TJ
+  int chunks_per_row[MAX_PAIRS]; // ceil(col_tiles / CJ)
+  unsigned long long item_start[MAX_PAIRS + 1];
+  unsigned long long total_items;
+  int CJ;                        // column tiles per work item
+  float box[3];
+  float inv_box[3];
+  float cut2;
+  float inv_step;
+  int nbins;
+  const float* thr;              // [nbins + 1]
+  unsigned long long* hist;      // [n_pairs][nbins]
+  unsigned long long* counter;   // dynamic work counter
+  unsigned int flush_tiles;      // flush after this many column tiles (u32 overflow guard)
+  unsigned int one;              // == 1, kept opaque to the compiler (see bin_two)
+};
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Exact bin of an in-cutoff squared distance: k in {g-1, g}, g = rint(sqrt(d2)/step)
+// (|sqrt.approx error| * nbins << 0.5), decided against the threshold table thr[g].
+// Scalar C++ form, used on the slow paths (diagonal tiles, exact-division mode).
+__device__ __forceinline__ void bin_one(float d2, bool valid, const float* __restrict__ s_thr,
+                                        unsigned int* __restrict__ s_cnt, float inv_step) {
+  if (valid) {
+    const float d = sqrt_approx(d2);
+    const float t = fmaf(d, inv_step, RINT_MAGIC);
+    const unsigned g = __float_as_uint(t) - RINT_MAGIC_BITS;
+    const float tg = s_thr[g];
+    const unsigned k = g - (d2 >= tg ? 0u : 1u);
+    atomicAdd(&s_cnt[k], 1u);
+  }
+}
+
+// Same decision for two squared distances without divergent control flow:
+//   p  = d2 < cut2                       in cutoff
+//   g  = bits(fma(sqrt(d2), 1/step, 1.5*2^23)) - bits(1.5*2^23)
+//   tg = thr[g]                           (shared, predicated on p)
+//   k  = g - (d2 < tg) ;  p -> ++cnt[k]
+// thr_c = smem address of thr[0] minus 4*bits(1.5*2^23); delta = &cnt[0] - &thr[0] (bytes).
+// ptxas never predicates ATOMS (it wraps it in BSSY/BRA/BSYNC), so there are three ways
+// to issue the increment (AM):
+//   0: predicated red (ptxas emits a branch around ATOMS.ADD)
+//   1: unconditional ATOMS.ADD; lanes outside the cutoff hit a per-lane dump slot
+//   2: as 1 with a literal 1 (ATOMS.POPC.INC)
+// `one` is 1 but opaque to the compiler (a literal turns the reduction into POPC.INC).
+template <int AM>
+__device__ __forceinline__ void bin_two(float2 d2, float cut2, float2 inv_step2, uint32_t thr_c,
+                                        uint32_t delta, uint32_t one, uint32_t dump) {
+#define MDK_BIN_HEAD                                   \
+  "{\n"                                                \
+  ".reg .pred p0, q0, p1, q1;\n"                       \
+  ".reg .f32 e0, e1, t0, t1, g0, g1;\n"                \
+  ".reg .b64 ee, tt;\n"                                \
+  ".reg .u32 a0, a1, b0, b1;\n"                        \
+  "setp.lt.f32 p0, %0, %2;\n"                          \
+  "setp.lt.f32 p1, %1, %2;\n"                          \
+  "sqrt.approx.ftz.f32 e0, %0;\n"                      \
+  "sqrt.approx.ftz.f32 e1, %1;\n"                      \
+  "mov.b64 ee, {e0, e1};\n"                            \
+  "fma.rn.f32x2 tt, ee, %3, %4;\n"                     \
+  "mov.b64 {t0, t1}, tt;\n"                            \
+  "mov.b32 b0, t0;\n"                                  \
+  "mov.b32 b1, t1;\n"                                  \
+  "mad.lo.u32 a0, b0, 4, %5;\n"                        \
+  "mad.lo.u32 a1, b1, 4, %5;\n"                        \
+  "@p0 ld.shared.f32 g0, [a0];\n"                      \
+  "@p1 ld.shared.f32 g1, [a1];\n"                      \
+  "setp.lt.f32 q0, %0, g0;\n"                          \
+  "setp.lt.f32 q1, %1, g1;\n"                          \
+  "add.u32 a0, a0, %6;\n"                              \
+  "add.u32 a1, a1, %6;\n"                              \
+  "@q0 add.u32 a0, a0, -4;\n"                          \
+  "@q1 add.u32 a1, a1, -4;\n"
+#define MDK_BIN_ARGS                                                                        \
+  "f"(d2.x), "f"(d2.y), "f"(cut2), "l"(*reinterpret_cast<unsigned long long*>(&inv_step2)), \
+      "l"(0x4B4000004B400000ull), "r"(thr_c), "r"(delta), "r"(one), "r"(dump)
+  if (AM == 0) {
+    asm volatile(MDK_BIN_HEAD
+                 "@p0 red.shared.add.u32 [a0], %7;\n"
+                 "@p1 red.shared.add.u32 [a1], %7;\n"
+                 "}\n" ::MDK_BIN_ARGS
+                 : "memory");
+  } else if (AM == 1) {
+    asm volatile(MDK_BIN_HEAD
+                 "selp.u32 a0, a0, %8, p0;\n"
+                 "selp.u32 a1, a1, %8, p1;\n"
+                 "red.shared.add.u32 [a0], %7;\n"
+                 "red.shared.add.u32 [a1], %7;\n"
+                 "}\n" ::MDK_BIN_ARGS
+                 : "memory");
+  } else {
+    asm volatile(MDK_BIN_HEAD
+                 "selp.u32 a0, a0, %8, p0;\n"
+                 "selp.u32 a1, a1, %8, p1;\n"
+                 "red.shared.add.u32 [a0], 1;\n"
+                 "red.shared.add.u32 [a1], 1;\n"
+                 "}\n" ::MDK_BIN_ARGS
+                 : "memory");
+  }
+#undef MDK_BIN_HEAD
+#undef MDK_BIN_ARGS
+}
+
+// Flush the CTA-private histogram to the global one and clear it.
+template <int NT>
+__device__ __forceinline__ void flush_hist(unsigned int* s_cnt, int nbins,
+                                           unsigned long long* __restrict__ ghist) {
+  __syncthreads();
+  for (int b = threadIdx.x; b < nbins; b += NT) {
+    const unsigned v = s_cnt[b];
+    if (v) {
+      atomicAdd(&ghist[b], static_cast<unsigned long long>(v));
+      s_cnt[b] = 0u;
+    }
+  }
+  __syncthreads();
+}
+
+template <int NT, int R, bool EXACT, int AM>
+__global__ void __launch_bounds__(NT) rdf_pair_hist_kernel(const __grid_constant__ RdfParams P) {
+  constexpr int TI = NT * R;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: [stage0 xyz | stage1 xyz | mbar x2 | item | thr (nbins+1) | cnt (nbins, padded
+  // to 32) | 32 dump slots]
+  float* s_tile = reinterpret_cast<float*>(smem_raw);                 // 2 * 3 * TJ floats
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tile + 2 * 3 * TJ); // 2 barriers
+  unsigned long long* s_item = reinterpret_cast<unsigned long long*>(s_bar + 2);
+  float* s_thr = reinterpret_cast<float*>(s_item + 2);
+  const int thr_len = (P.nbins + 1 + 3) & ~3;
+  unsigned int* s_cnt = reinterpret_cast<unsigned int*>(s_thr + thr_len);
+
+  const int tid = threadIdx.x;
+  for (int b = tid; b <= P.nbins; b += NT) s_thr[b] = __ldg(P.thr + b);
+  for (int b = tid; b < P.nbins; b += NT) s_cnt[b] = 0u;
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  uint32_t phase[2] = {0u, 0u};
+  int cur_pair = -1;
+  unsigned int tiles_since_flush = 0;
+
+  const float inv_step = P.inv_step;
+  const float2 inv_step2 = make_float2(inv_step, inv_step);
+  const float cut2 = P.cut2;
+  const uint32_t thr_c = smem_u32(s_thr) - 4u * RINT_MAGIC_BITS;
+  const uint32_t cnt_delta = smem_u32(s_cnt) - smem_u32(s_thr);
+  const uint32_t one = P.one;
+  const uint32_t dump = smem_u32(s_cnt) + 4u * ((P.nbins + 31) & ~31) + 4u * (tid & 31);
+  const float2 magic2 = make_float2(RINT_MAGIC, RINT_MAGIC);
+  const float2 nmagic2 = make_float2(-RINT_MAGIC, -RINT_MAGIC);
+  const float2 invLx = make_float2(P.inv_box[0], P.inv_box[0]);
+  const float2 invLy = make_float2(P.inv_box[1], P.inv_box[1]);
+  const float2 invLz = make_float2(P.inv_box[2], P.inv_box[2]);
+  const float2 nLx = make_float2(-P.box[0], -P.box[0]);
+  const float2 nLy = make_float2(-P.box[1], -P.box[1]);
+  const float2 nLz = make_float2(-P.box[2], -P.box[2]);
+
+  for (;;) {
+    if (tid == 0) s_item[0] = atomicAdd(P.counter, 1ull);
+    __syncthreads();
+    const unsigned long long item = s_item[0];
+    __syncthreads();
+    if (item >= P.total_items) break;
+
+    // ---- decode item -> (pair, frame, row tile, column chunk) -------------------------
+    int p = 0;
+    while (p + 1 < P.n_pairs && item >= P.item_start[p + 1]) ++p;
+    const unsigned long long local = item - P.item_start[p];
+    const int cpr = P.chunks_per_row[p];
+    const unsigned long long ipf = static_cast<unsigned long long>(P.row_tiles[p]) * cpr;
+    const int f = static_cast<int>(local / ipf);
+    const int rem = static_cast<int>(local % ipf);
+    const int I = rem / cpr;
+    const int c = rem % cpr;
+    const int a = P.pair_a[p], b = P.pair_b[p];
+    const bool same = (a == b);
+    int j_tile0 = c * P.CJ;
+    int j_tile1 = min(j_tile0 + P.CJ, P.col_tiles[p]);
+    if (same) j_tile0 = max(j_tile0, I * (TI / TJ));  // only columns j > i
+    if (j_tile0 >= j_tile1) continue;                 // empty item (below the diagonal)
+
+    if (p != cur_pair) {
+      if (cur_pair >= 0) flush_hist<NT>(s_cnt, P.nbins, P.hist + (size_t)cur_pair * P.nbins);
+      cur_pair = p;
+      tiles_since_flush = 0;
+    }
+
+    const float* __restrict__ fx = P.pos + (size_t)f * 3 * P.n_pad;
+    const float* __restrict__ fy = fx + P.n_pad;
+    const float* __restrict__ fz = fy + P.n_pad;
+
+    // ---- row atoms -> registers (negated, duplicated) -----------------------------------
+    const int row_base = P.sp_lo[a] + I * TI;
+    float2 nxi[R], nyi[R], nzi[R];
+    int irow[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = row_base + r * NT + tid;
+      irow[r] = i;
+      float x = __int_as_float(0x7fc00000), y = x, z = x;  // NaN rows never pass d2 < cut2
+      if (i < P.sp_hi[a]) {
+        x = __ldg(fx + i);
+        y = __ldg(fy + i);
+        z = __ldg(fz + i);
+      }
+      nxi[r] = make_float2(-x, -x);
+      nyi[r] = make_float2(-y, -y);
+      nzi[r] = make_float2(-z, -z);
+    }
+
+    // ---- column tiles: TMA double buffer ------------------------------------------------
+    const int col_base = P.sp_lo[b];
+    auto issue = [&](int jt, int stage) {
+      float* dst = s_tile + stage * 3 * TJ;
+      const size_t off = (size_t)col_base + (size_t)jt * TJ;
+      mbar_expect_tx(&s_bar[stage], 3u * TJ * sizeof(float));
+      bulk_g2s(dst, fx + off, TJ * sizeof(float), &s_bar[stage]);
+      bulk_g2s(dst + TJ, fy + off, TJ * sizeof(float), &s_bar[stage]);
+      bulk_g2s(dst + 2 * TJ, fz + off, TJ * sizeof(float), &s_bar[stage]);
+    };
+    if (tid == 0) {
+      issue(j_tile0, 0);
+      if (j_tile0 + 1 < j_tile1) issue(j_tile0 + 1, 1);
+    }
+
+    for (int jt = j_tile0; jt < j_tile1; ++jt) {
+      const int stage = (jt - j_tile0) & 1;
+      mbar_wait(&s_bar[stage], phase[stage]);
+      phase[stage] ^= 1u;
+      const float* __restrict__ sx = s_tile + stage * 3 * TJ;
+      const float* __restrict__ sy = sx + TJ;
+      const float* __restrict__ sz = sy + TJ;
+      const int j0 = col_base + jt * TJ;
+      const bool diag = same && (j0 < row_base + TI);  // tile overlaps this row tile
+
+      if (!EXACT && !diag) {
+#pragma unroll 2
+        for (int jj = 0; jj < TJ; jj += 2) {
+          const float2 xj = *reinterpret_cast<const float2*>(sx + jj);
+          const float2 yj = *reinterpret_cast<const float2*>(sy + jj);
+          const float2 zj = *reinterpret_cast<const float2*>(sz + jj);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float2 dx = __fadd2_rn(xj, nxi[r]);
+            const float2 dy = __fadd2_rn(yj, nyi[r]);
+            const float2 dz = __fadd2_rn(zj, nzi[r]);
+            const float2 tx = __ffma2_rn(dx, invLx, magic2);
+            const float2 ty = __ffma2_rn(dy, invLy, magic2);
+            const float2 tz = __ffma2_rn(dz, invLz, magic2);
+            const float2 nx = __fadd2_rn(tx, nmagic2);
+            const float2 ny = __fadd2_rn(ty, nmagic2);
+            const float2 nz = __fadd2_rn(tz, nmagic2);
+            const float2 rx = __ffma2_rn(nx, nLx, dx);
+            const float2 ry = __ffma2_rn(ny, nLy, dy);
+            const float2 rz = __ffma2_rn(nz, nLz, dz);
+            // squares packed; the two adds stay scalar: ptxas 12.9 contracts
+            // mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would break the reference's
+            // rounding sequence (x*x + y*y) + z*z.
+            const float2 xx = __fmul2_rn(rx, rx);
+            const float2 yy = __fmul2_rn(ry, ry);
+            const float2 zz = __fmul2_rn(rz, rz);
+            float2 d2;
+            d2.x = __fadd_rn(__fadd_rn(xx.x, yy.x), zz.x);
+            d2.y = __fadd_rn(__fadd_rn(xx.y, yy.y), zz.y);
+            bin_two<AM>(d2, cut2, inv_step2, thr_c, cnt_delta, one, dump);
+          }
+        }
+      } else {
+        // diagonal tiles (j > i mask) and the exact-division fallback: scalar path
+        for (int jj = 0; jj < TJ; ++jj) {
+          const float xj = sx[jj], yj = sy[jj], zj = sz[jj];
+          const int j = j0 + jj;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            float rx = __fsub_rn(xj, -nxi[r].x);
+            float ry = __fsub_rn(yj, -nyi[r].x);
+            float rz = __fsub_rn(zj, -nzi[r].x);
+            if (EXACT) {
+              rx = __fsub_rn(rx, __fmul_rn(rintf(__fdiv_rn(rx, P.box[0])), P.box[0]));
+              ry = __fsub_rn(ry, __fmul_rn(rintf(__fdiv_rn(ry, P.box[1])), P.box[1]));
+              rz = __fsub_rn(rz, __fmul_rn(rintf(__fdiv_rn(rz, P.box[2])), P.box[2]));
+            } else {
+              const float qx = __fadd_rn(fmaf(rx, P.inv_box[0], RINT_MAGIC), -RINT_MAGIC);
+              const float qy = __fadd_rn(fmaf(ry, P.inv_box[1], RINT_MAGIC), -RINT_MAGIC);
+              const float qz = __fadd_rn(fmaf(rz, P.inv_box[2], RINT_MAGIC), -RINT_MAGIC);
+              rx = fmaf(qx, -P.box[0], rx);
+              ry = fmaf(qy, -P.box[1], ry);
+              rz = fmaf(qz, -P.box[2], rz);
+            }
+            const float d2 =
+                __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
+            const bool ok = (d2 < cut2) && (!same || j > irow[r]);
+            bin_one(d2, ok, s_thr, s_cnt, inv_step);
+          }
+        }
+      }
+      __syncthreads();  // everyone is done reading this stage
+      if (tid == 0 && jt + 2 < j_tile1) issue(jt + 2, stage);
+      if (++tiles_since_flush >= P.flush_tiles) {
+        flush_hist<NT>(s_cnt, P.nbins, P.hist + (size_t)cur_pair * P.nbins);
+        tiles_since_flush = 0;
+      }
+    }
+  }
+  if (cur_pair >= 0) flush_hist<NT>(s_cnt, P.nbins, P.hist + (size_t)cur_pair * P.nbins);
+}
+
+// ---------------------------------------------------------------------------------------
+// pack / extent kernels
+// ---------------------------------------------------------------------------------------
+__global__ void rdf_pack_kernel(const float* __restrict__ traj, long long T, long long atom_first,
+                                long long atom_count, const int* __restrict__ frames,
+                                float* __restrict__ out, long long n_pad, long long dst_first,
+                                long long dst_span) {
+  const int k = blockIdx.y;
+  const long long f = frames[k];
+  float* ox = out + (size_t)k * 3 * n_pad + dst_first;
+  const float nanv = __int_as_float(0x7fc00000);
+  for (long long a = blockIdx.x * (long long)blockDim.x + threadIdx.x; a < dst_span;
+       a += (long long)gridDim.x * blockDim.x) {
+    float x = nanv, y = nanv, z = nanv;
+    if (a < atom_count) {
+      const float* src = traj + ((size_t)(atom_first + a) * T + f) * 3;
+      x = __ldg(src);
+      y = __ldg(src + 1);
+      z = __ldg(src + 2);
+    }
+    ox[a] = x;
+    ox[n_pad + a] = y;
+    ox[2 * n_pad + a] = z;
+  }
+}
+
+__device__ __forceinline__ void atomic_min_f(float* addr, float v) {
+  // valid for any sign: compare as ordered ints
+  if (v >= 0.f)
+    atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else
+    atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* addr, float v) {
+  if (v >= 0.f)
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else
+    atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void coord_extent_kernel(const float* __restrict__ pos, long long n_pad,
+                                    long long total, float* __restrict__ minmax) {
+  // pos viewed as [F*3][n_pad]; dim = row % 3
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const float v = __ldg(pos + e);
+    const int d = static_cast<int>((e / n_pad) % 3);
+    if (v == v) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if (q == d) {
+          mn[q] = fminf(mn[q], v);
+          mx[q] = fmaxf(mx[q], v);
+        }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[q] = fminf(mn[q], __shfl_xor_sync(0xffffffffu, mn[q], o));
+      mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (mn[q] != INFINITY) atomic_min_f(minmax + q, mn[q]);
+      if (mx[q] != -INFINITY) atomic_max_f(minmax + 3 + q, mx[q]);
+    }
+  }
+}
+
+template <int NT, int R, bool EXACT, int AM>
+int launch_rdf(const RdfParams& P, size_t smem, int grid, cudaStream_t s) {
+  auto kern = rdf_pair_hist_kernel<NT, R, EXACT, AM>;
+  MDK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, NT, smem, s>>>(P);
+  MDK_LAUNCH_CHECK();
+  return MDK_OK;
+}
+
+template <int NT, int R>
+int launch_rdf_cfg(const RdfParams& P, size_t smem, int grid, cudaStream_t s, bool exact, int am) {
+  if (exact) return launch_rdf<NT, R, true, 0>(P, smem, grid, s);
+  switch (am) {
+    case 0: return launch_rdf<NT, R, false, 0>(P, smem, grid, s);
+    case 1: return launch_rdf<NT, R, false, 1>(P, smem, grid, s);
+    default: return launch_rdf<NT, R, false, 2>(P, smem, grid, s);
+  }
+}
+
+}  // namespace mdk
+
+using namespace mdk;
+
+extern "C" int mdk_rdf_tile(void) { return TJ; }
+
+extern "C" int mdk_rdf_thresholds(float cutoff, int nbins, float* thr, float* cut2_out) {
+  MDK_CHECK_ARG(nbins >= 1 && cutoff > 0.f && thr && cut2_out, "rdf_thresholds: bad argument");
+  // tf.histogram_fixed_width CPU functor: step = double(hi - lo) / double(nbins), lo = 0
+  const volatile double step = static_cast<double>(cutoff) / static_cast<double>(nbins);
+  auto bin_ge = [&](float d, int m) {
+    volatile double q = static_cast<double>(d) / step;
+    return q >= static_cast<double>(m);  // floor(q) >= m
+  };
+  // smallest fp32 x >= 0 with sqrtf_rn(x) >= dmin
+  auto d2_threshold = [&](float dmin) {
+    volatile float x = dmin * dmin;
+    for (;;) {
+      volatile float s = sqrtf(x);
+      if (s >= dmin) break;
+      x = nextafterf(x, INFINITY);
+    }
+    for (;;) {
+      if (x <= 0.f) break;
+      volatile float xm = nextafterf(x, 0.f);
+      volatile float s = sqrtf(xm);
+      if (s >= dmin) x = xm; else break;
+    }
+    return (float)x;
+  };
+  thr[0] = 0.f;
+  for (int m = 1; m < nbins; ++m) {
+    volatile float d = static_cast<float>(static_cast<double>(m) * step);
+    while (!bin_ge(d, m)) d = nextafterf(d, INFINITY);
+    for (;;) {
+      volatile float dm = nextafterf(d, 0.f);
+      if (dm >= 0.f && bin_ge(dm, m)) d = dm; else break;
+    }
+    thr[m] = d2_threshold(d);
+  }
+  thr[nbins] = INFINITY;
+  *cut2_out = d2_threshold(cutoff);
+  return MDK_OK;
+}
+
+extern "C" int mdk_rdf_pack(const float* traj, long long A_total, long long T, long long atom_first,
+                            long long atom_count, const int* frames, int n_frames, float* out,
+                            long long n_pad, long long dst_first, long long dst_span,
+                            mdk_stream_t stream) {
+  MDK_CHECK_ARG(traj && frames && out, "rdf_pack: null pointer");
+  MDK_CHECK_ARG(atom_first >= 0 && atom_count >= 0 && atom_first + atom_count <= A_total,
+                "rdf_pack: atom range [%lld, +%lld) outside %lld", atom_first, atom_count, A_total);
+  MDK_CHECK_ARG(dst_span >= atom_count && dst_first >= 0 && dst_first + dst_span <= n_pad,
+                "rdf_pack: destination range outside n_pad");
+  MDK_CHECK_ARG(n_frames >= 0 && n_frames <= 65535, "rdf_pack: n_frames must be <= 65535 per call");
+  if (n_frames == 0 || dst_span == 0) return MDK_OK;
+  const int threads = 256;
+  long long blocks = (dst_span + threads - 1) / threads;
+  if (blocks > 4096) blocks = 4096;
+  dim3 grid((unsigned)blocks, (unsigned)n_frames);
+  rdf_pack_kernel<<<grid, threads, 0, as_stream(stream)>>>(traj, T, atom_first, atom_count, frames,
+                                                           out, n_pad, dst_first, dst_span);
+  MDK_LAUNCH_CHECK();
+  return MDK_OK;
+}
+
+extern "C" int mdk_coord_extent(const float* pos_soa, int n_frames, long long n_pad, float* minmax,
+                                mdk_stream_t stream) {
+  MDK_CHECK_ARG(pos_soa && minmax && n_frames >= 0 && n_pad >= 0, "coord_extent: bad argument");
+  const long long total = (long long)n_frames * 3 * n_pad;
+  if (total == 0) return MDK_OK;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  coord_extent_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(pos_soa, n_pad, total, minmax);
+  MDK_LAUNCH_CHECK();
+  return MDK_OK;
+}
+
+extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad, const int* sp_lo,
+                            const int* sp_hi, int n_species, const float* box, float cut2,
+                            float cutoff, int nbins, const float* thr, unsigned long long* hist,
+                            unsigned int* work_counter, int flags, mdk_stream_t stream) {
+  MDK_CHECK_ARG(pos_soa && sp_lo && sp_hi && box && thr && hist && work_counter,
+                "rdf_hist: null pointer");
+  MDK_CHECK_ARG(n_species >= 1 && n_species <= MDK_MAX_SPECIES,
+                "rdf_hist: n_species %d outside [1, %d]", n_species, MDK_MAX_SPECIES);
+  MDK_CHECK_ARG(nbins >= 1 && cutoff > 0.f && cut2 > 0.f, "rdf_hist: bad nbins/cutoff");
+  MDK_CHECK_ARG(n_frames >= 0 && n_pad % 4 == 0, "rdf_hist: n_pad must be a multiple of 4");
+  for (int s = 0; s < n_species; ++s) {
+    MDK_CHECK_ARG(sp_lo[s] % TJ == 0 && sp_hi[s] >= sp_lo[s] && sp_hi[s] <= n_pad,
+                  "rdf_hist: species block %d [%d, %d) must start at a multiple of %d inside n_pad",
+                  s, sp_lo[s], sp_hi[s], TJ);
+    const long long padded_end = ((long long)(sp_hi[s] + TJ - 1) / TJ) * TJ;
+    MDK_CHECK_ARG(padded_end <= n_pad && (s + 1 == n_species || padded_end <= sp_lo[s + 1]),
+                  "rdf_hist: species block %d is not padded to a multiple of %d", s, TJ);
+    MDK_CHECK_ARG(box[s % 3] > 0.f, "rdf_hist: box must be positive");
+  }
+  if (n_frames == 0) return MDK_OK;
+  cudaStream_t s = as_stream(stream);
+
+  // tile configuration: small systems use narrow row tiles.  flags bits 8..11 / 12..15
+  // override the (threads, rows-per-thread) configuration / atomic mode (tuning only).
+  int max_len = 0;
+  for (int q = 0; q < n_species; ++q)
+    max_len = max_len > sp_hi[q] - sp_lo[q] ? max_len : sp_hi[q] - sp_lo[q];
+  const bool exact = (flags & MDK_RDF_EXACT_DIV) != 0;
+  int cfg = (flags >> 8) & 0xf;   // 0 = auto, 1: 128x2, 2: 128x4, 3: 256x2, 4: 256x4
+  int am = (flags >> 12) & 0xf;   // 0 = auto, else AM = am - 1
+  if (cfg == 0) cfg = max_len <= 8192 ? 1 : 4;
+  am = am == 0 ? 0 : am - 1;
+  MDK_CHECK_ARG(cfg >= 1 && cfg <= 4 && am >= 0 && am <= 2, "rdf_hist: bad tuning flags");
+  const int NT = (cfg <= 2) ? 128 : 256;
+  const int R = (cfg == 1 || cfg == 3) ? 2 : 4;
+  const int TI = NT * R;
+
+  RdfParams P;
+  memset(&P, 0, sizeof(P));
+  P.pos = pos_soa;
+  P.n_pad = n_pad;
+  P.n_frames = n_frames;
+  P.n_species = n_species;
+  for (int q = 0; q < n_species; ++q) {
+    P.sp_lo[q] = sp_lo[q];
+    P.sp_hi[q] = sp_hi[q];
+  }
+  for (int d = 0; d < 3; ++d) {
+    P.box[d] = box[d];
+    P.inv_box[d] = 1.0f / box[d];
+  }
+  P.cut2 = cut2;
+  P.inv_step = static_cast<float>(static_cast<double>(nbins) / static_cast<double>(cutoff));
+  P.nbins = nbins;
+  P.thr = thr;
+  P.hist = hist;
+  P.counter = reinterpret_cast<unsigned long long*>(work_counter);
+
+  const size_t smem = (size_t)2 * 3 * TJ * sizeof(float) + 2 * sizeof(uint64_t) +
+                      2 * sizeof(unsigned long long) +
+                      (size_t)((nbins + 1 + 3) & ~3) * sizeof(float) +
+                      (size_t)(((nbins + 31) & ~31) + 32) * sizeof(unsigned);
+  if (smem > 227 * 1024) {
+    set_error("rdf_hist: nbins=%d needs %zu bytes of shared memory (> 227 KB)", nbins, smem);
+    return MDK_EUNSUPPORTED;
+  }
+  // resident CTAs per SM (shared-memory bound) -> persistent grid
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  const int max_by_threads = 2048 / NT;
+  if (per_sm > max_by_threads) per_sm = max_by_threads;
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  const int grid = sm_count() * per_sm;
+
+  // work items: choose CJ so that there are >= 8 items per CTA where possible
+  int np = 0;
+  for (int a = 0; a < n_species; ++a)
+    for (int b = a; b < n_species; ++b) {
+      P.pair_a[np] = a;
+      P.pair_b[np] = b;
+      P.row_tiles[np] = (sp_hi[a] - sp_lo[a] + TI - 1) / TI;
+      P.col_tiles[np] = (sp_hi[b] - sp_lo[b] + TJ - 1) / TJ;
+      ++np;
+    }
+  P.n_pairs = np;
+  auto count_items = [&](int CJ) {
+    unsigned long long tot = 0;
+    for (int p = 0; p < np; ++p) {
+      P.chunks_per_row[p] = (P.col_tiles[p] + CJ - 1) / CJ;
+      P.item_start[p] = tot;
+      tot += (unsigned long long)n_frames * P.row_tiles[p] * P.chunks_per_row[p];
+    }
+    P.item_start[np] = tot;
+    return tot;
+  };
+  int CJ = 64;
+  unsigned long long total = count_items(CJ);
+  while (CJ > 1 && total < (unsigned long long)grid * 16) {
+    CJ /= 2;
+    total = count_items(CJ);
+  }
+  P.CJ = CJ;
+  P.total_items = total;
+  // u32 private counters: flush before a bin could overflow (TI * TJ pairs per tile)
+  P.flush_tiles = (unsigned)((1ull << 31) / ((unsigned long long)TI * TJ));
+  P.one = 1u;
+
+  MDK_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s));
+  switch (cfg) {
+    case 1: return launch_rdf_cfg<128, 2>(P, smem, grid, s, exact, am);
+    case 2: return launch_rdf_cfg<128, 4>(P, smem, grid, s, exact, am);
+    case 3: return launch_rdf_cfg<256, 2>(P, smem, grid, s, exact, am);
+    default: return launch_rdf_cfg<256, 4>(P, smem, grid, s, exact, am);
+  }
+}

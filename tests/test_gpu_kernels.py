@@ -1,0 +1,286 @@
+"""Parity of the sm_100a kernels (through the C ABI) against the NumPy oracle.
+
+Bars (BASELINE.json north_star): RDF bin counts bit-exact; MSD / ACF series within 1e-5
+relative; unwrapped positions bit-exact (fp32 store); ionic current within fp32 storage
+rounding of the fp64 sum.
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # north_star tolerance for floating-point series
+
+
+def _nacl(n_atoms, n_frames, box, seed):
+    from lammps_analysis_b200.synthetic import nacl_trajectory
+
+    return nacl_trajectory(n_atoms, n_frames, box, seed)
+
+
+def _oracle_counts(data, species, box, frames, cutoff, nbins, minibatch, n_batches):
+    from oracle import rdf as orc
+
+    pos = {s: data[s]["Positions"] for s in species}
+    return orc.rdf_counts(pos, species, box, np.asarray(frames), cutoff, nbins, minibatch,
+                          n_batches)
+
+
+@pytest.mark.parametrize("n_atoms,n_frames,box", [(216, 6, 20.0), (1000, 4, 32.0)])
+def test_rdf_counts_bit_exact(cuda, n_atoms, n_frames, box):
+    import torch
+    from lammps_analysis_b200.engine import RdfEngine, to_device_f32
+    from oracle import rdf as orc
+
+    data, box_arr = _nacl(n_atoms, n_frames, box, seed=1)
+    species = ["Na", "Cl"]
+    cutoff = orc.default_cutoff(box_arr)
+    nbins = orc.default_number_of_bins(cutoff)
+    frames = np.arange(n_frames)
+    ref = _oracle_counts(data, species, box_arr, frames, cutoff, nbins, 100, n_frames)
+
+    eng = RdfEngine([data[s]["Positions"].shape[0] for s in species], box_arr, cutoff, nbins,
+                    device=cuda)
+    trajs = [to_device_f32(data[s]["Positions"], cuda) for s in species]
+    eng.add_frames(trajs, frames)
+    got = eng.counts()
+    keys = [f"{species[a]}_{species[b]}"
+            for a, b in itertools.combinations_with_replacement(range(2), 2)]
+    for p, key in enumerate(keys):
+        mism = int(np.count_nonzero(got[p] != ref[key]))
+        assert mism == 0, f"{key}: {mism} bins differ"
+        assert got[p].sum() == ref[key].sum()
+    # Q1: pair totals per frame are bounded by (n-1)(n-2)/2 and (n_a-1)(n_b-1)
+    assert got.sum() > 0
+
+
+@pytest.mark.parametrize("tuning", [0x100, 0x200, 0x300, 0x400, 0x1100, 0x2100, 0x3100])
+def test_rdf_kernel_variants_agree(cuda, tuning):
+    """Every tile configuration / atomic mode yields the same integers."""
+    from lammps_analysis_b200.engine import RdfEngine, to_device_f32
+    from oracle import rdf as orc
+
+    data, box_arr = _nacl(1000, 2, 32.0, seed=7)
+    species = ["Na", "Cl"]
+    cutoff = orc.default_cutoff(box_arr)
+    nbins = orc.default_number_of_bins(cutoff)
+    trajs = [to_device_f32(data[s]["Positions"], cuda) for s in species]
+    base = RdfEngine([500, 500], box_arr, cutoff, nbins, device=cuda)
+    base.add_frames(trajs, [0, 1])
+    var = RdfEngine([500, 500], box_arr, cutoff, nbins, device=cuda)
+    var.add_frames(trajs, [0, 1], tuning=tuning)
+    assert np.array_equal(base.counts(), var.counts())
+
+
+def test_rdf_exact_division_mode(cuda):
+    """cutoff >= L/2 forces the true-division minimum image; still bit-exact."""
+    from lammps_analysis_b200.engine import RdfEngine, to_device_f32
+
+    data, box_arr = _nacl(216, 3, 20.0, seed=3)
+    species = ["Na", "Cl"]
+    cutoff, nbins = 12.5, 500
+    ref = _oracle_counts(data, species, box_arr, np.arange(3), cutoff, nbins, 50, 3)
+    eng = RdfEngine([108, 108], box_arr, cutoff, nbins, device=cuda)
+    assert eng.exact_div
+    eng.add_frames([to_device_f32(data[s]["Positions"], cuda) for s in species], np.arange(3))
+    got = eng.counts()
+    for p, key in enumerate(["Na_Na", "Na_Cl", "Cl_Cl"]):
+        assert np.array_equal(got[p], ref[key]), key
+
+
+def test_rdf_single_species_and_empty(cuda):
+    from lammps_analysis_b200.engine import RdfEngine, to_device_f32
+    from oracle import rdf as orc
+
+    rng = np.random.default_rng(5)
+    pos = (rng.random((300, 2, 3)) * 18.0).astype(np.float32)
+    box = np.array([18.0, 18.0, 18.0])
+    cutoff, nbins = 8.9, 890
+    ref = orc.rdf_counts({"1": pos}, ["1"], box, np.arange(2), cutoff, nbins, 64, 2)
+    eng = RdfEngine([300], box, cutoff, nbins, device=cuda)
+    eng.add_frames([to_device_f32(pos, cuda)], np.arange(2))
+    assert np.array_equal(eng.counts()[0], ref["1_1"])
+    # no frames -> all-zero histogram, no launch error
+    eng2 = RdfEngine([300], box, cutoff, nbins, device=cuda)
+    eng2.add_frames([to_device_f32(pos, cuda)], np.arange(0))
+    assert eng2.counts().sum() == 0
+
+
+def _plan(A, T, data_range, ct, memory=60e9, scale=150):
+    from oracle.planner import ArrayDatabase, plan_trajectory_calculator
+
+    class _Shape:
+        def __init__(self, shape):
+            self.shape = shape
+
+    db = ArrayDatabase({"x": _Shape((A, T, 3))})
+    return plan_trajectory_calculator(db, ["x"], data_range, ct,
+                                      {"linear": {"scale_factor": scale}}, memory)
+
+
+@pytest.mark.parametrize("A,T,N,ct,memory", [
+    (64, 400, 50, 1, 60e9),       # one batch
+    (64, 400, 50, 3, 60e9),       # correlation_time > 1
+    (60, 1000, 100, 1, 2.0e5 * 60 / 64),  # several batches + remainder
+])
+def test_msd_matches_oracle(cuda, A, T, N, ct, memory):
+    from lammps_analysis_b200.engine import msd_series, plan_windows, to_device_f32
+    from oracle import dynamics as od
+
+    rng = np.random.default_rng(11)
+    x = np.cumsum(rng.normal(0, 0.1, size=(A, T, 3)), axis=1).astype(np.float32)
+    plan = _plan(A, T, N, ct, memory)
+    tau = np.arange(N)
+    ref, ref_count = od.einstein_msd(x, plan, N, ct, tau)
+    launches = plan_windows(plan, N, ct, A)
+    got, count = msd_series(to_device_f32(x, cuda), launches, N, ct, tau)
+    assert count == ref_count
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=RTOL, atol=0)
+
+
+def test_msd_sparse_tau(cuda):
+    from lammps_analysis_b200.engine import msd_series, plan_windows, to_device_f32
+    from oracle import dynamics as od
+
+    rng = np.random.default_rng(12)
+    A, T, N = 32, 300, 80
+    x = np.cumsum(rng.normal(0, 0.1, size=(A, T, 3)), axis=1).astype(np.float32)
+    plan = _plan(A, T, N, 1)
+    tau = np.linspace(0, N - 1, 17, dtype=int)
+    ref, ref_count = od.einstein_msd(x, plan, N, 1, tau)
+    got, count = msd_series(to_device_f32(x, cuda), plan_windows(plan, N, 1, A), N, 1, tau)
+    assert count == ref_count
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=RTOL, atol=0)
+
+
+@pytest.mark.parametrize("A,T,N,ct", [(48, 300, 40, 1), (48, 300, 40, 4), (20, 700, 130, 1)])
+def test_acf_matches_oracle(cuda, A, T, N, ct):
+    from lammps_analysis_b200.engine import acf_series, plan_windows, to_device_f32
+    from oracle import dynamics as od
+
+    rng = np.random.default_rng(13)
+    v = rng.normal(0, 1.0, size=(A, T, 3))
+    for t in range(1, T):
+        v[:, t] = 0.9 * v[:, t - 1] + 0.4 * v[:, t]
+    v = v.astype(np.float32)
+    plan = _plan(A, T, N, ct)
+    time = np.arange(N) * 0.002
+    ref_sum, ref_count, ref_sig = od.gk_diffusion_acf(v, plan, N, ct, time, 1.0, 1.0)
+    launches = plan_windows(plan, N, ct, A)
+    got, count, wins, sizes = acf_series(to_device_f32(v, cuda), launches, N, ct)
+    assert count == ref_count
+    scale = np.abs(ref_sum).max()
+    np.testing.assert_allclose(got.cpu().numpy(), ref_sum, rtol=RTOL, atol=RTOL * 1e-2 * scale)
+    # per-window series -> sigmas (cumulative trapezoid of the atom-mean ACF)
+    from scipy.integrate import cumulative_trapezoid
+
+    win = np.concatenate([w.cpu().numpy() for w in wins], axis=0)
+    sig = cumulative_trapezoid(win / sizes[0], x=time, axis=1)
+    assert sig.shape == ref_sig.shape
+    np.testing.assert_allclose(sig, ref_sig, rtol=RTOL, atol=RTOL * np.abs(ref_sig).max())
+
+
+def test_unwrap_bit_exact_with_carry(cuda):
+    import torch
+    from lammps_analysis_b200 import kernels as K
+    from lammps_analysis_b200.engine import to_device_f32
+    from oracle import transformations as ot
+
+    rng = np.random.default_rng(21)
+    A, T = 70, 333
+    box = np.array([10.0, 11.5, 9.25])
+    walk = np.cumsum(rng.normal(0, 1.5, size=(A, T, 3)), axis=1) + rng.random((A, 1, 3)) * box
+    pos = np.mod(walk, box).astype(np.float32)
+    ref = ot.run_unwrap(pos, box, batch_size=100)  # 3 batches + remainder, carry-over
+    dev = to_device_f32(pos, cuda)
+    out = torch.empty_like(dev)
+    carry_pos = torch.zeros(A, 3, dtype=torch.float32, device=cuda)
+    carry_img = torch.zeros(A, 3, dtype=torch.float64, device=cuda)
+    have = False
+    for lo in range(0, T, 100):
+        hi = min(T, lo + 100)
+        chunk = dev[:, lo:hi].contiguous()
+        o = torch.empty_like(chunk)
+        K.unwrap(chunk, box, carry_pos, carry_img, have, o)
+        out[:, lo:hi] = o
+        have = True
+    got = out.cpu().numpy()
+    assert np.array_equal(got, ref)
+    # one batch over the whole series gives the same answer
+    out2 = torch.empty_like(dev)
+    carry_img.zero_()
+    K.unwrap(dev, box, carry_pos, carry_img, False, out2)
+    assert np.array_equal(out2.cpu().numpy(), ref)
+
+
+def test_unwrap_reference_known_answer(cuda):
+    """CI/unit_tests/transformations/test_transformations.py:147-189 (unwrap with carry)."""
+    import json
+    import os
+    import torch
+    from lammps_analysis_b200 import kernels as K
+    from lammps_analysis_b200.engine import to_device_f32
+
+    path = os.path.join(os.path.dirname(__file__), "golden", "unwrap_carry.json")
+    g = json.load(open(path))
+    pos = np.asarray(g["pos"], dtype=np.float32)
+    box = np.asarray(g["box"], dtype=np.float64)
+    dev = to_device_f32(pos, cuda)
+    out = torch.empty_like(dev)
+    carry_pos = to_device_f32(np.asarray(g["last_pos"], dtype=np.float32), cuda)
+    carry_img = torch.as_tensor(np.asarray(g["last_image_box"], dtype=np.float64), device=cuda)
+    K.unwrap(dev, box, carry_pos, carry_img, True, out)
+    np.testing.assert_allclose(out.cpu().numpy(), np.asarray(g["expected"]), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(carry_img.cpu().numpy(), np.asarray(g["expected_image_box"]))
+
+
+def test_unwrap_indices(cuda):
+    import torch
+    from lammps_analysis_b200 import kernels as K
+    from lammps_analysis_b200.engine import to_device_f32
+    from oracle import transformations as ot
+
+    rng = np.random.default_rng(22)
+    pos = (rng.random((40, 50, 3)) * 7.3).astype(np.float32)
+    img = rng.integers(-3, 4, size=(40, 50, 3)).astype(np.float32)
+    box = np.array([7.3, 7.3, 8.1])
+    ref = ot.unwrap_via_indices_transform_batch(pos, img, box).astype(np.float32)
+    out = torch.empty(40, 50, 3, dtype=torch.float32, device=cuda)
+    K.unwrap_indices(to_device_f32(pos, cuda), to_device_f32(img, cuda), box, out)
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("mode", ["scalar", "per_atom", "per_atom_frame"])
+def test_ionic_current(cuda, mode):
+    import torch
+    from lammps_analysis_b200 import kernels as K
+    from lammps_analysis_b200.engine import to_device_f32
+    from oracle import transformations as ot
+
+    rng = np.random.default_rng(23)
+    A, T = 123, 257
+    v_na = rng.normal(size=(A, T, 3)).astype(np.float32)
+    v_cl = rng.normal(size=(A + 7, T, 3)).astype(np.float32)
+    if mode == "scalar":
+        q_na, q_cl = 1.0, -1.0
+        d_na, d_cl = q_na, q_cl
+    elif mode == "per_atom":
+        q_na = rng.normal(size=(A, 1, 1)).astype(np.float32)
+        q_cl = rng.normal(size=(A + 7, 1, 1)).astype(np.float32)
+        d_na, d_cl = to_device_f32(q_na.ravel(), cuda), to_device_f32(q_cl.ravel(), cuda)
+    else:
+        q_na = rng.normal(size=(A, T, 1)).astype(np.float32)
+        q_cl = rng.normal(size=(A + 7, T, 1)).astype(np.float32)
+        d_na, d_cl = to_device_f32(q_na[..., 0], cuda), to_device_f32(q_cl[..., 0], cuda)
+    ref = ot.ionic_current_transform_batch({
+        "Na": {"Velocities": v_na, "Charge": np.asarray(q_na, dtype=np.float64).reshape(
+            (1, 1, 1) if mode == "scalar" else q_na.shape)},
+        "Cl": {"Velocities": v_cl, "Charge": np.asarray(q_cl, dtype=np.float64).reshape(
+            (1, 1, 1) if mode == "scalar" else q_cl.shape)},
+    })
+    J = torch.zeros(T, 3, dtype=torch.float64, device=cuda)
+    K.ionic_current(to_device_f32(v_na, cuda), d_na, J)
+    K.ionic_current(to_device_f32(v_cl, cuda), d_cl, J)
+    np.testing.assert_allclose(J.cpu().numpy(), ref, rtol=1e-12, atol=1e-11)

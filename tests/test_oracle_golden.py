@@ -1,0 +1,158 @@
+"""Pins the oracle (oracle/) against the known answers the reference's own unit tests hold
+for the hot path: unwrap with carry-over, unwrap via indices, ionic current,
+memory-manager planning arithmetic, fit_einstein_curve.  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import dynamics as od
+from oracle import planner as op
+from oracle import transformations as ot
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+    with open(os.path.join(GOLDEN, name)) as fh:
+        return json.load(fh)
+
+
+def test_unwrap_with_carry_known_answer():
+    g = _load("unwrap_carry.json")
+    out, carry = ot.unwrap_transform_batch(
+        np.asarray(g["pos"]), np.asarray(g["box"]),
+        {"last_pos": np.asarray(g["last_pos"]), "last_image_box": np.asarray(g["last_image_box"])},
+    )
+    np.testing.assert_allclose(out, np.asarray(g["expected"]), atol=1e-12)
+    np.testing.assert_allclose(carry["last_pos"], g["expected_last_pos"])
+    np.testing.assert_allclose(carry["last_image_box"], g["expected_image_box"])
+
+
+def test_unwrap_via_indices_known_answer():
+    # CI/unit_tests/transformations/test_transformations.py:192-213
+    rng = np.random.default_rng(0)
+    pos = rng.random((5, 7, 3))
+    box_im = rng.integers(-10, 10, size=(5, 7, 3)).astype(float)
+    box_l = np.array([1.1, 2.2, 3.3])
+    np.testing.assert_allclose(
+        ot.unwrap_via_indices_transform_batch(pos, box_im, box_l), pos + box_im * box_l
+    )
+
+
+def test_ionic_current_known_answer():
+    # CI/unit_tests/transformations/test_transformations.py:59-79
+    rng = np.random.default_rng(1)
+    batch, should = {}, np.zeros((7, 3))
+    for sp in ["Na", "Cl"]:
+        vel = rng.random((5, 7, 3))
+        charge = np.array([[[rng.random()]]])
+        batch[sp] = {"Velocities": vel, "Charge": charge}
+        should += np.sum(vel * charge, axis=0)
+    np.testing.assert_allclose(ot.ionic_current_transform_batch(batch), should)
+
+
+class _FakeDB:
+    # CI/unit_tests/memory_manager/test_memory_manager.py:28-46
+    def __init__(self, data_size=500, rows=10, columns=10):
+        self.data_size, self.rows, self.columns = data_size, rows, columns
+
+    def get_data_size(self, item):
+        return self.rows, self.columns, self.data_size
+
+
+def test_planner_known_answers():
+    g = _load("planner_cases.json")
+    for case in g["get_batch_size"]:
+        mm = op.MemoryManager(
+            data_path=["Test/Path"],
+            database=_FakeDB(case["data_size"], case["rows"], case["columns"]),
+            memory_fraction=case["fraction"], memory=case["memory"],
+        )
+        assert list(mm.get_batch_size()) == case["expect"]
+    mm = op.MemoryManager()
+    with pytest.raises(ValueError):
+        mm.get_batch_size()
+    c = g["atomwise_minibatch"]
+    mm = op.MemoryManager(data_path=["Test/Path"],
+                          database=_FakeDB(c["data_size"], c["rows"], c["columns"]),
+                          memory_fraction=c["fraction"], memory=c["memory"])
+    mm._compute_atomwise_minibatch(c["data_range"])
+    assert mm.batch_size == c["expect"]["batch_size"]
+    assert mm.n_batches == c["expect"]["n_batches"]
+    assert mm.n_atom_batches == c["expect"]["n_atom_batches"]
+    assert mm.atom_remainder == c["expect"]["atom_remainder"]
+    for case in g["get_ensemble_loop"]:
+        mm = op.MemoryManager(data_path=["Test/Path"], database=_FakeDB(), memory=60e9)
+        mm.batch_size = case["batch_size"]
+        loops, minibatch = mm.get_ensemble_loop(case["data_range"], case["correlation_time"])
+        assert [loops, minibatch] == case["expect"]
+    for case in g["scale_functions"]:
+        fn, par = op.MemoryManager._select_scale_function(case["fn"])
+        assert fn(case["x"], **par) == case["expect"]
+    fn, par = op.MemoryManager._select_scale_function({"linear": {"scale_factor": 2}})
+    assert fn(10, **par) == 20
+    fn, par = op.MemoryManager._select_scale_function({"log-linear": {"scale_factor": 2}})
+    assert fn(10, **par) == 20 * np.log(10)
+
+
+def test_fit_einstein_curve_known_answers():
+    # CI/unit_tests/utils/test_calculator_helper_methods.py:42-69 (coarser grid: 200 points
+    # keeps the ~200 curve_fit calls inside the CPU-suite time budget)
+    x = np.linspace(0, 1000, 200)
+    popt, _, _, _ = od.fit_einstein_curve(x, 5 * x + 3, fit_max_index=199)
+    assert popt[0] == pytest.approx(5.0, 0.01)
+    y = np.exp(-0.05 * x) * x**2 + 5 * x + 3
+    popt, _, _, _ = od.fit_einstein_curve(x, y, fit_max_index=199)
+    assert popt[0] == pytest.approx(5.0, 0.01)
+
+
+def test_tfp_autocorrelation_is_unbiased_direct_sum():
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=(3, 37, 3))
+    acf = od.tfp_auto_correlation(x)
+    N = x.shape[1]
+    direct = np.stack(
+        [(x[:, : N - m] * x[:, m:]).sum(axis=1) / (N - m) for m in range(N)], axis=1
+    )
+    np.testing.assert_allclose(acf, direct, rtol=1e-10, atol=1e-12)
+
+
+def test_random_walk_diffusion_coefficient():
+    # CI/integration_tests/calculators/test_einstein_diffusion_coefficients.py:52-99 scaled
+    # down (100 atoms x 2000 steps): D from the MSD slope within the reference's rtol=0.2
+    rng = np.random.default_rng(3)
+    D, dt = 1.2345, 0.1
+    A, T, N = 100, 2000, 200
+    x = np.cumsum(rng.normal(0, np.sqrt(2 * D * dt), size=(A, T, 3)), axis=1).astype(np.float32)
+    plan = dict(batch_size=T, n_batches=1, remainder=0, minibatch=False)
+    tau = np.arange(N)
+    msd_sum, count = od.einstein_msd(x, plan, N, 1, tau)
+    assert count == (T - N) * (A + 1)
+    res = od.einstein_finish(msd_sum, count, tau * dt, 1.0, 1.0, N - 1)
+    assert res["diffusion_coefficient"] == pytest.approx(D, rel=0.2)
+    np.testing.assert_allclose(res["msd"], 6 * D * tau * dt, rtol=0.9, atol=1e-9)
+
+
+def test_rdf_counts_independent_of_batch_plan():
+    from oracle import rdf as orc
+
+    rng = np.random.default_rng(4)
+    box = np.array([12.0, 12.0, 12.0])
+    pos = {"Na": (rng.random((30, 3, 3)) * 12).astype(np.float32),
+           "Cl": (rng.random((26, 3, 3)) * 12).astype(np.float32)}
+    cutoff = orc.default_cutoff(box)
+    nbins = orc.default_number_of_bins(cutoff)
+    a = orc.rdf_counts(pos, ["Na", "Cl"], box, np.arange(3), cutoff, nbins, 7, 3)
+    b = orc.rdf_counts(pos, ["Na", "Cl"], box, np.arange(3), cutoff, nbins, 56, 1)
+    allpos = np.concatenate([pos["Na"], pos["Cl"]], axis=0)
+    c = orc.rdf_counts_direct(allpos, [0, 30], [30, 26], box, cutoff, nbins)
+    for p, key in enumerate(["Na_Na", "Na_Cl", "Cl_Cl"]):
+        assert np.array_equal(a[key], b[key])
+    assert np.array_equal(a["Na_Na"], c[(0, 0)])
+    assert np.array_equal(a["Na_Cl"], c[(0, 1)])
+    assert np.array_equal(a["Cl_Cl"], c[(1, 1)])
+    # Q1: the first atom of every species is dropped
+    assert a["Na_Na"].sum() <= 3 * 29 * 28 // 2
+    assert a["Na_Cl"].sum() <= 3 * 29 * 25

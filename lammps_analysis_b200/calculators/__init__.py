@@ -1,0 +1,14 @@
+"""Hot-path calculators behind the MDSuite names (mdsuite/calculators/__init__.py:29-87)."""
+from .coordination_number_calculation import CoordinationNumbers
+from .einstein_diffusion_coefficients import EinsteinDiffusionCoefficients
+from .green_kubo_ionic_conductivity import GreenKuboIonicConductivity
+from .green_kubo_self_diffusion_coefficients import GreenKuboDiffusionCoefficients
+from .radial_distribution_function import RadialDistributionFunction
+
+__all__ = [
+    "RadialDistributionFunction",
+    "CoordinationNumbers",
+    "EinsteinDiffusionCoefficients",
+    "GreenKuboDiffusionCoefficients",
+    "GreenKuboIonicConductivity",
+]

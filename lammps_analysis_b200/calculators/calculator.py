@@ -1,0 +1,158 @@
+"""Calculator shell: the ``@call`` cache/run/store protocol and the trajectory-calculator base
+(dependency resolution, tau handling, batch plan).
+
+Mirrors mdsuite/calculators/calculator.py:52-317 and
+mdsuite/calculators/trajectory_calculator.py:117-297.  Plotting is dropped (``plot=`` is
+accepted and ignored: bokeh / matplotlib are outside the hot path).
+"""
+from __future__ import annotations
+
+import functools
+import logging
+from collections import OrderedDict
+from typing import List
+
+import numpy as np
+
+from ..planner import BatchPlan, plan_batches
+from ..project import Computation, args_to_parameters, subjects_key
+from ..store import join_path
+
+log = logging.getLogger("mdsuite_b200")
+
+
+def call(func):
+    """Decorator of ``Calculator.__call__`` (calculator.py:52-148): per experiment, fill
+    ``self.args``; return the stored computation when one with identical args and experiment
+    version exists; otherwise run, store, re-apply the user args and return the stored
+    object.  Project-level calls return ``{experiment_name: Computation}``."""
+
+    @functools.wraps(func)
+    def inner(self, *args, **kwargs):
+        return_dict = self.experiment is None
+        out = {}
+        for experiment in self.experiments:
+            cls = self.__class__(experiment=experiment)
+            func(cls, *args, **kwargs)
+            data = cls.get_computation_data()
+            if data is None:
+                cls.prepare_db_entry()
+                cls.save_computation_args()
+                cls.run_analysis()
+                cls.save_db_data()
+                func(cls, *args, **kwargs)
+                data = cls.get_computation_data()
+            out[experiment.name] = data
+        return out if return_dict else out[self.experiment.name]
+
+    return inner
+
+
+class Calculator:
+    analysis_name = "Calculator"
+    result_keys: list = None
+    result_series_keys: list = None
+
+    def __init__(self, experiment=None, experiments=None, **kwargs):
+        self.experiment = experiment
+        if experiments is None:
+            experiments = [experiment]
+        self.experiments = experiments
+        self.args = None
+        self.plot = False
+        self._queued_data: List = []
+        self._saved_parameters = None
+
+    # -- cache protocol (database/calculator_database.py:91-248) ---------------------------------
+    def _parameters(self) -> dict:
+        return args_to_parameters(self.args, self.experiment.version)
+
+    def get_computation_data(self) -> Computation:
+        return self.experiment.project.find_computation(self.analysis_name, self.experiment.name,
+                                                        self._parameters())
+
+    def prepare_db_entry(self):
+        self._queued_data = []
+
+    def save_computation_args(self):
+        # stored *before* the run, i.e. with the user's -1 / None defaults unresolved
+        self._saved_parameters = self._parameters()
+
+    def queue_data(self, data: dict, subjects: list):
+        self._queued_data.append((subjects_key(list(subjects)), data))
+
+    def save_db_data(self):
+        results = OrderedDict(self._queued_data)
+        self.experiment.project.store_computation(self.analysis_name, self.experiment.name,
+                                                  self._saved_parameters, results)
+
+    def run_analysis(self):
+        """calculator.py:310-317."""
+        self.run_calculator()
+
+    def run_calculator(self):
+        raise NotImplementedError
+
+
+class TrajectoryCalculator(Calculator):
+    """trajectory_calculator.py:52-406 without the tf.data plumbing."""
+
+    loaded_property: str = None       # dataset name, e.g. "Unwrapped_Positions"
+    system_property: bool = False
+    scale_function: dict = None
+    dependency: str = None
+
+    def __init__(self, experiment=None, experiments=None, **kwargs):
+        super().__init__(experiment=experiment, experiments=experiments, **kwargs)
+        self.data_resolution = None
+        self.plan: BatchPlan = None
+
+    # -- dependencies (:117-194) ---------------------------------------------------------------------
+    def _run_dependency_check(self):
+        store = self.experiment.store
+        if self.system_property:
+            path = join_path("Observables", self.loaded_property)
+            if not store.check_existence(path):
+                self._resolve_dependencies(self.loaded_property)
+            return
+        for sp in self.args.species:
+            if not store.check_existence(join_path(sp, self.loaded_property)):
+                self._resolve_dependencies(self.loaded_property)
+                break
+
+    def _resolve_dependencies(self, dependency: str):
+        run = self.experiment.run
+        if dependency == "Unwrapped_Positions":
+            # _unwrap_choice (:181-194): box images available -> indices, else box hopping
+            first = next(iter(self.experiment.species))
+            if self.experiment.store.check_existence(join_path(first, "Box_Images")):
+                run.UnwrapViaIndices()
+            else:
+                run.CoordinateUnwrapper()
+        elif dependency == "Ionic_Current":
+            run.IonicCurrent()
+        else:
+            raise KeyError("Data not in database and cannot be generated.")  # :171-174
+
+    # -- tau values (:196-228) ----------------------------------------------------------------------------
+    def _handle_tau_values(self) -> np.ndarray:
+        tau = self.args.tau_values
+        if isinstance(tau, (int, np.integer)):
+            self.data_resolution = int(tau)
+            self.args.tau_values = np.linspace(0, self.args.data_range - 1, int(tau), dtype=int)
+        if isinstance(self.args.tau_values, (list, np.ndarray)):
+            self.data_resolution = len(self.args.tau_values)
+            self.args.data_range = int(self.args.tau_values[-1] + 1)
+        if isinstance(self.args.tau_values, slice):
+            self.args.tau_values = np.linspace(0, self.args.data_range - 1, self.args.data_range,
+                                               dtype=int)[self.args.tau_values]
+            self.data_resolution = len(self.args.tau_values)
+        return (np.asarray(self.args.tau_values) * self.experiment.time_step
+                * self.experiment.sample_rate)
+
+    # -- batch plan (:243-297) ------------------------------------------------------------------------------
+    def _prepare_managers(self, data_path: list, correct: bool = False) -> BatchPlan:
+        sizes = [self.experiment.store.get_data_size(p) for p in data_path]
+        self.plan = plan_batches(sizes, self.args.data_range, self.args.correlation_time,
+                                 self.scale_function)
+        return self.plan

@@ -1,0 +1,163 @@
+"""RadialDistributionFunction: partial g(r) for every species pair.
+
+Mirrors mdsuite/calculators/radial_distribution_function.py (Args :58-71, __call__ :138-213,
+check_input :215-250, _initialize_rdf_parameters :252-279, prefactor :299-345, g(r) :347-382,
+ideal_correction :719-826, run_calculator :828-887).  The pair pass itself -- the reference's
+frame batches x atom minibatches x masked species-pair histograms -- is one fused kernel
+launch per HBM-sized frame batch (engine.RdfEngine -> mdk_rdf_hist); the reference plan only
+partitions an integer sum, so the counts do not depend on it.  Frames shard across ranks.
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass
+from typing import Union
+
+import numpy as np
+
+from .. import distributed as D
+from ..engine import RdfEngine
+from ..store import join_path
+from .calculator import TrajectoryCalculator, call
+
+
+@dataclass
+class Args:
+    number_of_bins: int
+    number_of_configurations: int
+    correlation_time: int
+    atom_selection: object
+    data_range: int
+    cutoff: float
+    start: int
+    stop: int
+    species: list
+    molecules: bool
+
+
+class RadialDistributionFunction(TrajectoryCalculator):
+    analysis_name = "Radial_Distribution_Function"
+    loaded_property = "Positions"
+    result_series_keys = ["x", "y"]
+    scale_function = {"quadratic": {"outer_scale_factor": 10, "inner_scale_factor": 5}}
+
+    @call
+    def __call__(self, plot: bool = True, number_of_bins: int = None, cutoff: float = None,
+                 save: bool = True, start: int = 0, stop: int = None,
+                 number_of_configurations: int = 500,
+                 atom_selection: Union[slice, dict] = np.s_[:], minibatch: int = -1,
+                 species: list = None, molecules: bool = False, **kwargs):
+        self.args = Args(number_of_bins=number_of_bins, cutoff=cutoff, start=start, stop=stop,
+                         atom_selection=atom_selection, data_range=1, correlation_time=1,
+                         molecules=molecules, species=species,
+                         number_of_configurations=number_of_configurations)
+        self.rdf_minibatch = minibatch  # accepted for API parity; the fused pass has no minibatch
+        self.plot = plot
+        self.use_tf_function = kwargs.pop("use_tf_function", False)
+        self.override_n_batches = kwargs.get("batches")
+        self.tqdm_limit = kwargs.pop("tqdm", 10)
+        self.parity_mode = kwargs.pop("parity_mode", True)   # Q1: drop first atom per species
+        self.tie_report = None
+
+    # -- :215-279 ----------------------------------------------------------------------------------
+    def check_input(self):
+        exp = self.experiment
+        if self.args.molecules:
+            raise NotImplementedError("molecule RDFs need the molecule-mapping subsystem "
+                                      "(out of the hot-path scope)")
+        if self.args.stop is None:
+            self.args.stop = exp.number_of_configurations - 1
+        if self.args.cutoff is None:
+            self.args.cutoff = exp.box_array[0] / 2 - 0.1
+        if self.args.number_of_configurations == -1:
+            self.args.number_of_configurations = exp.number_of_configurations - 1
+        if self.rdf_minibatch == -1:
+            self.rdf_minibatch = self.args.number_of_configurations
+        if self.args.number_of_bins is None:
+            self.args.number_of_bins = int(self.args.cutoff / 0.01)
+        if self.args.species is None:
+            self.args.species = list(exp.species)
+        self.bin_range = [0, self.args.cutoff]
+        self.index_list = list(range(len(self.args.species)))
+        self.sample_configurations = np.linspace(self.args.start, self.args.stop,
+                                                 self.args.number_of_configurations, dtype=int)
+        self.key_list = [f"{self.args.species[a]}_{self.args.species[b]}" for a, b in
+                         itertools.combinations_with_replacement(self.index_list, r=2)]
+        if len(np.unique(self.sample_configurations)) != len(self.sample_configurations):
+            # the reference's h5py fancy index rejects duplicate frame indices
+            raise ValueError("number_of_configurations exceeds the frames in [start, stop]: "
+                             "duplicate sample indices")
+
+    @property
+    def particles_list(self):
+        if isinstance(self.args.atom_selection, dict):
+            return [len(self.args.atom_selection[s]) for s in self.args.species]
+        return [self.experiment.species[s].n_particles for s in self.args.species]
+
+    # -- hot path --------------------------------------------------------------------------------------
+    def compute_counts(self) -> np.ndarray:
+        """int64 [n_pairs][nbins] histogram over the sampled frames (all ranks return the
+        reduced result)."""
+        exp = self.experiment
+        store = exp.store
+        sel = self.args.atom_selection
+        trajs = []
+        for s in self.args.species:
+            path = join_path(s, self.loaded_property)
+            if isinstance(sel, dict):
+                trajs.append(store.device(path, row_index=np.asarray(sel[s])))
+            else:
+                trajs.append(store.device(path))
+        self.engine = RdfEngine(self.particles_list, exp.box_array, self.args.cutoff,
+                                self.args.number_of_bins, drop_first=self.parity_mode)
+        frames = D.shard_frames(self.sample_configurations)
+        if len(frames):
+            self.engine.add_frames(trajs, frames)
+        D.all_reduce_sum_([self.engine.hist])
+        return self.engine.counts()
+
+    # -- :299-382, 719-826 -------------------------------------------------------------------------------
+    @property
+    def ideal_correction(self) -> np.ndarray:
+        cutoff, nbins = self.args.cutoff, self.args.number_of_bins
+        r = np.linspace(0.0, cutoff, nbins)
+        box0 = self.experiment.box_array[0]
+        lower, middle = box0 / 2, np.sqrt(2) * box0 / 2
+        shell = np.empty_like(r)
+        m1 = r <= lower
+        m2 = (~m1) & (r < middle)
+        m3 = ~(m1 | m2)
+        shell[m1] = 4 * np.pi * r[m1] ** 2
+        d = r[m2]
+        shell[m2] = 2 * np.pi * d * (3 - 4 * d)
+        d = r[m3]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            a1 = np.arctan(np.sqrt(4 * d**2 - 2))
+            a2 = 8 * d * np.arctan((2 * d * (4 * d**2 - 3))
+                                   / (np.sqrt(4 * d**2 - 2) * (4 * d**2 + 1)))
+            shell[m3] = 2 * d * (3 * np.pi - 12 * a1 + a2)
+        return shell * (cutoff / nbins)
+
+    def _calculate_prefactor(self, species: str) -> np.ndarray:
+        a, b = species.split("_")
+        scale = 2 if a == b else 1
+        if isinstance(self.args.atom_selection, dict):
+            n0, n1 = len(self.args.atom_selection[a]), len(self.args.atom_selection[b])
+        else:
+            n0 = self.experiment.species[a].n_particles
+            n1 = self.experiment.species[b].n_particles
+        rho = n1 / self.experiment.volume
+        with np.errstate(divide="ignore"):
+            return scale / (self.args.number_of_configurations * rho * self.ideal_correction * n0)
+
+    def run_calculator(self):
+        self.check_input()
+        counts = self.compute_counts()
+        x = (self.experiment.units.length / 1e-9) * np.linspace(0.0, self.args.cutoff,
+                                                                self.args.number_of_bins)
+        self.counts = {}
+        for p, names in enumerate(self.key_list):
+            self.counts[names] = counts[p]
+            with np.errstate(invalid="ignore"):
+                y = counts[p].astype(float) * self._calculate_prefactor(names)
+            self.queue_data(data={"x": x.tolist(), "y": y.tolist()}, subjects=names.split("_"))

@@ -140,26 +140,37 @@ def plan_windows(plan: dict, data_range: int, correlation_time: int, n_atoms: in
     return out
 
 
+def _local_rows(a_lo, a_hi, a_shard, row_offset, n_rows):
+    lo, hi = a_lo, a_hi
+    if a_shard is not None:
+        lo, hi = max(lo, a_shard[0]), min(hi, a_shard[1])
+    lo, hi = lo - row_offset, hi - row_offset
+    if hi > lo and (lo < 0 or hi > n_rows):
+        raise MdkError("atom range outside the rows resident on this device")
+    return lo, hi
+
+
 def msd_series(traj: torch.Tensor, launches, data_range: int, correlation_time: int,
-               tau_values, a_shard=None):
-    """Returns (msd_sum device float64 [n_tau], count).  ``a_shard`` = (lo, hi) restricts the
-    atoms this rank processes (multi-GPU atom sharding); count is always the full-plan
-    count, computed analytically (einstein_diffusion_coefficients.py:184, :244)."""
+               tau_values, a_shard=None, row_offset: int = 0):
+    """Returns (msd_sum device float64 [n_tau], count).
+
+    ``launches`` are in global atom indices; ``traj`` holds the global rows
+    [row_offset, row_offset + traj.shape[0]); ``a_shard`` = (lo, hi) restricts the atoms this
+    rank processes (multi-GPU atom sharding).  count is always the full-plan count, computed
+    analytically (einstein_diffusion_coefficients.py:184, :244)."""
     tau = torch.as_tensor(np.asarray(tau_values, dtype=np.int32), device=traj.device)
     out = torch.zeros(len(tau_values), dtype=torch.float64, device=traj.device)
     count = 0
     for a_lo, a_hi, t0, B, W in launches:
         count += W * ((a_hi - a_lo) + 1)
-        lo, hi = a_lo, a_hi
-        if a_shard is not None:
-            lo, hi = max(lo, a_shard[0]), min(hi, a_shard[1])
+        lo, hi = _local_rows(a_lo, a_hi, a_shard, row_offset, traj.shape[0])
         if hi > lo:
             K.msd_windowed(traj, lo, hi, t0, W, correlation_time, tau, data_range, out)
     return out, count
 
 
 def acf_series(traj: torch.Tensor, launches, data_range: int, correlation_time: int,
-               per_window: bool = True, a_shard=None):
+               per_window: bool = True, a_shard=None, row_offset: int = 0):
     """Returns (acf_sum device [N], count, [acf_win device [W][N] per launch], [A_sel]).
 
     count follows green_kubo_self_diffusion_coefficients.py:196, :334 (A + 1 per window).
@@ -171,9 +182,7 @@ def acf_series(traj: torch.Tensor, launches, data_range: int, correlation_time: 
     scratch = None
     for a_lo, a_hi, t0, B, W in launches:
         count += W * ((a_hi - a_lo) + 1)
-        lo, hi = a_lo, a_hi
-        if a_shard is not None:
-            lo, hi = max(lo, a_shard[0]), min(hi, a_shard[1])
+        lo, hi = _local_rows(a_lo, a_hi, a_shard, row_offset, traj.shape[0])
         win = torch.zeros(W, N, dtype=torch.float64, device=traj.device) if per_window else None
         if hi > lo:
             scratch = K.acf_windowed(traj, lo, hi, t0, B, N, W, correlation_time, out, win,

@@ -1,0 +1,199 @@
+"""Trajectory store: per-species arrays keyed ``"{species}/{Property}"`` with shape
+``(n_atoms, n_frames, n_dims)`` float32 -- the MDSuite simulation database layout
+(mdsuite/database/simulation_database.py:333-690: atom-major, time contiguous per atom,
+float32 on disk).  h5py is not available in this environment, so datasets are ``.npy`` files
+(memory-mapped on load) under ``<experiment>/database/``; the *interface* the hot path needs is
+kept: ``add_dataset / add_data / check_existence / get_data_size / load_data``.
+
+HBM residency: ``device(path, ...)`` returns a CUDA tensor of (a row range of) a dataset and
+keeps it cached, so that consecutive calculators do not re-upload; uploads go through pinned
+host staging in bounded chunks.
+"""
+from __future__ import annotations
+
+import json
+import os
+from collections import OrderedDict
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from .config import config
+
+
+def join_path(*args) -> str:
+    """meta_functions.join_path (:73-93): database paths always use '/'."""
+    return "/".join(args)
+
+
+class TrajectoryStore:
+    def __init__(self, directory: Optional[str] = None):
+        self.directory = directory
+        self._arrays: Dict[str, np.ndarray] = {}
+        self._device_cache: "OrderedDict[Tuple, object]" = OrderedDict()
+        self._device_bytes = 0
+        self.h2d_bytes = 0  # bytes uploaded so far (bench.py reads this)
+        if directory is not None:
+            os.makedirs(directory, exist_ok=True)
+            self._load_index()
+
+    # ---- persistence -------------------------------------------------------------------
+    def _index_path(self):
+        return os.path.join(self.directory, "index.json")
+
+    def _file_of(self, path: str) -> str:
+        return os.path.join(self.directory, path.replace("/", "__") + ".npy")
+
+    def _load_index(self):
+        if os.path.exists(self._index_path()):
+            with open(self._index_path()) as fh:
+                for path in json.load(fh):
+                    if os.path.exists(self._file_of(path)):
+                        self._arrays[path] = np.load(self._file_of(path), mmap_mode="r+")
+
+    def _save_index(self):
+        if self.directory is not None:
+            with open(self._index_path(), "w") as fh:
+                json.dump(sorted(self._arrays), fh)
+
+    # ---- simulation_database.Database interface ------------------------------------------
+    def check_existence(self, path: str) -> bool:
+        """simulation_database.py:546-572."""
+        return path in self._arrays
+
+    def add_dataset(self, path: str, shape: Tuple[int, int, int]):
+        """simulation_database.py:452-497: float32 dataset of (n_rows, n_frames, n_dims)."""
+        if path in self._arrays:
+            raise ValueError(f"dataset {path} already exists")
+        if self.directory is not None:
+            arr = np.lib.format.open_memmap(self._file_of(path), mode="w+", dtype=np.float32,
+                                            shape=tuple(int(s) for s in shape))
+        else:
+            arr = np.zeros(shape, dtype=np.float32)
+        self._arrays[path] = arr
+        self._save_index()
+        return arr
+
+    def resize_dataset(self, path: str, n_frames: int):
+        """simulation_database.py:380-420 (extend along the frame axis)."""
+        old = self._arrays[path]
+        if old.shape[1] >= n_frames:
+            return old
+        data = np.array(old)
+        del self._arrays[path]
+        self.invalidate(path)
+        new = self.add_dataset(path, (old.shape[0], n_frames, old.shape[2]))
+        new[:, : data.shape[1]] = data
+        return new
+
+    def add_data(self, path: str, data, start: int = 0):
+        """Write ``data`` (n_rows, k, n_dims) at frame offset ``start``; values are rounded to
+        float32 exactly as the HDF5 store does (simulation_database.py:333-378)."""
+        arr = self._arrays[path]
+        data = np.asarray(data)
+        arr[:, start : start + data.shape[1]] = data.astype(np.float32, copy=False)
+        self.invalidate(path)
+
+    def put(self, path: str, array):
+        """Create-or-replace a whole dataset from an array (ScriptInput-style ingest)."""
+        array = np.asarray(array)
+        if array.ndim != 3:
+            raise ValueError("datasets are (n_rows, n_frames, n_dims)")
+        if path in self._arrays:
+            del self._arrays[path]
+            self.invalidate(path)
+        arr = self.add_dataset(path, array.shape)
+        arr[...] = array.astype(np.float32, copy=False)
+        return arr
+
+    def get_data_size(self, path: str):
+        """(n_rows, n_configurations, n_bytes) -- simulation_database.py:683-690."""
+        a = self._arrays[path]
+        return a.shape[0], a.shape[1], int(a.size * 4)
+
+    def shape(self, path: str):
+        return self._arrays[path].shape
+
+    def load_data(self, path: str, select_slice=np.s_[:]) -> np.ndarray:
+        """Host read as float64 (simulation_database.py:594-639 casts to tf.float64)."""
+        return np.asarray(self._arrays[path][select_slice], dtype=np.float64)
+
+    def host(self, path: str) -> np.ndarray:
+        return self._arrays[path]
+
+    def paths(self):
+        return sorted(self._arrays)
+
+    # ---- HBM residency ------------------------------------------------------------------------
+    def _budget(self) -> int:
+        if config.device_cache_bytes is not None:
+            return int(config.device_cache_bytes)
+        import torch
+
+        free, _total = torch.cuda.mem_get_info()
+        config.device_cache_bytes = int(0.6 * free)
+        return config.device_cache_bytes
+
+    def invalidate(self, path: Optional[str] = None):
+        """Drop cached device copies (of one dataset, or all)."""
+        for key in [k for k in self._device_cache if path is None or k[0] == path]:
+            t = self._device_cache.pop(key)
+            self._device_bytes -= t.numel() * t.element_size()
+
+    def device(self, path: str, rows: Optional[Tuple[int, int]] = None,
+               row_index: Optional[np.ndarray] = None, device=None):
+        """CUDA float32 tensor of dataset rows [lo, hi) (or a fancy row selection)."""
+        import torch
+
+        from ._lib import MdkError
+
+        if not torch.cuda.is_available():
+            raise MdkError("CUDA device required: the trajectory store has no CPU compute path")
+        dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        arr = self._arrays[path]
+        if row_index is not None:
+            row_index = np.asarray(row_index)
+            key = (path, "idx", hash(row_index.tobytes()), str(dev))
+        else:
+            lo, hi = (0, arr.shape[0]) if rows is None else (int(rows[0]), int(rows[1]))
+            key = (path, lo, hi, str(dev))
+        hit = self._device_cache.get(key)
+        if hit is not None:
+            self._device_cache.move_to_end(key)
+            return hit
+        src = arr[row_index] if row_index is not None else arr[lo:hi]
+        nbytes = int(np.prod(src.shape)) * 4
+        budget = self._budget()
+        while self._device_cache and self._device_bytes + nbytes > budget:
+            _, old = self._device_cache.popitem(last=False)
+            self._device_bytes -= old.numel() * old.element_size()
+        out = torch.empty(src.shape, dtype=torch.float32, device=dev)
+        self._upload(src, out)
+        self._device_cache[key] = out
+        self._device_bytes += nbytes
+        return out
+
+    def _upload(self, src: np.ndarray, dst, chunk_bytes: int = 256 << 20):
+        """Host -> device through a pinned staging buffer, double buffered."""
+        import torch
+
+        n_rows = src.shape[0]
+        if n_rows == 0:
+            return
+        row_bytes = int(np.prod(src.shape[1:])) * 4
+        rows_per = max(1, chunk_bytes // max(row_bytes, 1))
+        stage = [torch.empty((min(rows_per, n_rows),) + tuple(src.shape[1:]), dtype=torch.float32,
+                             pin_memory=True) for _ in range(2)]
+        events = [None, None]
+        for i, lo in enumerate(range(0, n_rows, rows_per)):
+            hi = min(n_rows, lo + rows_per)
+            s = stage[i & 1]
+            if events[i & 1] is not None:
+                events[i & 1].synchronize()
+            s[: hi - lo].numpy()[...] = src[lo:hi]
+            dst[lo:hi].copy_(s[: hi - lo], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            events[i & 1] = ev
+            self.h2d_bytes += (hi - lo) * row_bytes
+        torch.cuda.current_stream().synchronize()

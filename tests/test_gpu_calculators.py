@@ -1,0 +1,248 @@
+"""End-to-end parity of the calculator API (Project -> Experiment -> run.X) against the oracle
+on the BASELINE parity configs (scaled where the oracle would take minutes).
+
+C1: 1,000-atom NaCl LAMMPS text dump, 100 frames -> RadialDistributionFunction (+CN)
+C2: same system, 1,500 frames, data_range 200    -> Einstein + Green-Kubo diffusion
+C3: 1,728-atom NaCl, 1,200 frames, data_range 150 -> unwrap, ionic current, GK ionic conductivity
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5  # BASELINE.json north_star: series and transport coefficients within 1e-5 relative
+MEM = 60e9   # planner memory pinned so that the oracle and the product share one plan
+
+
+@pytest.fixture(scope="module")
+def nacl_c1(tmp_path_factory, cuda):
+    from lammps_analysis_b200.config import config
+    from lammps_analysis_b200.file_io import write_lammps_dump
+    from lammps_analysis_b200.project import Project
+    from lammps_analysis_b200.synthetic import nacl_trajectory
+
+    config.planner_memory_bytes = MEM
+    tmp = tmp_path_factory.mktemp("c1")
+    data, box = nacl_trajectory(1000, 100, 32.0, seed=1)
+    dump = str(tmp / "nacl.lammpstraj")
+    write_lammps_dump(dump, data, box, step_stride=10)
+    project = Project("c1", storage_path=str(tmp))
+    exp = project.add_experiment("NaCl", timestep=0.002, temperature=1400.0, units="metal",
+                                 simulation_data=dump)
+    return project, exp, data, box
+
+
+def test_ingest_matches_source(nacl_c1):
+    project, exp, data, box = nacl_c1
+    assert list(exp.species) == ["Na", "Cl"]
+    assert exp.number_of_configurations == 100 and exp.sample_rate == 10
+    assert exp.box_array == [32.0, 32.0, 32.0]
+    for sp in ("Na", "Cl"):
+        for prop in ("Positions", "Velocities"):
+            assert np.array_equal(exp.store.host(f"{sp}/{prop}"), data[sp][prop])
+
+
+def test_c1_rdf_bit_exact_and_normalised(nacl_c1):
+    from oracle import rdf as orc
+
+    project, exp, data, box = nacl_c1
+    res = exp.run.RadialDistributionFunction(number_of_configurations=100, plot=False)
+    species = ["Na", "Cl"]
+    cutoff = orc.default_cutoff(box)
+    nbins = orc.default_number_of_bins(cutoff)
+    assert nbins == 1590
+    frames = orc.sample_configurations(0, 99, 100)
+    # reference plan at 60 GB: 100 single-frame batches x 10 atom minibatches
+    bs, nb = orc.rdf_plan({"Na": 500, "Cl": 500}, 100, 100, MEM)
+    assert (bs, nb) == (1, 100)
+    ref_counts = orc.rdf_counts({s: data[s]["Positions"] for s in species}, species, box, frames,
+                                cutoff, nbins, 100, nb)
+    ref = orc.rdf_normalise(ref_counts, {"Na": 500, "Cl": 500}, box, cutoff, nbins, 100, 1e-10)
+    assert res.keys() == ["Na_Na", "Na_Cl", "Cl_Cl"]
+    # integer counts: recover them from the calculator that produced the stored result
+    calc = exp.run.RadialDistributionFunction
+    calc.__class__.__call__.__wrapped__(calc, number_of_configurations=100, plot=False)
+    calc.check_input()
+    counts = calc.compute_counts()
+    ties = 0
+    for p, key in enumerate(res.keys()):
+        ties += int(np.count_nonzero(counts[p] != ref_counts[key]))
+        np.testing.assert_allclose(res[key]["x"], ref[key]["x"], rtol=1e-12)
+        y, yr = np.array(res[key]["y"]), np.array(ref[key]["y"])
+        assert np.isnan(y[0]) or np.isinf(y[0])          # Q2: r[0] = 0
+        np.testing.assert_allclose(y[1:], yr[1:], rtol=RTOL)
+    assert ties == 0, f"{ties} bins differ from the oracle"
+
+
+def test_cache_returns_stored_computation(nacl_c1):
+    project, exp, data, box = nacl_c1
+    a = exp.run.RadialDistributionFunction(number_of_configurations=100, plot=False)
+    b = exp.run.RadialDistributionFunction(number_of_configurations=100, plot=False)
+    assert a.id == b.id
+    assert a.computation_parameter["number_of_configurations"] == 100
+    assert a.computation_parameter["cutoff"] is None      # stored with unresolved defaults
+    d = project.run.RadialDistributionFunction(number_of_configurations=100, plot=False)
+    assert list(d) == ["NaCl"] and d["NaCl"].id == a.id
+    c = exp.run.RadialDistributionFunction(number_of_configurations=50, plot=False)
+    assert c.id != a.id
+
+
+def test_c1_coordination_numbers(nacl_c1):
+    from oracle import coordination as oc
+
+    project, exp, data, box = nacl_c1
+    rdf = exp.run.RadialDistributionFunction(number_of_configurations=100, plot=False)
+    cn = exp.run.CoordinationNumbers(rdf_data=rdf, plot=False, savgol_window_length=31)
+    vol_nm3 = np.prod(box) * (1e-10) ** 3 / 1e-27
+    ref = oc.coordination_numbers(rdf.data_dict, {"Na": 500, "Cl": 500}, vol_nm3,
+                                  savgol_window_length=31)
+    for key in ref:
+        np.testing.assert_allclose(cn[key]["cn"], ref[key]["cn"], rtol=1e-9)
+        assert cn[key]["CN_1"] == pytest.approx(ref[key]["CN_1"], rel=1e-9)
+        assert cn[key]["CN_1_error"] == pytest.approx(ref[key]["CN_1_error"], rel=1e-6, abs=1e-12)
+
+
+@pytest.fixture(scope="module")
+def nacl_c2(tmp_path_factory, cuda):
+    from lammps_analysis_b200.config import config
+    from lammps_analysis_b200.file_io import ScriptInput
+    from lammps_analysis_b200.project import Project
+    from lammps_analysis_b200.synthetic import nacl_trajectory
+
+    config.planner_memory_bytes = MEM
+    tmp = tmp_path_factory.mktemp("c2")
+    data, box = nacl_trajectory(1000, 1500, 32.0, seed=2, sigma_step=0.3)
+    project = Project("c2", storage_path=str(tmp))
+    exp = project.add_experiment("NaCl", timestep=0.002, temperature=1400.0, units="metal")
+    exp.add_data(ScriptInput(data, box, sample_rate=10, charges={"Na": 1.0, "Cl": -1.0},
+                             atom_major=True))
+    return project, exp, data, box
+
+
+def _oracle_plan(A, T, N, ct, scale):
+    from oracle.planner import ArrayDatabase, plan_trajectory_calculator
+
+    class _S:
+        shape = (A, T, 3)
+
+    return plan_trajectory_calculator(ArrayDatabase({"x": _S()}), ["x"], N, ct,
+                                      {"linear": {"scale_factor": scale}}, MEM)
+
+
+def test_c2_einstein(nacl_c2):
+    from oracle import dynamics as od
+    from oracle import transformations as ot
+
+    project, exp, data, box = nacl_c2
+    N = 200
+    res = exp.run.EinsteinDiffusionCoefficients(data_range=N, plot=False)
+    plan = _oracle_plan(500, 1500, N, 1, 150)
+    for sp in ("Na", "Cl"):
+        unw = ot.run_unwrap(data[sp]["Positions"], box, batch_size=1500)
+        assert np.array_equal(exp.store.host(f"{sp}/Unwrapped_Positions"), unw)
+        tau, _, _, times = od.handle_tau_values(np.s_[:], N, 0.002, 10)
+        msd_sum, count = od.einstein_msd(unw, plan, N, 1, tau)
+        assert count == 1300 * 501
+        ref = od.einstein_finish(msd_sum, count, times, 1e-10, 1e-12, N - 1)
+        np.testing.assert_allclose(res[sp]["msd"], ref["msd"], rtol=RTOL)
+        np.testing.assert_allclose(res[sp]["time"], ref["time"], rtol=1e-12)
+        assert res[sp]["diffusion_coefficient"] == pytest.approx(ref["diffusion_coefficient"],
+                                                                 rel=RTOL)
+        assert res[sp]["uncertainty"] == pytest.approx(ref["uncertainty"], rel=1e-3)
+
+
+def test_c2_green_kubo_diffusion(nacl_c2):
+    from oracle import dynamics as od
+
+    project, exp, data, box = nacl_c2
+    N = 200
+    res = exp.run.GreenKuboDiffusionCoefficients(data_range=N, plot=False)
+    plan = _oracle_plan(500, 1500, N, 1, 150)
+    for sp in ("Na", "Cl"):
+        _, _, _, times = od.handle_tau_values(np.s_[:], N, 0.002, 10)
+        time = times * 1e-12
+        acf_sum, count, sigmas = od.gk_diffusion_acf(data[sp]["Velocities"], plan, N, 1, time,
+                                                     1e-10, 1e-12)
+        ref = od.gk_diffusion_finish(acf_sum, count, sigmas, time, N - 1)
+        scale = np.abs(ref["acf"]).max()
+        np.testing.assert_allclose(res[sp]["acf"], ref["acf"], rtol=RTOL, atol=1e-7 * scale)
+        np.testing.assert_allclose(res[sp]["integral"], ref["integral"], rtol=RTOL)
+        assert res[sp]["diffusion_coefficient"][0] == pytest.approx(
+            ref["diffusion_coefficient"][0], rel=RTOL)
+        assert res[sp]["uncertainty"][0] == pytest.approx(ref["uncertainty"][0], rel=1e-4)
+
+
+def test_c3_ionic_conductivity(tmp_path, cuda):
+    from lammps_analysis_b200.config import config
+    from lammps_analysis_b200.file_io import ScriptInput
+    from lammps_analysis_b200.project import Project
+    from lammps_analysis_b200.synthetic import nacl_trajectory
+    from oracle import dynamics as od
+    from oracle import transformations as ot
+    from oracle.planner import ArrayDatabase, plan_trajectory_calculator
+
+    config.planner_memory_bytes = MEM
+    data, box = nacl_trajectory(1728, 1200, 38.0, seed=3)
+    project = Project("c3", storage_path=str(tmp_path))
+    exp = project.add_experiment("NaCl", timestep=0.002, temperature=1400.0, units="metal")
+    exp.add_data(ScriptInput(data, box, sample_rate=10, atom_major=True))
+    exp.species["Na"].charge = 1.0
+    exp.species["Cl"].charge = -1.0
+    N = 150
+    res = exp.run.GreenKuboIonicConductivity(data_range=N, plot=False)
+    J_ref = ot.run_ionic_current({s: data[s]["Velocities"] for s in ("Na", "Cl")},
+                                 {"Na": 1.0, "Cl": -1.0})
+    J = exp.store.host("Observables/Ionic_Current")
+    assert J.shape == (1, 1200, 3)
+    # fp64 atom sum rounded once to float32: allow 1 ulp for the summation order
+    np.testing.assert_allclose(J, J_ref, rtol=2e-7, atol=1e-6)
+
+    class _S:
+        shape = (1, 1200, 3)
+
+    plan = plan_trajectory_calculator(ArrayDatabase({"x": _S()}), ["x"], N, 1,
+                                      {"linear": {"scale_factor": 5}}, MEM)
+    tau, _, _, times = od.handle_tau_values(np.s_[:], N, 0.002, 10)
+    acf_sum, count, sigmas = od.gk_ionic_acf(J.astype(np.float64), plan, N, 1, tau, times)
+    pref = od.gk_ionic_prefactor(1e-10, 1e-12, 1400.0, float(np.prod(box)))
+    ref = od.gk_ionic_finish(acf_sum, count, sigmas, times, pref, N - 1)
+    assert count == 1050
+    scale = np.abs(ref["acf"]).max()
+    np.testing.assert_allclose(res["System"]["acf"], ref["acf"], rtol=RTOL, atol=1e-7 * scale)
+    assert res["System"]["ionic_conductivity"][0] == pytest.approx(
+        ref["ionic_conductivity"][0], rel=RTOL)
+    assert res["System"]["uncertainty"][0] == pytest.approx(ref["uncertainty"][0], rel=1e-4)
+
+
+def test_atom_minibatch_plan_matches_oracle(tmp_path, cuda):
+    """Forces the planner's atom mini-batch path (memory too small for one data_range window),
+    as the reference's tests do with change_memory_fraction."""
+    from lammps_analysis_b200.config import config
+    from lammps_analysis_b200.file_io import ScriptInput
+    from lammps_analysis_b200.project import Project
+    from oracle import dynamics as od
+    from oracle.planner import ArrayDatabase, plan_trajectory_calculator
+
+    rng = np.random.default_rng(9)
+    A, T, N = 200, 400, 120
+    x = np.cumsum(rng.normal(0, 0.1, size=(A, T, 3)), axis=1).astype(np.float32)
+    mem = 150 * (A * 12) * 100 / 0.5     # room for 100 frames of all atoms -> minibatch
+    config.planner_memory_bytes = mem
+    try:
+        project = Project("mb", storage_path=str(tmp_path))
+        exp = project.add_experiment("X", timestep=0.001, temperature=300.0, units="real")
+        exp.add_data(ScriptInput({"Ar": {"Unwrapped_Positions": x}}, [50.0] * 3, atom_major=True))
+        res = exp.run.EinsteinDiffusionCoefficients(data_range=N, plot=False)
+
+        class _S:
+            shape = (A, T, 3)
+
+        plan = plan_trajectory_calculator(ArrayDatabase({"x": _S()}), ["x"], N, 1,
+                                          {"linear": {"scale_factor": 150}}, mem)
+        assert plan["minibatch"] and plan["n_atom_batches"] == 2
+        msd_sum, count = od.einstein_msd(x, plan, N, 1, np.arange(N))
+        ref = np.array(msd_sum) / count * (1e-10) ** 2
+        np.testing.assert_allclose(res["Ar"]["msd"], ref, rtol=RTOL)
+    finally:
+        config.planner_memory_bytes = MEM

@@ -1,0 +1,262 @@
+"""CPU-only tests of the host side: planner, store, ingest, fits, cache protocol, C ABI exports."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_libmdk_exports_every_declared_symbol():
+    """The shared library loads without a GPU and exports everything include/mdk.h declares."""
+    from lammps_analysis_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "mdk.h")).read()
+    declared = set(re.findall(r"\b(mdk_[a-z0-9_]+)\s*\(", hdr))
+    declared.discard("mdk_stream_t")
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in mdk.h but not exported"
+    assert set(_lib.PROTOTYPES) | {"mdk_last_error"} == declared
+    assert _lib.load().mdk_version() == 100
+
+
+def test_rdf_thresholds_reproduce_double_step_binning():
+    """mdk_rdf_thresholds (host helper, no GPU): bin(d2) via the table equals
+    int(min(double(d)/step, nbins-1)) for every sampled fp32 distance."""
+    from lammps_analysis_b200 import kernels as K
+
+    cutoff, nbins = np.float32(15.9), 1590
+    thr, cut2 = K.rdf_thresholds(float(cutoff), nbins)
+    assert thr[0] == 0 and np.isinf(thr[nbins]) and np.all(np.diff(thr[:nbins]) > 0)
+    rng = np.random.default_rng(0)
+    d2 = (rng.random(2_000_000).astype(np.float32) * np.float32(cutoff) ** 2).astype(np.float32)
+    # adversarial samples: the thresholds themselves and their neighbours
+    d2 = np.concatenate([d2, thr[1:nbins], np.nextafter(thr[1:nbins], np.float32(0)),
+                         np.nextafter(thr[1:nbins], np.float32(np.inf))]).astype(np.float32)
+    d = np.sqrt(d2)                       # correctly rounded fp32 sqrt
+    inside = d < cutoff
+    assert np.array_equal(inside, d2 < np.float32(cut2))
+    step = float(cutoff) / nbins
+    want = np.minimum(d[inside].astype(np.float64) / step, nbins - 1).astype(np.int64)
+    got = np.searchsorted(thr[1:nbins], d2[inside], side="right")
+    assert np.array_equal(got, want)
+
+
+def test_product_planner_matches_oracle_planner():
+    from lammps_analysis_b200.planner import plan_batches
+    from oracle.planner import MemoryManager
+
+    class DB:
+        def __init__(self, size):
+            self.size = size
+
+        def get_data_size(self, item):
+            return self.size
+
+    rng = np.random.default_rng(0)
+    specs = [{"linear": {"scale_factor": 150}}, {"linear": {"scale_factor": 5}},
+             {"quadratic": {"inner_scale_factor": 5, "outer_scale_factor": 10}}, None]
+    for _ in range(1500):
+        rows, cols = int(rng.integers(1, 5000)), int(rng.integers(2, 20000))
+        size = (rows, cols, rows * cols * 12)
+        mem = float(10 ** rng.uniform(2, 11))
+        N, ct = int(rng.integers(1, 600)), int(rng.integers(1, 6))
+        sf = specs[int(rng.integers(0, 4))]
+        mm = MemoryManager(data_path=[0], database=DB(size), memory_fraction=0.5,
+                           scale_function=sf, memory=mem)
+        mm.get_batch_size()
+        loops, minibatch = mm.get_ensemble_loop(N, ct)
+        p = plan_batches([size], N, ct, sf, memory=mem, memory_fraction=0.5)
+        assert (p.batch_size, p.n_batches, p.remainder, p.ensemble_loop, p.minibatch) == (
+            mm.batch_size, mm.n_batches, mm.remainder, loops, minibatch)
+        if minibatch:
+            assert (p.atom_batch_size, p.n_atom_batches, p.atom_remainder) == (
+                mm.atom_batch_size, mm.n_atom_batches, mm.atom_remainder)
+
+
+def test_survey_worked_plans():
+    """SURVEY.md A.5 worked plans at 60 GB."""
+    from lammps_analysis_b200.planner import plan_batches
+
+    ein = {"linear": {"scale_factor": 150}}
+    p = plan_batches([(500, 5000, 500 * 5000 * 12)], 500, 1, ein, memory=60e9, memory_fraction=0.5)
+    assert (p.batch_size, p.n_batches, p.ensemble_loop, p.minibatch) == (5000, 1, 4500, False)
+    p = plan_batches([(500_000, 2000, 500_000 * 2000 * 12)], 500, 1, ein, memory=60e9,
+                     memory_fraction=0.5)
+    assert p.minibatch and p.batch_size == 2000 and p.atom_batch_size == 250_000
+    assert p.n_atom_batches == 2 and p.ensemble_loop == 1500
+    p = plan_batches([(1, 10000, 10000 * 12)], 500, 1, {"linear": {"scale_factor": 5}},
+                     memory=60e9, memory_fraction=0.5)
+    assert (p.batch_size, p.n_batches, p.ensemble_loop) == (10000, 1, 9500)
+
+
+def test_plan_windows_matches_oracle_iteration():
+    from lammps_analysis_b200.engine import plan_windows
+    from lammps_analysis_b200.planner import plan_batches
+    from oracle.planner import iter_batches, iter_ensembles
+
+    for (A, T, N, ct, mem) in [(64, 400, 50, 1, 60e9), (60, 1000, 100, 2, 2.0e5 * 60 / 64),
+                               (200, 400, 120, 1, 150 * 200 * 12 * 100 / 0.5)]:
+        p = plan_batches([(A, T, A * T * 12)], N, ct, {"linear": {"scale_factor": 150}},
+                         memory=mem, memory_fraction=0.5).as_dict()
+        want = []
+        for atom_sel, start, stop, size in iter_batches(p):
+            wins = [(s, e) for s, e in iter_ensembles(size, N, ct) if e <= size]
+            if wins:
+                lo = 0 if atom_sel == slice(None) else atom_sel.start
+                hi = A if atom_sel == slice(None) else atom_sel.stop
+                want.append((lo, hi, start, size, len(wins)))
+        assert plan_windows(p, N, ct, A) == want
+
+
+def test_store_roundtrip_and_float32_rounding(tmp_path):
+    from lammps_analysis_b200.store import TrajectoryStore
+
+    st = TrajectoryStore(str(tmp_path / "db"))
+    x = np.random.default_rng(0).normal(size=(5, 7, 3))
+    st.add_dataset("Na/Positions", (5, 7, 3))
+    st.add_data("Na/Positions", x[:, :4], start=0)
+    st.add_data("Na/Positions", x[:, 4:], start=4)
+    assert st.check_existence("Na/Positions") and not st.check_existence("Na/Velocities")
+    assert st.get_data_size("Na/Positions") == (5, 7, 5 * 7 * 3 * 4)
+    got = st.load_data("Na/Positions", np.s_[1:3, 2:5])
+    assert got.dtype == np.float64
+    assert np.array_equal(got, x.astype(np.float32).astype(np.float64)[1:3, 2:5])
+    st2 = TrajectoryStore(str(tmp_path / "db"))          # re-open from disk
+    assert np.array_equal(st2.host("Na/Positions"), x.astype(np.float32))
+    st2.resize_dataset("Na/Positions", 10)
+    assert st2.shape("Na/Positions") == (5, 10, 3)
+    assert np.array_equal(st2.host("Na/Positions")[:, :7], x.astype(np.float32))
+
+
+def test_lammps_dump_roundtrip_with_unsorted_ids(tmp_path):
+    from lammps_analysis_b200.file_io import LAMMPSTrajectoryFile, write_lammps_dump
+    from lammps_analysis_b200.synthetic import nacl_trajectory
+
+    data, box = nacl_trajectory(64, 4, 12.0, 1)
+    path = str(tmp_path / "t.lammpstraj")
+    write_lammps_dump(path, data, box, step_stride=5)
+    # shuffle atom rows inside every frame: the reader must sort by id
+    lines = open(path).read().splitlines()
+    rng = np.random.default_rng(0)
+    out = []
+    for f in range(4):
+        blk = lines[f * 73:(f + 1) * 73]
+        rows = blk[9:]
+        rng.shuffle(rows)
+        out += blk[:9] + list(rows)
+    open(path, "w").write("\n".join(out) + "\n")
+    reader = LAMMPSTrajectoryFile(path)
+    meta = reader.metadata
+    assert meta.n_configurations == 4 and meta.sample_rate == 5 and meta.box_l == [12.0] * 3
+    assert [(s.name, s.n_particles) for s in meta.species_list] == [("Na", 32), ("Cl", 32)]
+    chunks = list(reader.get_configurations_generator(3))
+    for sp in ("Na", "Cl"):
+        for prop in ("Positions", "Velocities"):
+            got = np.concatenate([c.data[sp][prop] for c in chunks], axis=1)
+            assert np.array_equal(got.astype(np.float32), data[sp][prop])
+
+
+def test_closed_form_einstein_fit_matches_curve_fit():
+    from lammps_analysis_b200.calculators.einstein_diffusion_coefficients import fit_einstein_curve
+    from oracle import dynamics as od
+
+    rng = np.random.default_rng(0)
+    x = np.arange(150) * 0.02e-12
+    y = 6 * 1.3e-9 * x + 1e-21 * np.sqrt(np.arange(150)) + rng.normal(0, 1e-23, 150)
+    a = od.fit_einstein_curve(x, y, 149)
+    b = fit_einstein_curve(x, y, 149)
+    np.testing.assert_allclose(b[0], a[0], rtol=1e-6)
+    np.testing.assert_allclose(np.sqrt(np.diag(b[1])), np.sqrt(np.diag(a[1])), rtol=1e-4)
+    np.testing.assert_allclose(b[2], a[2], rtol=1e-6)
+    # reference known answers (CI/unit_tests/utils/test_calculator_helper_methods.py:42-69)
+    xs = np.linspace(0, 1000, 1000)
+    assert fit_einstein_curve(xs, 5 * xs + 3, 999)[0][0] == pytest.approx(5.0, 0.01)
+    ys = np.exp(-0.05 * xs) * xs**2 + 5 * xs + 3
+    assert fit_einstein_curve(xs, ys, 999)[0][0] == pytest.approx(5.0, 0.01)
+
+
+def test_golden_section_search_matches_recursive_oracle():
+    from lammps_analysis_b200.calculators.coordination_number_calculation import \
+        golden_section_search
+    from oracle import coordination as oc
+
+    r = np.linspace(0.05, 1.5, 600)
+    g = 1 + np.exp(-3 * r) * np.cos(14 * r) * 2
+    assert golden_section_search([r, g], r[300], r[80]) == oc.golden_section_search(
+        [r, g], r[300], r[80])
+
+
+def test_cache_protocol_with_fake_calculator(tmp_path):
+    """calculator.py:52-148: identical args + version -> stored object, no recompute."""
+    from dataclasses import dataclass
+
+    from lammps_analysis_b200.calculators.calculator import Calculator, call
+    from lammps_analysis_b200.file_io import ScriptInput
+    from lammps_analysis_b200.project import Project
+
+    runs = []
+
+    @dataclass
+    class Args:
+        k: int
+        sel: object
+
+    class Fake(Calculator):
+        analysis_name = "Fake"
+
+        @call
+        def __call__(self, k: int = -1, sel=np.s_[:]):
+            self.args = Args(k=k, sel=sel)
+
+        def run_calculator(self):
+            if self.args.k == -1:
+                self.args.k = 7          # default resolved during the run
+            runs.append(self.args.k)
+            self.queue_data({"value": self.args.k * 2}, subjects=["Na", "Na"])
+            self.queue_data({"value": 1}, subjects=["System"])
+
+    project = Project("p", storage_path=str(tmp_path))
+    exp = project.add_experiment("e", timestep=1.0, temperature=1.0, units="si")
+    exp.add_data(ScriptInput({"Na": {"Positions": np.zeros((3, 2, 3))}}, [1, 1, 1]))
+    a = Fake(experiment=exp)()
+    b = Fake(experiment=exp)()
+    assert runs == [7] and a.id == b.id
+    assert a["Na_Na"] == {"value": 14} and a.keys() == ["Na_Na", "System"]
+    assert a.computation_parameter == {"k": -1, "sel": "slice(None, None, None)", "version": 1}
+    with pytest.raises(KeyError):
+        a["Cl"]
+    Fake(experiment=exp)(k=3)
+    assert runs == [7, 3]
+    exp.add_data(ScriptInput({"Na": {"Positions": np.zeros((3, 2, 3))}}, [1, 1, 1], name="more"))
+    assert exp.version == 2 and exp.number_of_configurations == 6
+    Fake(experiment=exp)()               # new data -> new version -> recompute
+    assert runs == [7, 3, 7]
+    both = Fake(experiments=[exp])()     # project-style call returns a dict
+    assert list(both) == ["e"]
+    # a re-opened project finds the stored computation
+    again = Project("p", storage_path=str(tmp_path))
+    assert Fake(experiment=again.experiments["e"])().id == both["e"].id
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "lammps_analysis_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_kernels_refuse_cpu_tensors():
+    import torch
+
+    from lammps_analysis_b200 import kernels as K
+    from lammps_analysis_b200._lib import MdkError
+
+    with pytest.raises(MdkError):
+        K.msd_windowed(torch.zeros(2, 4, 3), 0, 2, 0, 1, 1, torch.zeros(2, dtype=torch.int32), 2,
+                       torch.zeros(2, dtype=torch.float64))

@@ -101,18 +101,23 @@ class RadialDistributionFunction(TrajectoryCalculator):
         exp = self.experiment
         store = exp.store
         sel = self.args.atom_selection
-        trajs = []
-        for s in self.args.species:
-            path = join_path(s, self.loaded_property)
-            if isinstance(sel, dict):
-                trajs.append(store.device(path, row_index=np.asarray(sel[s])))
-            else:
+        frames = D.shard_frames(self.sample_configurations)
+        trajs, frame_ids = [], frames
+        paths = [join_path(s, self.loaded_property) for s in self.args.species]
+        resident = all(store.is_resident(p) for p in paths) and not isinstance(sel, dict)
+        for s, path in zip(self.args.species, paths):
+            if resident:
                 trajs.append(store.device(path))
+            else:
+                # upload only the sampled frames of this rank
+                rows = np.asarray(sel[s]) if isinstance(sel, dict) else None
+                trajs.append(store.device_frames(path, frames, row_index=rows))
+        if not resident:
+            frame_ids = np.arange(len(frames))
         self.engine = RdfEngine(self.particles_list, exp.box_array, self.args.cutoff,
                                 self.args.number_of_bins, drop_first=self.parity_mode)
-        frames = D.shard_frames(self.sample_configurations)
         if len(frames):
-            self.engine.add_frames(trajs, frames)
+            self.engine.add_frames(trajs, frame_ids)
         D.all_reduce_sum_([self.engine.hist])
         return self.engine.counts()
 

@@ -14,9 +14,28 @@ from typing import List, Tuple
 import numpy as np
 
 
+import contextlib
+
+_local_only = False
+
+
+@contextlib.contextmanager
+def local_only():
+    """Inside this context the calculators treat the process as a single rank: the caller has
+    already given every rank its own shard (bench.py's weak-scaling run) and reduces itself."""
+    global _local_only
+    old, _local_only = _local_only, True
+    try:
+        yield
+    finally:
+        _local_only = old
+
+
 def _dist():
     import torch.distributed as dist
 
+    if _local_only:
+        return None
     return dist if (dist.is_available() and dist.is_initialized()) else None
 
 

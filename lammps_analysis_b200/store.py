@@ -161,6 +161,10 @@ class TrajectoryStore:
         if hit is not None:
             self._device_cache.move_to_end(key)
             return hit
+        if row_index is None:
+            whole = self._device_cache.get((path, 0, arr.shape[0], str(dev)))
+            if whole is not None:
+                return whole[lo:hi]          # rows are the leading axis: a contiguous view
         src = arr[row_index] if row_index is not None else arr[lo:hi]
         nbytes = int(np.prod(src.shape)) * 4
         budget = self._budget()
@@ -172,6 +176,41 @@ class TrajectoryStore:
         self._device_cache[key] = out
         self._device_bytes += nbytes
         return out
+
+    def is_resident(self, path: str) -> bool:
+        return any(k[0] == path and k[1] == 0 and k[2] == self._arrays[path].shape[0]
+                   for k in self._device_cache if k[1] != "idx")
+
+    def adopt_device(self, path: str, tensor):
+        """Register a device tensor that already holds the whole dataset ``path`` (e.g. the
+        output a transformation just produced), so that the next calculator does not re-upload
+        it."""
+        self.invalidate(path)
+        key = (path, 0, int(tensor.shape[0]), str(tensor.device))
+        self._device_cache[key] = tensor
+        self._device_bytes += tensor.numel() * tensor.element_size()
+
+    def device_frames(self, path: str, frames, row_index=None, device=None):
+        """CUDA float32 [rows][len(frames)][dims] holding only the selected frames (not
+        cached): the RDF samples a few frames of a long trajectory."""
+        import torch
+
+        arr = self._arrays[path]
+        frames = np.asarray(frames, dtype=np.int64)
+        src = arr[:, frames] if row_index is None else arr[np.asarray(row_index)][:, frames]
+        dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        out = torch.empty(src.shape, dtype=torch.float32, device=dev)
+        self._upload(np.ascontiguousarray(src), out)
+        return out
+
+    def remove(self, path: str):
+        """Delete a dataset (host, disk and device copies)."""
+        self.invalidate(path)
+        arr = self._arrays.pop(path, None)
+        del arr
+        if self.directory is not None and os.path.exists(self._file_of(path)):
+            os.remove(self._file_of(path))
+        self._save_index()
 
     def _upload(self, src: np.ndarray, dst, chunk_bytes: int = 256 << 20):
         """Host -> device through a pinned staging buffer, double buffered."""

@@ -66,6 +66,7 @@ class _SingleSpeciesTrafo(Transformations):
             per_frame = n_atoms * 12 * (len(paths) + 1)
             frames_per_chunk = max(1, min(n_frames, self.chunk_bytes // max(per_frame, 1)))
             carry = None
+            whole = None
             for t0 in range(0, n_frames, frames_per_chunk):
                 t1 = min(n_frames, t0 + frames_per_chunk)
                 if t0 == 0 and t1 == n_frames:
@@ -76,8 +77,10 @@ class _SingleSpeciesTrafo(Transformations):
                 out_dev = torch.empty_like(inputs[0])
                 carry = self.transform_batch(inputs, out_dev, carry)
                 out_host[:, t0:t1] = out_dev.cpu().numpy()
+                whole = out_dev if (t0 == 0 and t1 == n_frames) else None
             exp.store.invalidate(out_path)
-        exp.version += 0  # derived data does not change the experiment version upstream
+            if whole is not None:
+                exp.store.adopt_device(out_path, whole)  # stays resident for the calculator
 
 
 class CoordinateUnwrapper(_SingleSpeciesTrafo):

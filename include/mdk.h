@@ -117,6 +117,12 @@ int mdk_msd_windowed(const float* traj, long long A, long long T, long long a_lo
                      long long t0, int W, int ct, const int* tau, int n_tau, int span,
                      double* msd_sum, mdk_stream_t stream);
 
+/* Same sums for the dense lag set tau = 0 .. n_lags-1 with correlation_time 1 (the default
+ * `tau_values = np.s_[:]`): register-ring kernel, one position load per n_lags/… updates.
+ *   msd_sum[k] += sum_{w<W} sum_a sum_d (x[a, t0+w+k, d] - x[a, t0+w, d])^2,  k < n_lags */
+int mdk_msd_dense(const float* traj, long long A, long long T, long long a_lo, long long a_hi,
+                  long long t0, int W, int n_lags, double* msd_sum, mdk_stream_t stream);
+
 /* Lag products for the windowed unbiased autocorrelation.
  *   P[t - t0][m] += sum_{a in [a_lo,a_hi)} sum_d v[a,t,d] * v[a,t+m,d]
  *   for t0 <= t < t0 + B, 0 <= m < N, t + m < t0 + B          (P: device f64 [B][N])

@@ -38,6 +38,7 @@ PROTOTYPES = {
     "mdk_coord_extent": [_P, _I, _LL, _P, _P],
     "mdk_rdf_hist": [_P, _I, _LL, _P, _P, _I, _P, _F, _F, _I, _P, _P, _P, _I, _P],
     "mdk_msd_windowed": [_P, _LL, _LL, _LL, _LL, _LL, _I, _I, _P, _I, _I, _P, _P],
+    "mdk_msd_dense": [_P, _LL, _LL, _LL, _LL, _LL, _I, _I, _P, _P],
     "mdk_acf_lagprod": [_P, _LL, _LL, _LL, _LL, _LL, _I, _I, _P, _P],
     "mdk_acf_windows": [_P, _I, _I, _I, _I, _P, _P, _P],
     "mdk_unwrap": [_P, _LL, _LL, _P, _P, _I, _P, _P, _P],

@@ -12,6 +12,8 @@
 // carries one rounding), short runs are summed in fp32 and folded into fp64 accumulators.
 #include "mdk_common.cuh"
 
+#include <cstdlib>
+
 namespace mdk {
 
 constexpr int DYN_NT = 128;  // threads per CTA: one lag per thread and pass
@@ -82,6 +84,126 @@ msd_windowed_kernel(const float* __restrict__ traj, long long T, long long a_lo,
       const int k = kb + r * DYN_NT + tid;
       if (ok[r]) atomicAdd(msd_sum + k, acc64[r]);
     }
+  }
+}
+
+// ---- Einstein MSD, dense lags (tau = 0 .. n_lags-1, correlation_time 1) ----------------------
+// Thread k owns the MD_R consecutive lags k*MD_R .. k*MD_R+MD_R-1 and slides over the window
+// origins: the MD_R positions x(w + lag) it needs at origin w are kept in a register ring, so
+// one origin costs ONE new position load (plus the broadcast origin) for MD_R updates instead
+// of one load per update.  MD_R is odd, which makes the lane stride (MD_R positions) conflict
+// free for the float2 {x,y} array and the z array in shared memory.  Differences and squares
+// run on FADD2/FFMA2 for {x,y} and FADD/FFMA for z; fp32 partial sums over MD_FOLD origins are
+// folded into fp64.
+constexpr int MD_R = 9;
+constexpr int MD_NT = 64;
+constexpr int MD_FOLD = 3;  // outer iterations (of MD_R origins) between fp64 folds
+
+__global__ void __launch_bounds__(MD_NT)
+msd_dense_kernel(const float* __restrict__ traj, long long T, long long a_lo, long long a_hi,
+                 int atoms_per_cta, long long t0, int W, int n_lags, int Wc, int len_alloc,
+                 double* __restrict__ msd_sum) {
+  extern __shared__ __align__(16) float md_smem[];  // xy: 2*len_alloc floats, z: len_alloc floats
+  float2* s_xy = reinterpret_cast<float2*>(md_smem);
+  float* s_z = md_smem + 2 * len_alloc;
+  const int tid = threadIdx.x;
+  const int w0 = blockIdx.x * Wc;
+  const int w1 = min(W, w0 + Wc);
+  if (w0 >= w1) return;
+  const int nw = w1 - w0;
+  const int lag0 = (blockIdx.z * MD_NT + tid) * MD_R;  // first lag of this thread
+  const int lag_blk0 = blockIdx.z * MD_NT * MD_R;
+  const int lags_here = min(n_lags - lag_blk0, MD_NT * MD_R);
+  const int len = nw + lags_here - 1;                  // frames staged per atom
+  const long long t_begin = t0 + w0 + lag_blk0;        // smem index 0 <-> this frame ...
+  // ... but origins start at lag_blk0 frames *before* it: stage origins separately when the
+  // lag block is not the first one.
+  const long long a0 = a_lo + (long long)blockIdx.y * atoms_per_cta;
+  const long long a1 = min(a_hi, a0 + atoms_per_cta);
+  const int kR = tid * MD_R;  // local lag offset inside the block
+  float* s_oxy = s_z + len_alloc;  // origin copies for lag blocks > 0: xy (2*Wc) then z (Wc)
+
+  double acc64[MD_R];
+#pragma unroll
+  for (int b = 0; b < MD_R; ++b) acc64[b] = 0.0;
+
+  for (long long a = a0; a < a1; ++a) {
+    const float* __restrict__ row = traj + (size_t)a * T * 3;
+    __syncthreads();
+    {
+      const float* __restrict__ src = row + (size_t)t_begin * 3;
+      for (int e = tid; e < 3 * len; e += MD_NT) {
+        const float v = __ldg(src + e);
+        const int t = e / 3, d = e - 3 * t;
+        if (d < 2) md_smem[2 * t + d] = v; else s_z[t] = v;
+      }
+      if (lag_blk0 > 0) {
+        const float* __restrict__ so = row + (size_t)(t0 + w0) * 3;
+        for (int e = tid; e < 3 * nw; e += MD_NT) {
+          const float v = __ldg(so + e);
+          const int t = e / 3, d = e - 3 * t;
+          if (d < 2) s_oxy[2 * t + d] = v; else s_oxy[2 * Wc + t] = v;
+        }
+      }
+    }
+    __syncthreads();
+    const float2* __restrict__ o_xy = lag_blk0 > 0 ? reinterpret_cast<const float2*>(s_oxy) : s_xy;
+    const float* __restrict__ o_z = lag_blk0 > 0 ? s_oxy + 2 * Wc : s_z;
+
+    float2 qxy[MD_R];
+    float qz[MD_R];
+#pragma unroll
+    for (int b = 0; b < MD_R; ++b) {
+      qxy[b] = s_xy[kR + b];
+      qz[b] = s_z[kR + b];
+    }
+    float2 axy[MD_R];
+    float az[MD_R];
+#pragma unroll
+    for (int b = 0; b < MD_R; ++b) {
+      axy[b] = make_float2(0.f, 0.f);
+      az[b] = 0.f;
+    }
+    int fold = 0;
+    for (int w = 0; w < nw; w += MD_R) {
+#pragma unroll
+      for (int s = 0; s < MD_R; ++s) {
+        const int ws = w + s;
+        if (ws < nw) {
+          const float2 oxy = o_xy[ws];
+          const float2 noxy = make_float2(-oxy.x, -oxy.y);
+          const float noz = -o_z[ws];
+#pragma unroll
+          for (int b = 0; b < MD_R; ++b) {
+            const int slot = (s + b) % MD_R;
+            const float2 d = __fadd2_rn(qxy[slot], noxy);
+            const float dz = qz[slot] + noz;
+            axy[b] = __ffma2_rn(d, d, axy[b]);
+            az[b] = fmaf(dz, dz, az[b]);
+          }
+          // slot s held frame ws + lag0: dead now; refill with frame ws + lag0 + MD_R
+          const int nx = min(ws + kR + MD_R, len_alloc - 1);
+          qxy[s] = s_xy[nx];
+          qz[s] = s_z[nx];
+        }
+      }
+      if (++fold == MD_FOLD) {
+        fold = 0;
+#pragma unroll
+        for (int b = 0; b < MD_R; ++b) {
+          acc64[b] += (double)((axy[b].x + axy[b].y) + az[b]);
+          axy[b] = make_float2(0.f, 0.f);
+          az[b] = 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < MD_R; ++b) acc64[b] += (double)((axy[b].x + axy[b].y) + az[b]);
+  }
+#pragma unroll
+  for (int b = 0; b < MD_R; ++b) {
+    const int k = lag0 + b;
+    if (k < n_lags) atomicAdd(msd_sum + k, acc64[b]);
   }
 }
 
@@ -158,6 +280,162 @@ acf_lagprod_kernel(const float* __restrict__ traj, long long T, long long a_lo, 
   }
 }
 
+// ---- Green-Kubo lag products, register-tiled band Gram kernel -------------------------------
+// P[t][t'-t] += sum_a sum_d v[a][t][d] * v[a][t'][d] for t <= t' < t + N: the band of the Gram
+// matrix of the (3A x B) velocity matrix.  A CTA owns a 64 x 64 tile of (t, t') and a slice of
+// the atoms; a thread owns 8 x 8 outputs (64 fp32 accumulators as 32 f32x2 pairs) so that one
+// atom costs 96 FFMA2 against 12 LDS.128.  Operands are staged per atom as SoA rows
+// [side][dim][64] by 4-byte cp.async (global layout is [A][T][3], so a (atom, 64 frames) slab is
+// 768 contiguous bytes) in a 3-stage ring.  fp32 accumulation runs over at most GB_FOLD atoms
+// (3 * GB_FOLD products), then folds into the global fp64 P with atomicAdd(double).
+constexpr int GB_T = 64;      // tile edge
+constexpr int GB_NT = 64;     // threads per CTA (2 warps)
+constexpr int GB_KA = 8;      // atoms per pipeline stage
+constexpr int GB_ST = 3;      // pipeline stages
+constexpr int GB_FOLD = 2048; // atoms per fp32 accumulation run
+constexpr int GB_SLAB = 2 * 3 * GB_T;  // floats per atom per stage (a side + b side)
+
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src, bool valid) {
+  const unsigned d = smem_u32(dst_smem);
+  const int sz = valid ? 4 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__global__ void __launch_bounds__(GB_NT, 8)
+acf_band_kernel(const float* __restrict__ traj, long long T, long long a_lo, long long a_hi,
+                int atoms_per_cta, long long t0, int B, int N, int nbj, double* __restrict__ P) {
+  extern __shared__ __align__(16) float gb_smem[];  // GB_ST * GB_KA * GB_SLAB floats
+  const int tid = threadIdx.x;
+  const int bi = blockIdx.x / nbj;
+  const int bj = bi + blockIdx.x % nbj;
+  const int ta0 = bi * GB_T, tb0 = bj * GB_T;  // tile origins (relative to t0)
+  if (tb0 >= B) return;
+  const long long a0 = a_lo + (long long)blockIdx.y * atoms_per_cta;
+  const long long a1 = min(a_hi, a0 + atoms_per_cta);
+  if (a0 >= a1) return;
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int li = lane >> 3, lj = lane & 7;
+  const int ra = 32 * warp + 4 * li;  // local a rows: ra + (i&3) + 16*(i>>2)
+  const int cb = 4 * lj;              // local b cols: cb + (j&3) + 32*(j>>2)
+
+  float2 acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+
+  // stage loader.  A stage holds GB_KA atoms x 2 sides x 192 floats; for one (atom, side) the
+  // 192 source floats are contiguous in global memory.  Thread tid copies the three elements
+  // q = tid, tid + 64, tid + 128 of every (atom, side) slab: their dim/frame split and smem
+  // offsets are per-thread constants.
+  int q_src[3], q_dst[3], q_t[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int q = c * GB_NT + tid;
+    q_t[c] = q / 3;
+    q_src[c] = q;
+    q_dst[c] = (q - 3 * q_t[c]) * GB_T + q_t[c];
+  }
+  bool ok_a[3], ok_b[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    ok_a[c] = ta0 + q_t[c] < B;
+    ok_b[c] = tb0 + q_t[c] < B;
+  }
+  const float* const src_a0 = traj + ((size_t)a0 * T + t0 + ta0) * 3;
+  const float* const src_b0 = traj + ((size_t)a0 * T + t0 + tb0) * 3;
+  const size_t row_stride = (size_t)T * 3;
+  auto load_stage = [&](long long a_first, int stage) {
+    float* dst = gb_smem + (size_t)stage * GB_KA * GB_SLAB;
+    const float* sa = src_a0 + (size_t)(a_first - a0) * row_stride;
+    const float* sb = src_b0 + (size_t)(a_first - a0) * row_stride;
+#pragma unroll 1
+    for (int ka = 0; ka < GB_KA; ++ka) {
+      const bool live = a_first + ka < a1;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const bool va = live && ok_a[c], vb = live && ok_b[c];
+        cp_async4(dst + q_dst[c], va ? sa + q_src[c] : src_a0, va);
+        cp_async4(dst + 3 * GB_T + q_dst[c], vb ? sb + q_src[c] : src_a0, vb);
+      }
+      dst += GB_SLAB;
+      sa += row_stride;
+      sb += row_stride;
+    }
+  };
+
+  auto flush = [&]() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ta = ta0 + ra + (i & 3) + 16 * (i >> 2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int tb = tb0 + cb + (j & 3) + 32 * (j >> 2);
+        const int m = tb - ta;
+        const float v = (j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x;
+        if (ta < B && tb < B && m >= 0 && m < N) atomicAdd(P + (size_t)ta * N + m, (double)v);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+  };
+
+  const int n_stage_total = (int)((a1 - a0 + GB_KA - 1) / GB_KA);
+  // prologue
+#pragma unroll
+  for (int s = 0; s < GB_ST - 1; ++s) {
+    if (s < n_stage_total) load_stage(a0 + (long long)s * GB_KA, s);
+    cp_async_commit();
+  }
+  int since_fold = 0;
+  for (int st = 0; st < n_stage_total; ++st) {
+    cp_async_wait<GB_ST - 2>();
+    __syncthreads();
+    {
+      const int nxt = st + GB_ST - 1;
+      if (nxt < n_stage_total) load_stage(a0 + (long long)nxt * GB_KA, nxt % GB_ST);
+      cp_async_commit();
+    }
+    const float* sbase = gb_smem + (size_t)(st % GB_ST) * GB_KA * GB_SLAB;
+#pragma unroll 2
+    for (int ka = 0; ka < GB_KA; ++ka) {
+      const float* sa = sbase + ka * GB_SLAB;
+      const float* sb = sa + 3 * GB_T;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float4 a_lo4 = *reinterpret_cast<const float4*>(sa + d * GB_T + ra);
+        const float4 a_hi4 = *reinterpret_cast<const float4*>(sa + d * GB_T + ra + 16);
+        const float4 b_lo4 = *reinterpret_cast<const float4*>(sb + d * GB_T + cb);
+        const float4 b_hi4 = *reinterpret_cast<const float4*>(sb + d * GB_T + cb + 32);
+        const float av[8] = {a_lo4.x, a_lo4.y, a_lo4.z, a_lo4.w, a_hi4.x, a_hi4.y, a_hi4.z, a_hi4.w};
+        const float2 bv[4] = {make_float2(b_lo4.x, b_lo4.y), make_float2(b_lo4.z, b_lo4.w),
+                              make_float2(b_hi4.x, b_hi4.y), make_float2(b_hi4.z, b_hi4.w)};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 a2 = make_float2(av[i], av[i]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(a2, bv[j], acc[i][j]);
+        }
+      }
+    }
+    since_fold += GB_KA;
+    if (since_fold >= GB_FOLD) {
+      flush();
+      since_fold = 0;
+    }
+  }
+  cp_async_wait<0>();
+  flush();
+}
+
 // ---- prefix sum of P along t (in place, inclusive), 8 lags x 128 time chunks per CTA -----
 constexpr int SCAN_M = 8;
 constexpr int SCAN_C = 128;
@@ -210,9 +488,9 @@ acf_windows_kernel(const double* __restrict__ C, int B, int N, int W, int ct,
   atomicAdd(acf_sum + m, tot);
 }
 
-static int pick_atoms_per_cta(long long n_atoms, long long chunks) {
-  // aim for ~8 CTAs per SM overall while keeping >= 1 atom per CTA
-  const long long target = (long long)sm_count() * 8;
+static int pick_atoms_per_cta(long long n_atoms, long long chunks, int ctas_per_sm = 8) {
+  // aim for ~ctas_per_sm CTAs per SM overall while keeping >= 1 atom per CTA
+  const long long target = (long long)sm_count() * ctas_per_sm;
   long long groups = (target + chunks - 1) / chunks;
   if (groups < 1) groups = 1;
   if (groups > n_atoms) groups = n_atoms;
@@ -258,6 +536,36 @@ extern "C" int mdk_msd_windowed(const float* traj, long long A, long long T, lon
   return MDK_OK;
 }
 
+extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long long a_lo,
+                             long long a_hi, long long t0, int W, int n_lags, double* msd_sum,
+                             mdk_stream_t stream) {
+  MDK_CHECK_ARG(traj && msd_sum, "msd_dense: null pointer");
+  MDK_CHECK_ARG(0 <= a_lo && a_lo <= a_hi && a_hi <= A, "msd_dense: bad atom range");
+  MDK_CHECK_ARG(W >= 0 && n_lags >= 1, "msd_dense: bad window spec");
+  if (W == 0 || a_lo == a_hi) return MDK_OK;
+  MDK_CHECK_ARG(t0 >= 0 && t0 + (long long)(W - 1) + n_lags <= T,
+                "msd_dense: windows [t0=%lld, W=%d, n_lags=%d] exceed T=%lld", t0, W, n_lags, T);
+  const int lag_span = MD_NT * MD_R;
+  const int lag_blocks = (n_lags + lag_span - 1) / lag_span;
+  const int Wc = W < 512 ? W : 512;
+  // every thread may read up to one ring refill past its last lag: size the tile for the full
+  // lag span of a block so that those (discarded) reads stay inside the allocation
+  const int len_alloc = (Wc + lag_span + MD_R + 3) & ~3;  // multiple of 4: float2 views stay aligned
+  const size_t smem = ((size_t)3 * len_alloc + (lag_blocks > 1 ? (size_t)3 * Wc : 0)) * sizeof(float);
+  const int chunks = (W + Wc - 1) / Wc;
+  // 64-thread CTAs: aim for several waves of ~11 resident CTAs per SM
+  const int apc = pick_atoms_per_cta(a_hi - a_lo, (long long)chunks * lag_blocks, 48);
+  const long long groups = (a_hi - a_lo + apc - 1) / apc;
+  MDK_CHECK_ARG(groups <= 65535 && lag_blocks <= 65535, "msd_dense: grid too large");
+  MDK_CUDA(cudaFuncSetAttribute(msd_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  dim3 grid(chunks, (unsigned)groups, lag_blocks);
+  msd_dense_kernel<<<grid, MD_NT, smem, as_stream(stream)>>>(traj, T, a_lo, a_hi, apc, t0, W,
+                                                             n_lags, Wc, len_alloc, msd_sum);
+  MDK_LAUNCH_CHECK();
+  return MDK_OK;
+}
+
 extern "C" int mdk_acf_lagprod(const float* traj, long long A, long long T, long long a_lo,
                                long long a_hi, long long t0, int B, int N, double* P,
                                mdk_stream_t stream) {
@@ -265,20 +573,44 @@ extern "C" int mdk_acf_lagprod(const float* traj, long long A, long long T, long
   MDK_CHECK_ARG(0 <= a_lo && a_lo <= a_hi && a_hi <= A, "acf_lagprod: bad atom range");
   MDK_CHECK_ARG(B >= 1 && N >= 1 && t0 >= 0 && t0 + B <= T, "acf_lagprod: bad frame range");
   if (a_lo == a_hi) return MDK_OK;
-  const size_t smem = (size_t)(ACF_TC + N - 1) * 12;
-  if (smem > 200 * 1024) {
-    set_error("acf_lagprod: data_range %d does not fit in shared memory", N);
-    return MDK_EUNSUPPORTED;
+  const long long n_atoms = a_hi - a_lo;
+  const char* legacy = getenv("MDK_ACF_LEGACY");
+  if (legacy && legacy[0] == '1') {
+    const size_t smem = (size_t)(ACF_TC + N - 1) * 12;
+    if (smem > 200 * 1024) {
+      set_error("acf_lagprod: data_range %d does not fit in shared memory", N);
+      return MDK_EUNSUPPORTED;
+    }
+    const int chunks = (B + ACF_TC - 1) / ACF_TC;
+    const int apc = pick_atoms_per_cta(n_atoms, chunks);
+    const long long groups = (n_atoms + apc - 1) / apc;
+    MDK_CHECK_ARG(groups <= 65535, "acf_lagprod: too many atom groups");
+    MDK_CUDA(cudaFuncSetAttribute(acf_lagprod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    dim3 grid(chunks, (unsigned)groups);
+    acf_lagprod_kernel<<<grid, DYN_NT, smem, as_stream(stream)>>>(traj, T, a_lo, a_hi, apc, t0, B,
+                                                                  N, P);
+    MDK_LAUNCH_CHECK();
+    return MDK_OK;
   }
-  const int chunks = (B + ACF_TC - 1) / ACF_TC;
-  const int apc = pick_atoms_per_cta(a_hi - a_lo, chunks);
-  const long long groups = (a_hi - a_lo + apc - 1) / apc;
-  MDK_CHECK_ARG(groups <= 65535, "acf_lagprod: too many atom groups");
-  MDK_CUDA(cudaFuncSetAttribute(acf_lagprod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  // band Gram kernel: tiles (bi, bi + dj), dj < nbj
+  const int n_bi = (B + GB_T - 1) / GB_T;
+  const int nbj = (GB_T - 1 + N - 1) / GB_T + 1;
+  const long long tiles = (long long)n_bi * nbj;
+  // atom split: enough CTAs to fill the machine several times over, at least GB_KA atoms each
+  long long want = ((long long)sm_count() * 24 + tiles - 1) / tiles;
+  if (want < 1) want = 1;
+  long long apc = (n_atoms + want - 1) / want;
+  if (apc < 64) apc = n_atoms < 64 ? n_atoms : 64;
+  apc = ((apc + GB_KA - 1) / GB_KA) * GB_KA;
+  const long long groups = (n_atoms + apc - 1) / apc;
+  MDK_CHECK_ARG(groups <= 65535 && tiles < (1ll << 31), "acf_lagprod: grid too large");
+  const size_t smem = (size_t)GB_ST * GB_KA * GB_SLAB * sizeof(float);
+  MDK_CUDA(cudaFuncSetAttribute(acf_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
-  dim3 grid(chunks, (unsigned)groups);
-  acf_lagprod_kernel<<<grid, DYN_NT, smem, as_stream(stream)>>>(traj, T, a_lo, a_hi, apc, t0, B, N,
-                                                                P);
+  dim3 grid((unsigned)tiles, (unsigned)groups);
+  acf_band_kernel<<<grid, GB_NT, smem, as_stream(stream)>>>(traj, T, a_lo, a_hi, (int)apc, t0, B, N,
+                                                            nbj, P);
   MDK_LAUNCH_CHECK();
   return MDK_OK;
 }

@@ -158,14 +158,17 @@ def msd_series(traj: torch.Tensor, launches, data_range: int, correlation_time: 
     [row_offset, row_offset + traj.shape[0]); ``a_shard`` = (lo, hi) restricts the atoms this
     rank processes (multi-GPU atom sharding).  count is always the full-plan count, computed
     analytically (einstein_diffusion_coefficients.py:184, :244)."""
-    tau = torch.as_tensor(np.asarray(tau_values, dtype=np.int32), device=traj.device)
+    tau_host = np.asarray(tau_values, dtype=np.int32)
+    dense = bool(np.array_equal(tau_host, np.arange(len(tau_host))))
+    tau = torch.as_tensor(tau_host, device=traj.device)
     out = torch.zeros(len(tau_values), dtype=torch.float64, device=traj.device)
     count = 0
     for a_lo, a_hi, t0, B, W in launches:
         count += W * ((a_hi - a_lo) + 1)
         lo, hi = _local_rows(a_lo, a_hi, a_shard, row_offset, traj.shape[0])
         if hi > lo:
-            K.msd_windowed(traj, lo, hi, t0, W, correlation_time, tau, data_range, out)
+            K.msd_windowed(traj, lo, hi, t0, W, correlation_time, tau, data_range, out,
+                           dense=dense)
     return out, count
 
 

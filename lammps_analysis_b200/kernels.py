@@ -190,7 +190,7 @@ def rdf_hist(pos_soa: torch.Tensor, n_frames: int, layout: RdfLayout, box, cutof
 # Einstein MSD / Green-Kubo ACF
 # --------------------------------------------------------------------------------------
 def msd_windowed(traj: torch.Tensor, a_lo: int, a_hi: int, t0: int, W: int, ct: int,
-                 tau_dev: torch.Tensor, span: int, msd_sum: torch.Tensor):
+                 tau_dev: torch.Tensor, span: int, msd_sum: torch.Tensor, dense: bool = False):
     """msd_sum[k] += sum over windows, atoms, dims of (x(s+tau_k) - x(s))^2.
 
     Replaces einstein_diffusion_coefficients.py:168-190 and the window loop :230-244.
@@ -201,6 +201,15 @@ def msd_windowed(traj: torch.Tensor, a_lo: int, a_hi: int, t0: int, W: int, ct: 
     A, T, D = traj.shape
     if D != 3 or msd_sum.numel() != tau_dev.numel():
         raise MdkError("msd_windowed: bad shapes")
+    if dense and ct == 1:
+        # tau = 0 .. n-1: register-ring kernel
+        check(
+            _lib.load().mdk_msd_dense(_ptr(traj), A, T, a_lo, a_hi, t0, W, tau_dev.numel(),
+                                      _ptr(msd_sum), _stream()),
+            "mdk_msd_dense",
+        )
+        _count()
+        return
     check(
         _lib.load().mdk_msd_windowed(_ptr(traj), A, T, a_lo, a_hi, t0, W, ct, _ptr(tau_dev),
                                      tau_dev.numel(), span, _ptr(msd_sum), _stream()),

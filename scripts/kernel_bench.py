@@ -83,6 +83,8 @@ def main():
         o = torch.zeros(N, dtype=torch.float64, device=dev)
         t = timed(lambda: K.msd_windowed(traj, 0, A, 0, W, 1, tau, N, o))
         upd = W * A * N
+        print(json.dumps({"msd_legacy_s": t, "updates_per_s": upd / t}), flush=True)
+        t = timed(lambda: K.msd_windowed(traj, 0, A, 0, W, 1, tau, N, o, dense=True))
         print(json.dumps({"msd_s": t, "updates_per_s": upd / t, "tflops9": 9 * upd / t * 1e-12,
                           "GBps": 12 * A * T / t * 1e-9}), flush=True)
     if "acf" in what:

@@ -124,6 +124,8 @@ def _plan(A, T, data_range, ct, memory=60e9, scale=150):
     (64, 400, 50, 1, 60e9),       # one batch
     (64, 400, 50, 3, 60e9),       # correlation_time > 1
     (60, 1000, 100, 1, 2.0e5 * 60 / 64),  # several batches + remainder
+    (9, 1500, 700, 1, 60e9),      # more lags than one lag block of the dense kernel (576)
+    (5, 700, 577, 1, 60e9),       # one lag into the second lag block; few windows
 ])
 def test_msd_matches_oracle(cuda, A, T, N, ct, memory):
     from lammps_analysis_b200.engine import msd_series, plan_windows, to_device_f32

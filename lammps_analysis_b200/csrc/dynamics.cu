@@ -293,7 +293,11 @@ constexpr int GB_NT = 64;     // threads per CTA (2 warps)
 constexpr int GB_KA = 8;      // atoms per pipeline stage
 constexpr int GB_ST = 3;      // pipeline stages
 constexpr int GB_FOLD = 2048; // atoms per fp32 accumulation run
-constexpr int GB_SLAB = 2 * 3 * GB_T;  // floats per atom per stage (a side + b side)
+constexpr int GB_ROW = GB_T + 12;        // padded SoA row: dims land 12 banks apart, so the
+                                        // 4-byte cp.async scatter (lane -> frame q/3, dim q%3) is
+                                        // (almost) conflict free; multiple of 4 for LDS.128
+constexpr int GB_SIDE = 3 * GB_ROW;      // floats per (atom, side)
+constexpr int GB_SLAB = 2 * GB_SIDE;     // floats per atom per stage (a side + b side)
 
 __device__ __forceinline__ void cp_async4(float* dst_smem, const float* src, bool valid) {
   const unsigned d = smem_u32(dst_smem);
@@ -340,7 +344,7 @@ acf_band_kernel(const float* __restrict__ traj, long long T, long long a_lo, lon
     const int q = c * GB_NT + tid;
     q_t[c] = q / 3;
     q_src[c] = q;
-    q_dst[c] = (q - 3 * q_t[c]) * GB_T + q_t[c];
+    q_dst[c] = (q - 3 * q_t[c]) * GB_ROW + q_t[c];
   }
   bool ok_a[3], ok_b[3];
 #pragma unroll
@@ -362,7 +366,7 @@ acf_band_kernel(const float* __restrict__ traj, long long T, long long a_lo, lon
       for (int c = 0; c < 3; ++c) {
         const bool va = live && ok_a[c], vb = live && ok_b[c];
         cp_async4(dst + q_dst[c], va ? sa + q_src[c] : src_a0, va);
-        cp_async4(dst + 3 * GB_T + q_dst[c], vb ? sb + q_src[c] : src_a0, vb);
+        cp_async4(dst + GB_SIDE + q_dst[c], vb ? sb + q_src[c] : src_a0, vb);
       }
       dst += GB_SLAB;
       sa += row_stride;
@@ -408,13 +412,13 @@ acf_band_kernel(const float* __restrict__ traj, long long T, long long a_lo, lon
 #pragma unroll 2
     for (int ka = 0; ka < GB_KA; ++ka) {
       const float* sa = sbase + ka * GB_SLAB;
-      const float* sb = sa + 3 * GB_T;
+      const float* sb = sa + GB_SIDE;
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        const float4 a_lo4 = *reinterpret_cast<const float4*>(sa + d * GB_T + ra);
-        const float4 a_hi4 = *reinterpret_cast<const float4*>(sa + d * GB_T + ra + 16);
-        const float4 b_lo4 = *reinterpret_cast<const float4*>(sb + d * GB_T + cb);
-        const float4 b_hi4 = *reinterpret_cast<const float4*>(sb + d * GB_T + cb + 32);
+        const float4 a_lo4 = *reinterpret_cast<const float4*>(sa + d * GB_ROW + ra);
+        const float4 a_hi4 = *reinterpret_cast<const float4*>(sa + d * GB_ROW + ra + 16);
+        const float4 b_lo4 = *reinterpret_cast<const float4*>(sb + d * GB_ROW + cb);
+        const float4 b_hi4 = *reinterpret_cast<const float4*>(sb + d * GB_ROW + cb + 32);
         const float av[8] = {a_lo4.x, a_lo4.y, a_lo4.z, a_lo4.w, a_hi4.x, a_hi4.y, a_hi4.z, a_hi4.w};
         const float2 bv[4] = {make_float2(b_lo4.x, b_lo4.y), make_float2(b_lo4.z, b_lo4.w),
                               make_float2(b_hi4.x, b_hi4.y), make_float2(b_hi4.z, b_hi4.w)};

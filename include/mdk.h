@@ -33,6 +33,7 @@ extern "C" {
 #define MDK_EUNSUPPORTED -3 /* valid request outside what the kernels support */
 
 #define MDK_MAX_SPECIES 8
+#define MDK_RDF_SUBTILE 64 /* atoms per bounding box of mdk_rdf_bbox */
 
 /* flags for mdk_rdf_hist */
 #define MDK_RDF_EXACT_DIV 1 /* true fp32 division + separate mul/sub in the minimum image
@@ -92,6 +93,7 @@ int mdk_coord_extent(const float* pos_soa, int n_frames, long long n_pad, float*
  *   hist    : device u64 [n_pairs][nbins], pair order = combinations_with_replacement
  *             (0,0),(0,1),...,(1,1),... ; accumulated (+=)
  *   work_counter : device scratch, 8 bytes, 8-byte aligned; zeroed by the call
+ *   bbox    : NULL, or the tile boxes from mdk_rdf_bbox (enables block culling)
  * Pairs counted: i < j within a species block, all (i, j) across blocks, for each
  * frame: r = p_j - p_i; r -= rint(r / L) * L; d2 = (x*x + y*y) + z*z (fp32, each op
  * rounded); counted iff sqrt(d2) < cutoff.
@@ -100,7 +102,26 @@ int mdk_coord_extent(const float* pos_soa, int n_frames, long long n_pad, float*
 int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad, const int* sp_lo,
                  const int* sp_hi, int n_species, const float* box, float cut2, float cutoff,
                  int nbins, const float* thr, unsigned long long* hist,
-                 unsigned int* work_counter, int flags, mdk_stream_t stream);
+                 unsigned int* work_counter, const float* bbox, int flags, mdk_stream_t stream);
+
+/* Spatially ordered variant of mdk_rdf_pack for ONE frame of one species: the atoms are written
+ * in Hilbert-curve order of a 128^3 cell grid (the histogram does not depend on the order of the atoms
+ * inside a species block), NaN padded as above.  `workspace` is device scratch of at least
+ * mdk_rdf_sort_workspace(atom_count) bytes; box is a HOST float[3].
+ *   out_frame : [3][n_pad] fp32 (the frame's slab of the packed array) */
+long long mdk_rdf_sort_workspace(int max_atoms);
+int mdk_rdf_pack_sorted(const float* traj, long long A_total, long long T, long long atom_first,
+                        int atom_count, long long frame, float* out_frame, long long n_pad,
+                        long long dst_first, int dst_span, const float* box, void* workspace,
+                        long long workspace_bytes, mdk_stream_t stream);
+
+/* Bounding boxes {min xyz, max xyz} of every MDK_RDF_SUBTILE-atom run of a packed frame array
+ * (NaN padding ignored): bbox device float [n_frames][n_pad / MDK_RDF_SUBTILE][6].  Passed to
+ * mdk_rdf_hist they let the kernel skip (row group, column sub-tile) blocks whose minimum-image
+ * box distance exceeds the cutoff -- the counts are unchanged, only provably empty blocks are
+ * skipped. */
+int mdk_rdf_bbox(const float* pos_soa, int n_frames, long long n_pad, float* bbox,
+                 mdk_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
  * Einstein MSD / Green-Kubo ACF

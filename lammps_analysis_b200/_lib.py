@@ -36,7 +36,10 @@ PROTOTYPES = {
     "mdk_rdf_thresholds": [_F, _I, _P, _P],
     "mdk_rdf_pack": [_P, _LL, _LL, _LL, _LL, _P, _I, _P, _LL, _LL, _LL, _P],
     "mdk_coord_extent": [_P, _I, _LL, _P, _P],
-    "mdk_rdf_hist": [_P, _I, _LL, _P, _P, _I, _P, _F, _F, _I, _P, _P, _P, _I, _P],
+    "mdk_rdf_hist": [_P, _I, _LL, _P, _P, _I, _P, _F, _F, _I, _P, _P, _P, _P, _I, _P],
+    "mdk_rdf_sort_workspace": [_I],
+    "mdk_rdf_pack_sorted": [_P, _LL, _LL, _LL, _I, _LL, _P, _LL, _LL, _I, _P, _P, _LL, _P],
+    "mdk_rdf_bbox": [_P, _I, _LL, _P, _P],
     "mdk_msd_windowed": [_P, _LL, _LL, _LL, _LL, _LL, _I, _I, _P, _I, _I, _P, _P],
     "mdk_msd_dense": [_P, _LL, _LL, _LL, _LL, _LL, _I, _I, _P, _P],
     "mdk_acf_lagprod": [_P, _LL, _LL, _LL, _LL, _LL, _I, _I, _P, _P],
@@ -62,7 +65,7 @@ def load():
     for name, argtypes in PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.argtypes = argtypes
-        fn.restype = _I
+        fn.restype = _LL if name == "mdk_rdf_sort_workspace" else _I
     lib.mdk_last_error.argtypes = []
     lib.mdk_last_error.restype = C.c_char_p
     _lib = lib

@@ -28,6 +28,8 @@
 namespace mdk {
 
 constexpr int TJ = 256;  // column tile (atoms) == padding granule of species blocks
+constexpr int SUB = MDK_RDF_SUBTILE;  // atoms per bounding box (culling granule)
+constexpr int NSUB = TJ / SUB;
 constexpr int MAX_PAIRS = MDK_MAX_SPECIES * (MDK_MAX_SPECIES + 1) / 2;
 constexpr float RINT_MAGIC = 12582912.0f;         // 1.5 * 2^23: ulp == 1, even
 constexpr unsigned RINT_MAGIC_BITS = 0x4B400000u; // __float_as_uint(RINT_MAGIC)
@@ -59,7 +61,40 @@ struct RdfParams {
   unsigned long long* counter;   // dynamic work counter
   unsigned int flush_tiles;      // flush after this many column tiles (u32 overflow guard)
   unsigned int one;              // == 1, kept opaque to the compiler (see bin_two)
+  // culling (optional): per (frame, 256-atom tile) bounding boxes {min xyz, max xyz}
+  const float* bbox;             // [F][boxes_per_frame][6] (one per SUB atoms) or nullptr
+  int boxes_per_frame;
+  float cull2;                   // squared distance beyond which a block cannot hold a pair
+  float cull_eps[3];             // absolute slack per dimension for the box arithmetic
 };
+
+__device__ __forceinline__ void box_union(float (&acc)[6], const float* __restrict__ b) {
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    acc[d] = fminf(acc[d], __ldg(b + d));
+    acc[d + 3] = fmaxf(acc[d + 3], __ldg(b + d + 3));
+  }
+}
+
+// Conservative test: can any pair (p in box a, q in box b) have a minimum-image distance below
+// sqrt(cull2)?  Along one dimension |p - q| lies in [lo, hi] = [dc - h, dc + h] (dc = distance
+// of the centres, h = sum of the half widths), and the minimum image of a value v in [0, L) is
+// min(v, L - v) >= min(lo, L - hi); when hi >= L the bound is <= 0 and nothing is culled, so the
+// test is safe for any coordinates.  Returns true when the block can be skipped.
+__device__ __forceinline__ bool boxes_far(const float (&a)[6], const float* __restrict__ b,
+                                          const float (&L)[3], const float (&eps)[3],
+                                          float cull2) {
+  if (!(b[0] <= b[3])) return true;  // empty tile (padding only): nothing to count
+  float g2 = 0.f;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float dc = fabsf(0.5f * (a[d] + a[d + 3]) - 0.5f * (b[d] + b[d + 3]));
+    const float h = 0.5f * (a[d + 3] - a[d]) + 0.5f * (b[d + 3] - b[d]) + eps[d];
+    const float g = fmaxf(fminf(dc - h, L[d] - (dc + h)), 0.f);
+    g2 = fmaf(g, g, g2);
+  }
+  return g2 > cull2;
+}
 
 __device__ __forceinline__ float sqrt_approx(float x) {
   float y;
@@ -118,8 +153,6 @@ __device__ __forceinline__ void bin_two(float2 d2, float cut2, float2 inv_step2,
   "@p1 ld.shared.f32 g1, [a1];\n"                      \
   "setp.lt.f32 q0, %0, g0;\n"                          \
   "setp.lt.f32 q1, %1, g1;\n"                          \
-  "add.u32 a0, a0, %6;\n"                              \
-  "add.u32 a1, a1, %6;\n"                              \
   "@q0 add.u32 a0, a0, -4;\n"                          \
   "@q1 add.u32 a1, a1, -4;\n"
 #define MDK_BIN_ARGS                                                                        \
@@ -127,6 +160,8 @@ __device__ __forceinline__ void bin_two(float2 d2, float cut2, float2 inv_step2,
       "l"(0x4B4000004B400000ull), "r"(thr_c), "r"(delta), "r"(one), "r"(dump)
   if (AM == 0) {
     asm volatile(MDK_BIN_HEAD
+                 "add.u32 a0, a0, %6;\n"
+                 "add.u32 a1, a1, %6;\n"
                  "@p0 red.shared.add.u32 [a0], %7;\n"
                  "@p1 red.shared.add.u32 [a1], %7;\n"
                  "}\n" ::MDK_BIN_ARGS
@@ -135,6 +170,8 @@ __device__ __forceinline__ void bin_two(float2 d2, float cut2, float2 inv_step2,
     asm volatile(MDK_BIN_HEAD
                  "selp.u32 a0, a0, %8, p0;\n"
                  "selp.u32 a1, a1, %8, p1;\n"
+                 "add.u32 a0, a0, %6;\n"
+                 "add.u32 a1, a1, %6;\n"
                  "red.shared.add.u32 [a0], %7;\n"
                  "red.shared.add.u32 [a1], %7;\n"
                  "}\n" ::MDK_BIN_ARGS
@@ -143,6 +180,8 @@ __device__ __forceinline__ void bin_two(float2 d2, float cut2, float2 inv_step2,
     asm volatile(MDK_BIN_HEAD
                  "selp.u32 a0, a0, %8, p0;\n"
                  "selp.u32 a1, a1, %8, p1;\n"
+                 "add.u32 a0, a0, %6;\n"
+                 "add.u32 a1, a1, %6;\n"
                  "red.shared.add.u32 [a0], 1;\n"
                  "red.shared.add.u32 [a1], 1;\n"
                  "}\n" ::MDK_BIN_ARGS
@@ -167,7 +206,7 @@ __device__ __forceinline__ void flush_hist(unsigned int* s_cnt, int nbins,
   __syncthreads();
 }
 
-template <int NT, int R, bool EXACT, int AM>
+template <int NT, int R, bool EXACT, int AM, bool CULL>
 __global__ void __launch_bounds__(NT) rdf_pair_hist_kernel(const __grid_constant__ RdfParams P) {
   constexpr int TI = NT * R;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -200,7 +239,8 @@ __global__ void __launch_bounds__(NT) rdf_pair_hist_kernel(const __grid_constant
   const uint32_t thr_c = smem_u32(s_thr) - 4u * RINT_MAGIC_BITS;
   const uint32_t cnt_delta = smem_u32(s_cnt) - smem_u32(s_thr);
   const uint32_t one = P.one;
-  const uint32_t dump = smem_u32(s_cnt) + 4u * ((P.nbins + 31) & ~31) + 4u * (tid & 31);
+  // dump slot of this lane, expressed relative to the thr table (bin_two adds cnt_delta)
+  const uint32_t dump = smem_u32(s_thr) + 4u * ((P.nbins + 31) & ~31) + 4u * (tid & 31);
   const float2 magic2 = make_float2(RINT_MAGIC, RINT_MAGIC);
   const float2 nmagic2 = make_float2(-RINT_MAGIC, -RINT_MAGIC);
   const float2 invLx = make_float2(P.inv_box[0], P.inv_box[0]);
@@ -250,7 +290,9 @@ __global__ void __launch_bounds__(NT) rdf_pair_hist_kernel(const __grid_constant
     int irow[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int i = row_base + r * NT + tid;
+      // a warp owns 32*R consecutive rows (R groups of 32): consecutive atoms are spatial
+      // neighbours after the Hilbert ordering, so the R culling masks of a warp mostly agree
+      const int i = row_base + ((tid >> 5) * R + r) * 32 + (tid & 31);
       irow[r] = i;
       float x = __int_as_float(0x7fc00000), y = x, z = x;  // NaN rows never pass d2 < cut2
       if (i < P.sp_hi[a]) {
@@ -263,6 +305,44 @@ __global__ void __launch_bounds__(NT) rdf_pair_hist_kernel(const __grid_constant
       nzi[r] = make_float2(-z, -z);
     }
 
+    // ---- bounding boxes of this row tile (CTA) and of each warp's 32-row groups -----------
+    constexpr bool cull = CULL;  // P.bbox != nullptr
+    const float* __restrict__ fbox = P.bbox + (size_t)f * P.boxes_per_frame * 6;
+    float rbox[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    float wbox[R][6];
+    if constexpr (CULL) {
+      const int r_last = min(row_base + TI, P.sp_hi[a]);  // exclusive row bound
+      for (int t = row_base / SUB; t * SUB < r_last; ++t) box_union(rbox, fbox + (size_t)t * 6);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float c[3] = {-nxi[r].x, -nyi[r].x, -nzi[r].x};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          float mn = c[d] == c[d] ? c[d] : INFINITY;
+          float mx = c[d] == c[d] ? c[d] : -INFINITY;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          }
+          wbox[r][d] = mn;
+          wbox[r][d + 3] = mx;
+        }
+      }
+    }
+    const int col_box0 = P.sp_lo[b] / SUB;  // index of the first column box in the frame table
+    auto tile_far = [&](int jt) {
+      float cb6[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int q = 0; q < NSUB; ++q) box_union(cb6, fbox + (size_t)(col_box0 + jt * NSUB + q) * 6);
+      return boxes_far(rbox, cb6, P.box, P.cull_eps, P.cull2);
+    };
+    auto next_live = [&](int jt) {
+      if constexpr (CULL)
+        while (jt < j_tile1 && tile_far(jt)) ++jt;
+      return jt;
+    };
+
     // ---- column tiles: TMA double buffer ------------------------------------------------
     const int col_base = P.sp_lo[b];
     auto issue = [&](int jt, int stage) {
@@ -273,13 +353,15 @@ __global__ void __launch_bounds__(NT) rdf_pair_hist_kernel(const __grid_constant
       bulk_g2s(dst + TJ, fy + off, TJ * sizeof(float), &s_bar[stage]);
       bulk_g2s(dst + 2 * TJ, fz + off, TJ * sizeof(float), &s_bar[stage]);
     };
+    int jt = next_live(j_tile0);
+    if (jt >= j_tile1) continue;  // every column tile of this item is out of range
+    int jn = next_live(jt + 1);
     if (tid == 0) {
-      issue(j_tile0, 0);
-      if (j_tile0 + 1 < j_tile1) issue(j_tile0 + 1, 1);
+      issue(jt, 0);
+      if (jn < j_tile1) issue(jn, 1);
     }
 
-    for (int jt = j_tile0; jt < j_tile1; ++jt) {
-      const int stage = (jt - j_tile0) & 1;
+    for (int stage = 0; jt < j_tile1; stage ^= 1) {
       mbar_wait(&s_bar[stage], phase[stage]);
       phase[stage] ^= 1u;
       const float* __restrict__ sx = s_tile + stage * 3 * TJ;
@@ -288,36 +370,84 @@ __global__ void __launch_bounds__(NT) rdf_pair_hist_kernel(const __grid_constant
       const int j0 = col_base + jt * TJ;
       const bool diag = same && (j0 < row_base + TI);  // tile overlaps this row tile
 
-      if (!EXACT && !diag) {
-#pragma unroll 2
-        for (int jj = 0; jj < TJ; jj += 2) {
-          const float2 xj = *reinterpret_cast<const float2*>(sx + jj);
-          const float2 yj = *reinterpret_cast<const float2*>(sy + jj);
-          const float2 zj = *reinterpret_cast<const float2*>(sz + jj);
+      // which of this warp's row groups can reach which 64-atom sub-tile: bit (q * R + r)
+      unsigned rmask = 0xffffffffu;
+      if (CULL && !diag) {
+        rmask = 0u;
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const float2 dx = __fadd2_rn(xj, nxi[r]);
-            const float2 dy = __fadd2_rn(yj, nyi[r]);
-            const float2 dz = __fadd2_rn(zj, nzi[r]);
-            const float2 tx = __ffma2_rn(dx, invLx, magic2);
-            const float2 ty = __ffma2_rn(dy, invLy, magic2);
-            const float2 tz = __ffma2_rn(dz, invLz, magic2);
-            const float2 nx = __fadd2_rn(tx, nmagic2);
-            const float2 ny = __fadd2_rn(ty, nmagic2);
-            const float2 nz = __fadd2_rn(tz, nmagic2);
-            const float2 rx = __ffma2_rn(nx, nLx, dx);
-            const float2 ry = __ffma2_rn(ny, nLy, dy);
-            const float2 rz = __ffma2_rn(nz, nLz, dz);
-            // squares packed; the two adds stay scalar: ptxas 12.9 contracts
-            // mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would break the reference's
-            // rounding sequence (x*x + y*y) + z*z.
-            const float2 xx = __fmul2_rn(rx, rx);
-            const float2 yy = __fmul2_rn(ry, ry);
-            const float2 zz = __fmul2_rn(rz, rz);
-            float2 d2;
-            d2.x = __fadd_rn(__fadd_rn(xx.x, yy.x), zz.x);
-            d2.y = __fadd_rn(__fadd_rn(xx.y, yy.y), zz.y);
-            bin_two<AM>(d2, cut2, inv_step2, thr_c, cnt_delta, one, dump);
+        for (int q = 0; q < NSUB; ++q) {
+          const float* __restrict__ cb6 = fbox + (size_t)(col_box0 + jt * NSUB + q) * 6;
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if (!boxes_far(wbox[r], cb6, P.box, P.cull_eps, P.cull2)) rmask |= 1u << (q * R + r);
+        }
+      }
+
+      if (!EXACT && !diag) {
+        constexpr unsigned FULL = (1u << R) - 1u;
+        for (int q = 0; q < NSUB; ++q) {
+          const unsigned m = (rmask >> (q * R)) & FULL;
+          if (m == FULL) {
+#pragma unroll 2
+            for (int jj = q * SUB; jj < (q + 1) * SUB; jj += 2) {
+              const float2 xj = *reinterpret_cast<const float2*>(sx + jj);
+              const float2 yj = *reinterpret_cast<const float2*>(sy + jj);
+              const float2 zj = *reinterpret_cast<const float2*>(sz + jj);
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                const float2 dx = __fadd2_rn(xj, nxi[r]);
+                const float2 dy = __fadd2_rn(yj, nyi[r]);
+                const float2 dz = __fadd2_rn(zj, nzi[r]);
+                const float2 tx = __ffma2_rn(dx, invLx, magic2);
+                const float2 ty = __ffma2_rn(dy, invLy, magic2);
+                const float2 tz = __ffma2_rn(dz, invLz, magic2);
+                const float2 nx = __fadd2_rn(tx, nmagic2);
+                const float2 ny = __fadd2_rn(ty, nmagic2);
+                const float2 nz = __fadd2_rn(tz, nmagic2);
+                const float2 rx = __ffma2_rn(nx, nLx, dx);
+                const float2 ry = __ffma2_rn(ny, nLy, dy);
+                const float2 rz = __ffma2_rn(nz, nLz, dz);
+                // squares packed; the two adds stay scalar: ptxas 12.9 contracts
+                // mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would break the reference's
+                // rounding sequence (x*x + y*y) + z*z.
+                const float2 xx = __fmul2_rn(rx, rx);
+                const float2 yy = __fmul2_rn(ry, ry);
+                const float2 zz = __fmul2_rn(rz, rz);
+                float2 d2;
+                d2.x = __fadd_rn(__fadd_rn(xx.x, yy.x), zz.x);
+                d2.y = __fadd_rn(__fadd_rn(xx.y, yy.y), zz.y);
+                bin_two<AM>(d2, cut2, inv_step2, thr_c, cnt_delta, one, dump);
+              }
+            }
+          } else if (m != 0u) {
+            // some row groups of this warp are provably out of range of this sub-tile: same
+            // arithmetic, the (warp-uniform) mask skips them
+            for (int jj = q * SUB; jj < (q + 1) * SUB; jj += 2) {
+              const float2 xj = *reinterpret_cast<const float2*>(sx + jj);
+              const float2 yj = *reinterpret_cast<const float2*>(sy + jj);
+              const float2 zj = *reinterpret_cast<const float2*>(sz + jj);
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                if ((m >> r) & 1u) {
+                  const float2 dx = __fadd2_rn(xj, nxi[r]);
+                  const float2 dy = __fadd2_rn(yj, nyi[r]);
+                  const float2 dz = __fadd2_rn(zj, nzi[r]);
+                  const float2 nx = __fadd2_rn(__ffma2_rn(dx, invLx, magic2), nmagic2);
+                  const float2 ny = __fadd2_rn(__ffma2_rn(dy, invLy, magic2), nmagic2);
+                  const float2 nz = __fadd2_rn(__ffma2_rn(dz, invLz, magic2), nmagic2);
+                  const float2 rx = __ffma2_rn(nx, nLx, dx);
+                  const float2 ry = __ffma2_rn(ny, nLy, dy);
+                  const float2 rz = __ffma2_rn(nz, nLz, dz);
+                  const float2 xx = __fmul2_rn(rx, rx);
+                  const float2 yy = __fmul2_rn(ry, ry);
+                  const float2 zz = __fmul2_rn(rz, rz);
+                  float2 d2;
+                  d2.x = __fadd_rn(__fadd_rn(xx.x, yy.x), zz.x);
+                  d2.y = __fadd_rn(__fadd_rn(xx.y, yy.y), zz.y);
+                  bin_two<AM>(d2, cut2, inv_step2, thr_c, cnt_delta, one, dump);
+                }
+              }
+            }
           }
         }
       } else {
@@ -350,7 +480,10 @@ __global__ void __launch_bounds__(NT) rdf_pair_hist_kernel(const __grid_constant
         }
       }
       __syncthreads();  // everyone is done reading this stage
-      if (tid == 0 && jt + 2 < j_tile1) issue(jt + 2, stage);
+      const int jnn = jn < j_tile1 ? next_live(jn + 1) : j_tile1;
+      if (tid == 0 && jnn < j_tile1) issue(jnn, stage);
+      jt = jn;
+      jn = jnn;
       if (++tiles_since_flush >= P.flush_tiles) {
         flush_hist<NT>(s_cnt, P.nbins, P.hist + (size_t)cur_pair * P.nbins);
         tiles_since_flush = 0;
@@ -431,9 +564,9 @@ __global__ void coord_extent_kernel(const float* __restrict__ pos, long long n_p
   }
 }
 
-template <int NT, int R, bool EXACT, int AM>
+template <int NT, int R, bool EXACT, int AM, bool CULL>
 int launch_rdf(const RdfParams& P, size_t smem, int grid, cudaStream_t s) {
-  auto kern = rdf_pair_hist_kernel<NT, R, EXACT, AM>;
+  auto kern = rdf_pair_hist_kernel<NT, R, EXACT, AM, CULL>;
   MDK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, NT, smem, s>>>(P);
   MDK_LAUNCH_CHECK();
@@ -442,11 +575,12 @@ int launch_rdf(const RdfParams& P, size_t smem, int grid, cudaStream_t s) {
 
 template <int NT, int R>
 int launch_rdf_cfg(const RdfParams& P, size_t smem, int grid, cudaStream_t s, bool exact, int am) {
-  if (exact) return launch_rdf<NT, R, true, 0>(P, smem, grid, s);
+  if (exact) return launch_rdf<NT, R, true, 0, false>(P, smem, grid, s);
+  if (P.bbox) return launch_rdf<NT, R, false, 2, true>(P, smem, grid, s);  // culling: AM 2 only
   switch (am) {
-    case 0: return launch_rdf<NT, R, false, 0>(P, smem, grid, s);
-    case 1: return launch_rdf<NT, R, false, 1>(P, smem, grid, s);
-    default: return launch_rdf<NT, R, false, 2>(P, smem, grid, s);
+    case 0: return launch_rdf<NT, R, false, 0, false>(P, smem, grid, s);
+    case 1: return launch_rdf<NT, R, false, 1, false>(P, smem, grid, s);
+    default: return launch_rdf<NT, R, false, 2, false>(P, smem, grid, s);
   }
 }
 
@@ -532,7 +666,8 @@ extern "C" int mdk_coord_extent(const float* pos_soa, int n_frames, long long n_
 extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad, const int* sp_lo,
                             const int* sp_hi, int n_species, const float* box, float cut2,
                             float cutoff, int nbins, const float* thr, unsigned long long* hist,
-                            unsigned int* work_counter, int flags, mdk_stream_t stream) {
+                            unsigned int* work_counter, const float* bbox, int flags,
+                            mdk_stream_t stream) {
   MDK_CHECK_ARG(pos_soa && sp_lo && sp_hi && box && thr && hist && work_counter,
                 "rdf_hist: null pointer");
   MDK_CHECK_ARG(n_species >= 1 && n_species <= MDK_MAX_SPECIES,
@@ -635,6 +770,11 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
   // u32 private counters: flush before a bin could overflow (TI * TJ pairs per tile)
   P.flush_tiles = (unsigned)((1ull << 31) / ((unsigned long long)TI * TJ));
   P.one = 1u;
+  P.bbox = exact ? nullptr : bbox;  // culling only on the fast minimum-image path
+  P.boxes_per_frame = (int)(n_pad / SUB);
+  P.cull2 = cut2 * 1.0001f;
+  for (int d = 0; d < 3; ++d) P.cull_eps[d] = 1e-5f * box[d];
+  MDK_CHECK_ARG(!bbox || n_pad % TJ == 0, "rdf_hist: bbox needs n_pad to be a multiple of %d", TJ);
 
   MDK_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s));
   switch (cfg) {

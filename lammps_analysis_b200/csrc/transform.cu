@@ -12,110 +12,191 @@
 namespace mdk {
 
 // One warp per atom; each lane owns one frame of a 32-frame chunk.  The jump count is an
-// inclusive warp scan per dimension, the running image is carried across chunks in fp64.
-// jump = rint((p_t - p_{t-1}) / L) is decided in fp32 when the quotient is clearly away
-// from a half-integer and recomputed exactly as the reference does (fp64 division,
-// half-to-even) otherwise.
-__device__ __forceinline__ int jump_of(float p, float prev, float inv_l32, double l64) {
+// inclusive warp scan per dimension, the running image is carried across chunks and batches.
+// jump = rint((p_t - p_{t-1}) / L) is decided in fp32 (magic-number rounding, no conversion
+// instructions) when the quotient is clearly away from a half-integer and recomputed exactly as
+// the reference does (fp64 division, half-to-even) otherwise.  Jumps and images are small
+// integers and are kept as floats (exact below 2^24), so the scan needs no int<->float
+// conversions; the conversion (XU) pipe was the limiter of the first version of this kernel.
+// Output: fl32(double(p) + img * L) -- with a single fp32 FMA when L is exactly representable in
+// fp32 (then fmaf rounds the exact sum once, which is the same value), and skipped entirely
+// while the image is zero.
+__device__ __forceinline__ float jump_of(float p, float prev, float inv_l32, double l64) {
   const float q = (p - prev) * inv_l32;
-  const float n = rintf(q);
+  const float n = __fadd_rn(__fadd_rn(q, 12582912.0f), -12582912.0f);  // rint for |q| < 2^22
   if (fabsf(fabsf(q - n) - 0.5f) < 1e-3f || !(fabsf(q) < 1000.f)) {
     const double qq = ((double)p - (double)prev) / l64;
-    return (int)rint(qq);
+    return (float)rint(qq);
   }
-  return (int)n;
+  return n;
 }
 
-__global__ void __launch_bounds__(256)
+template <bool L32>
+__device__ __forceinline__ float shifted(float x, float m, double l64, float l32) {
+  if (m == 0.f) return x;
+  if (L32) return fmaf(m, l32, x);
+  return __double2float_rn(__dadd_rn((double)x, __dmul_rn((double)m, l64)));
+}
+
+constexpr int UNW_F = 4;    // frames per lane and chunk: a warp moves 128 frames = 1536 contiguous bytes
+constexpr int UNW_PF = 2;   // chunks kept in flight in registers
+constexpr int UNW_CH = 32 * UNW_F;        // frames per chunk
+constexpr int UNW_SLAB = 3 * UNW_CH;      // floats per chunk
+constexpr int UNW_WARPS = 4;
+
+// One warp per atom.  The warp streams the atom's row in chunks of 128 frames: the 384 floats are
+// read (and later written) as three fully coalesced 512-byte LDG.128/STG.128 rows and
+// re-distributed through a per-warp shared-memory slab so that lane l owns the 4 consecutive
+// frames 4l .. 4l+3.  Jumps are scanned inside the lane, then across the warp.
+template <bool L32, bool VEC>
+__global__ void __launch_bounds__(32 * UNW_WARPS)
 unwrap_kernel(const float* __restrict__ pos, long long A, long long T, double lx, double ly,
               double lz, float* __restrict__ carry_pos, int have_carry,
               double* __restrict__ carry_img, float* __restrict__ out) {
+  __shared__ __align__(16) float s_slab[UNW_WARPS][UNW_SLAB];
   const int lane = threadIdx.x & 31;
   const long long a = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (a >= A) return;
+  float* __restrict__ wsm = s_slab[threadIdx.x >> 5];
   const float* __restrict__ src = pos + (size_t)a * T * 3;
   float* __restrict__ dst = out + (size_t)a * T * 3;
-  const float ilx = (float)(1.0 / lx), ily = (float)(1.0 / ly), ilz = (float)(1.0 / lz);
+  const long long n_el = T * 3;
+  const float il[3] = {(float)(1.0 / lx), (float)(1.0 / ly), (float)(1.0 / lz)};
+  const double l64[3] = {lx, ly, lz};
+  const float l32[3] = {(float)lx, (float)ly, (float)lz};
 
   // carry: previous position and image (first batch: p_{-1} = p_0, img = 0)
-  float px, py, pz;
-  if (have_carry) {
-    px = carry_pos[a * 3 + 0];
-    py = carry_pos[a * 3 + 1];
-    pz = carry_pos[a * 3 + 2];
-  } else {
-    px = src[0];
-    py = src[1];
-    pz = src[2];
-  }
-  double ix = carry_img[a * 3 + 0], iy = carry_img[a * 3 + 1], iz = carry_img[a * 3 + 2];
-
-  float nx = 0.f, ny = 0.f, nz = 0.f;  // prefetched chunk
-  bool nvalid = lane < T;
-  if (nvalid) {
-    nx = __ldg(src + 3 * lane);
-    ny = __ldg(src + 3 * lane + 1);
-    nz = __ldg(src + 3 * lane + 2);
-  }
-  for (long long tb = 0; tb < T; tb += 32) {
-    const long long t = tb + lane;
-    const bool valid = nvalid;
-    const float x = nx, y = ny, z = nz;
-    const long long tn = t + 32;
-    nvalid = tn < T;
-    if (nvalid) {
-      nx = __ldg(src + 3 * tn);
-      ny = __ldg(src + 3 * tn + 1);
-      nz = __ldg(src + 3 * tn + 2);
-    }
-    float qx = __shfl_up_sync(0xffffffffu, x, 1);
-    float qy = __shfl_up_sync(0xffffffffu, y, 1);
-    float qz = __shfl_up_sync(0xffffffffu, z, 1);
-    if (lane == 0) {
-      qx = px;
-      qy = py;
-      qz = pz;
-    }
-    int jx = 0, jy = 0, jz = 0;
-    if (valid) {
-      jx = jump_of(x, qx, ilx, lx);
-      jy = jump_of(y, qy, ily, ly);
-      jz = jump_of(z, qz, ilz, lz);
-    }
+  float prevp[3], img[3];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int ux = __shfl_up_sync(0xffffffffu, jx, o);
-      const int uy = __shfl_up_sync(0xffffffffu, jy, o);
-      const int uz = __shfl_up_sync(0xffffffffu, jz, o);
-      if (lane >= o) {
-        jx += ux;
-        jy += uy;
-        jz += uz;
+  for (int d = 0; d < 3; ++d) {
+    prevp[d] = have_carry ? carry_pos[a * 3 + d] : src[d];
+    // images are integers, exact in fp32 below 2^24 box crossings
+    img[d] = (float)carry_img[a * 3 + d];
+  }
+
+  // element e of a chunk is loaded by lane (e/4)%32 in row (e/128): 16-byte vectors when the
+  // row start is 16-byte aligned (VEC: T % 4 == 0 and an aligned base), scalars otherwise
+  auto load_chunk = [&](long long tb, float4 (&r)[3]) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const long long e = tb * 3 + j * 128 + 4 * lane;
+      if (VEC && e + 3 < n_el) {
+        r[j] = __ldg(reinterpret_cast<const float4*>(src + e));
+      } else {
+        r[j].x = e + 0 < n_el ? __ldg(src + e + 0) : 0.f;
+        r[j].y = e + 1 < n_el ? __ldg(src + e + 1) : 0.f;
+        r[j].z = e + 2 < n_el ? __ldg(src + e + 2) : 0.f;
+        r[j].w = e + 3 < n_el ? __ldg(src + e + 3) : 0.f;
       }
     }
-    if (valid) {
-      const double mx = ix - (double)jx, my = iy - (double)jy, mz = iz - (double)jz;
-      dst[3 * t + 0] = __double2float_rn(__dadd_rn((double)x, __dmul_rn(mx, lx)));
-      dst[3 * t + 1] = __double2float_rn(__dadd_rn((double)y, __dmul_rn(my, ly)));
-      dst[3 * t + 2] = __double2float_rn(__dadd_rn((double)z, __dmul_rn(mz, lz)));
+  };
+  float4 pre[UNW_PF][3];
+#pragma unroll
+  for (int k = 0; k < UNW_PF; ++k) load_chunk((long long)k * UNW_CH, pre[k]);
+
+  for (long long tb = 0; tb < T; tb += UNW_CH) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) *reinterpret_cast<float4*>(wsm + j * 128 + 4 * lane) = pre[0][j];
+#pragma unroll
+    for (int k = 0; k + 1 < UNW_PF; ++k)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) pre[k][j] = pre[k + 1][j];
+    load_chunk(tb + (long long)UNW_PF * UNW_CH, pre[UNW_PF - 1]);
+    __syncwarp();
+    // lane l owns frames tb + 4l .. tb + 4l + 3: floats [12 l, 12 l + 12) of the slab
+    float p[UNW_F][3];
+    {
+      const float4 v0 = *reinterpret_cast<const float4*>(wsm + 12 * lane);
+      const float4 v1 = *reinterpret_cast<const float4*>(wsm + 12 * lane + 4);
+      const float4 v2 = *reinterpret_cast<const float4*>(wsm + 12 * lane + 8);
+      p[0][0] = v0.x; p[0][1] = v0.y; p[0][2] = v0.z; p[1][0] = v0.w;
+      p[1][1] = v1.x; p[1][2] = v1.y; p[2][0] = v1.z; p[2][1] = v1.w;
+      p[2][2] = v2.x; p[3][0] = v2.y; p[3][1] = v2.z; p[3][2] = v2.w;
     }
-    // chunk carry: last valid lane of this chunk
-    const int last = (int)min((long long)31, T - 1 - tb);
-    ix -= (double)__shfl_sync(0xffffffffu, jx, last);
-    iy -= (double)__shfl_sync(0xffffffffu, jy, last);
-    iz -= (double)__shfl_sync(0xffffffffu, jz, last);
-    px = __shfl_sync(0xffffffffu, x, last);
-    py = __shfl_sync(0xffffffffu, y, last);
-    pz = __shfl_sync(0xffffffffu, z, last);
+    __syncwarp();
+    const long long t_first = tb + UNW_F * lane;
+    const int n_here = (int)min((long long)UNW_F, max(0ll, T - t_first));  // valid frames
+    const int last_lane = (int)((min((long long)UNW_CH, T - tb) - 1) / UNW_F);
+    const int last_f = (int)((min((long long)UNW_CH, T - tb) - 1) % UNW_F);
+    float o[UNW_F][3];
+    bool any_jump = false;
+    float jl[UNW_F][3];  // inclusive prefix of the jumps inside the lane
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      float q = __shfl_up_sync(0xffffffffu, p[UNW_F - 1][d], 1);
+      if (lane == 0) q = prevp[d];
+      float run = 0.f;
+#pragma unroll
+      for (int f = 0; f < UNW_F; ++f) {
+        float j = 0.f;
+        if (f < n_here) j = jump_of(p[f][d], q, il[d], l64[d]);
+        run += j;
+        jl[f][d] = run;
+        q = p[f][d];
+      }
+      any_jump |= run != 0.f;
+    }
+    float off[3] = {0.f, 0.f, 0.f};  // exclusive scan of the lane totals
+    float tot[3] = {0.f, 0.f, 0.f};  // jumps of the whole chunk
+    if (__any_sync(0xffffffffu, any_jump)) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        float inc = jl[UNW_F - 1][d];
+#pragma unroll
+        for (int s2 = 1; s2 < 32; s2 <<= 1) {
+          const float u = __shfl_up_sync(0xffffffffu, inc, s2);
+          if (lane >= s2) inc += u;
+        }
+        off[d] = inc - jl[UNW_F - 1][d];
+        tot[d] = __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < UNW_F; ++f)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float m = img[d] - (off[d] + jl[f][d]);
+        float v = p[f][d];
+        if (m != 0.f) {
+          if (L32) v = fmaf(m, l32[d], v);
+          else v = __double2float_rn(__dadd_rn((double)v, __dmul_rn((double)m, l64[d])));
+        }
+        o[f][d] = v;
+      }
+    *reinterpret_cast<float4*>(wsm + 12 * lane) = make_float4(o[0][0], o[0][1], o[0][2], o[1][0]);
+    *reinterpret_cast<float4*>(wsm + 12 * lane + 4) = make_float4(o[1][1], o[1][2], o[2][0], o[2][1]);
+    *reinterpret_cast<float4*>(wsm + 12 * lane + 8) = make_float4(o[2][2], o[3][0], o[3][1], o[3][2]);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const long long e = tb * 3 + j * 128 + 4 * lane;
+      const float4 v = *reinterpret_cast<const float4*>(wsm + j * 128 + 4 * lane);
+      if (VEC && e + 3 < n_el) {
+        *reinterpret_cast<float4*>(dst + e) = v;
+      } else {
+        if (e + 0 < n_el) dst[e + 0] = v.x;
+        if (e + 1 < n_el) dst[e + 1] = v.y;
+        if (e + 2 < n_el) dst[e + 2] = v.z;
+        if (e + 3 < n_el) dst[e + 3] = v.w;
+      }
+    }
+    __syncwarp();
+    // chunk carry: image after the chunk, last valid position
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      img[d] -= tot[d];
+      float lp = p[0][d];
+#pragma unroll
+      for (int f = 1; f < UNW_F; ++f) lp = (f == last_f) ? p[f][d] : lp;
+      if (last_f == 0) lp = p[0][d];
+      prevp[d] = __shfl_sync(0xffffffffu, lp, last_lane);
+    }
   }
   if (lane == 0) {
-    carry_img[a * 3 + 0] = ix;
-    carry_img[a * 3 + 1] = iy;
-    carry_img[a * 3 + 2] = iz;
-    if (carry_pos) {
-      carry_pos[a * 3 + 0] = px;
-      carry_pos[a * 3 + 1] = py;
-      carry_pos[a * 3 + 2] = pz;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      carry_img[a * 3 + d] = (double)img[d];
+      if (carry_pos) carry_pos[a * 3 + d] = prevp[d];
     }
   }
 }
@@ -184,11 +265,23 @@ extern "C" int mdk_unwrap(const float* pos, long long A, long long T, const doub
   MDK_CHECK_ARG(!have_carry || carry_pos, "unwrap: have_carry set but carry_pos is NULL");
   MDK_CHECK_ARG(box[0] > 0 && box[1] > 0 && box[2] > 0, "unwrap: box must be positive");
   if (A == 0) return MDK_OK;
-  const long long threads = A * 32;
-  const long long blocks = (threads + 255) / 256;
+  const long long blocks = (A + UNW_WARPS - 1) / UNW_WARPS;
   MDK_CHECK_ARG(blocks < (1ll << 31), "unwrap: too many atoms for one launch");
-  unwrap_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
-      pos, A, T, box[0], box[1], box[2], carry_pos, have_carry, carry_img, out);
+  const bool l32 = box[0] == (double)(float)box[0] && box[1] == (double)(float)box[1] &&
+                   box[2] == (double)(float)box[2];
+  // 16-byte vector access needs every atom row (T * 12 bytes apart) to start 16-byte aligned
+  const bool vec = (T % 4 == 0) && (reinterpret_cast<uintptr_t>(pos) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+  const unsigned nb = (unsigned)blocks, nt = 32 * UNW_WARPS;
+  cudaStream_t st = as_stream(stream);
+#define MDK_UNWRAP_LAUNCH(L, V)                                                               \
+  unwrap_kernel<L, V><<<nb, nt, 0, st>>>(pos, A, T, box[0], box[1], box[2], carry_pos, have_carry, \
+                                         carry_img, out)
+  if (l32 && vec) MDK_UNWRAP_LAUNCH(true, true);
+  else if (l32) MDK_UNWRAP_LAUNCH(true, false);
+  else if (vec) MDK_UNWRAP_LAUNCH(false, true);
+  else MDK_UNWRAP_LAUNCH(false, false);
+#undef MDK_UNWRAP_LAUNCH
   MDK_LAUNCH_CHECK();
   return MDK_OK;
 }

@@ -155,9 +155,52 @@ def coord_extent(pos_soa: torch.Tensor, n_frames: int, n_pad: int) -> np.ndarray
     return mm.cpu().numpy()
 
 
+RDF_SUBTILE = 64  # MDK_RDF_SUBTILE
+
+
+def rdf_sort_workspace(max_atoms: int) -> int:
+    return int(_lib.load().mdk_rdf_sort_workspace(int(max_atoms)))
+
+
+def rdf_pack_sorted(traj: torch.Tensor, frame: int, out: torch.Tensor, k: int, layout: RdfLayout,
+                    species_index: int, atom_first: int, atom_count: int, box,
+                    workspace: torch.Tensor):
+    """Morton-ordered pack of one frame of one species into slab k of ``out`` ([k][3][n_pad])."""
+    _need_cuda(traj, torch.float32, "rdf_pack_sorted traj")
+    _need_cuda(out, torch.float32, "rdf_pack_sorted out")
+    A, T, D = traj.shape
+    if D != 3:
+        raise MdkError("rdf_pack_sorted: trajectory must be [A][T][3]")
+    lo = int(layout.sp_lo[species_index])
+    span = ((atom_count + layout.tile - 1) // layout.tile) * layout.tile
+    box32 = np.asarray(box, dtype=np.float32)
+    check(
+        _lib.load().mdk_rdf_pack_sorted(
+            _ptr(traj), A, T, atom_first, atom_count, int(frame),
+            C.c_void_p(out.data_ptr() + 4 * k * 3 * layout.n_pad), layout.n_pad, lo, span,
+            box32.ctypes.data_as(C.c_void_p), _ptr(workspace),
+            workspace.numel() * workspace.element_size(), _stream(),
+        ),
+        "mdk_rdf_pack_sorted",
+    )
+    _count(3)
+
+
+def rdf_bbox(pos_soa: torch.Tensor, n_frames: int, layout: RdfLayout, bbox: torch.Tensor):
+    """Bounding boxes [n_frames][n_pad / RDF_SUBTILE][6] of a packed frame array."""
+    _need_cuda(pos_soa, torch.float32, "rdf_bbox pos")
+    _need_cuda(bbox, torch.float32, "rdf_bbox out")
+    if bbox.numel() < n_frames * (layout.n_pad // RDF_SUBTILE) * 6:
+        raise MdkError("rdf_bbox: output too small")
+    check(_lib.load().mdk_rdf_bbox(_ptr(pos_soa), n_frames, layout.n_pad, _ptr(bbox), _stream()),
+          "mdk_rdf_bbox")
+    _count()
+
+
 def rdf_hist(pos_soa: torch.Tensor, n_frames: int, layout: RdfLayout, box, cutoff: float,
              nbins: int, thr_dev: torch.Tensor, cut2: float, hist: torch.Tensor,
-             work_counter: torch.Tensor, exact_div: bool = False, tuning: int = 0):
+             work_counter: torch.Tensor, exact_div: bool = False, tuning: int = 0,
+             bbox: torch.Tensor | None = None):
     """hist[pair][bin] += counts of all minimum-image pair distances below the cutoff.
 
     Replaces get_partial_triu_indices / apply_minimum_image (utils/linalg.py:84-122),
@@ -179,7 +222,7 @@ def rdf_hist(pos_soa: torch.Tensor, n_frames: int, layout: RdfLayout, box, cutof
             layout.sp_lo.ctypes.data_as(C.c_void_p), layout.sp_hi.ctypes.data_as(C.c_void_p),
             layout.n_species, box32.ctypes.data_as(C.c_void_p), C.c_float(cut2),
             C.c_float(cutoff), int(nbins), _ptr(thr_dev), _ptr(hist), _ptr(work_counter),
-            flags, _stream(),
+            _ptr(bbox) if bbox is not None else None, flags, _stream(),
         ),
         "mdk_rdf_hist",
     )

@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--rdf-frames", type=int, default=2)
     ap.add_argument("--rdf-box", type=float, default=170.0)
     ap.add_argument("--tunings", default="0")
+    ap.add_argument("--sort", type=int, default=-1, help="-1 auto, 0 off, 1 on")
+    ap.add_argument("--cutoff-frac", type=float, default=0.0)
     ap.add_argument("--dyn-atoms", type=int, default=20000)
     ap.add_argument("--dyn-frames", type=int, default=2000)
     ap.add_argument("--data-range", type=int, default=500)
@@ -50,15 +52,17 @@ def main():
     if "rdf" in what:
         n, F, L = args.rdf_atoms, args.rdf_frames, args.rdf_box
         traj = device_fluid(n, F, L, 4, dev)
-        cutoff = L / 2 - 0.1
+        cutoff = L / 2 - 0.1 if args.cutoff_frac <= 0 else args.cutoff_frac * L
         nbins = int(cutoff / 0.01)
+        sort = None if args.sort < 0 else bool(args.sort)
         for tun in [int(t, 0) for t in args.tunings.split(",")]:
-            eng = RdfEngine([n], [L, L, L], cutoff, nbins, drop_first=False, device=dev)
+            eng = RdfEngine([n], [L, L, L], cutoff, nbins, drop_first=False, device=dev,
+                            spatial_sort=sort)
             t = timed(lambda: eng.add_frames([traj], np.arange(F), check_extent=False, tuning=tun),
                       reps=2)
             pairs = F * n * (n - 1) / 2
             inside = eng.counts().sum() / eng.frames_done
-            r = {"rdf_tuning": hex(tun), "n": n, "F": F, "nbins": nbins, "s": t,
+            r = {"rdf_tuning": hex(tun), "sorted": eng.spatial_sort, "n": n, "F": F, "nbins": nbins, "s": t,
                  "pairs_per_s": pairs / t, "tflops20": 20 * pairs / t * 1e-12,
                  "inside_frac": float(inside / (n * (n - 1) / 2))}
             print(json.dumps(r), flush=True)
@@ -69,9 +73,10 @@ def main():
         o = torch.empty_like(traj)
         ci = torch.zeros(A, 3, dtype=torch.float64, device=dev)
         cp = torch.zeros(A, 3, dtype=torch.float32, device=dev)
-        t = timed(lambda: K.unwrap(traj, [60.0] * 3, cp, ci, False, o))
-        print(json.dumps({"unwrap_s": t, "atom_frames_per_s": A * T / t,
-                          "GBps": 24 * A * T / t * 1e-9}), flush=True)
+        for L in (60.0, 60.1):
+            t = timed(lambda: K.unwrap(traj, [L] * 3, cp, ci, False, o))
+            print(json.dumps({"unwrap_s": t, "box": L, "atom_frames_per_s": A * T / t,
+                              "GBps": 24 * A * T / t * 1e-9}), flush=True)
     if "ionic" in what:
         J = torch.zeros(T, 3, dtype=torch.float64, device=dev)
         t = timed(lambda: K.ionic_current(traj, 1.0, J))

@@ -108,6 +108,62 @@ def test_rdf_single_species_and_empty(cuda):
     assert eng2.counts().sum() == 0
 
 
+def test_rdf_sorted_culled_matches_oracle(cuda):
+    """Morton-ordered pack + block culling: same integers as the oracle (two species, so the
+    cross-species tiles and the diagonal tiles are both exercised)."""
+    from lammps_analysis_b200.engine import RdfEngine, to_device_f32
+    from oracle import rdf as orc
+
+    rng = np.random.default_rng(31)
+    n, L = 5000, 58.0
+    pos = {"A": (rng.random((n, 1, 3)) * L).astype(np.float32),
+           "B": (rng.random((n + 37, 1, 3)) * L).astype(np.float32)}
+    box = np.array([L, L, L])
+    cutoff, nbins = 14.0, 1400          # cutoff << L/2: many blocks are out of range
+    ref = orc.rdf_counts(pos, ["A", "B"], box, np.arange(1), cutoff, nbins, 100, 1)
+    eng = RdfEngine([n, n + 37], box, cutoff, nbins, device=cuda, spatial_sort=True)
+    assert eng.spatial_sort
+    eng.add_frames([to_device_f32(pos[s], cuda) for s in ("A", "B")], np.arange(1))
+    got = eng.counts()
+    for p, key in enumerate(["A_A", "A_B", "B_B"]):
+        assert np.array_equal(got[p], ref[key]), key
+
+
+@pytest.mark.parametrize("cutoff_frac", [0.12, 0.3, 0.4999])
+def test_rdf_culling_is_exact_at_scale(cuda, cutoff_frac):
+    """Size-independent property: the culled, spatially sorted pass returns exactly the
+    histogram of the plain all-pairs pass (100,000 atoms, 5e9 pairs per frame)."""
+    import torch
+    from lammps_analysis_b200.engine import RdfEngine
+    from lammps_analysis_b200.synthetic import device_fluid
+
+    n, L = 100_000, 170.0
+    traj = device_fluid(n, 2, L, 41, cuda)
+    cutoff = cutoff_frac * L
+    nbins = 2000
+    plain = RdfEngine([n], [L] * 3, cutoff, nbins, device=cuda, spatial_sort=False)
+    plain.add_frames([traj], np.arange(2))
+    culled = RdfEngine([n], [L] * 3, cutoff, nbins, device=cuda, spatial_sort=True)
+    culled.add_frames([traj], np.arange(2))
+    a, b = plain.counts(), culled.counts()
+    assert a.sum() > 0 and np.array_equal(a, b)
+
+
+def test_rdf_culling_with_unwrapped_coordinates(cuda):
+    """Coordinates spread over several box images: the box test must stay conservative."""
+    from lammps_analysis_b200.engine import RdfEngine, to_device_f32
+
+    rng = np.random.default_rng(32)
+    n, L = 20000, 40.0
+    pos = ((rng.random((n, 1, 3)) * 2.3 - 0.6) * L).astype(np.float32)  # spans 2.3 box lengths
+    cutoff, nbins = 9.0, 900
+    plain = RdfEngine([n], [L] * 3, cutoff, nbins, device=cuda, spatial_sort=False)
+    plain.add_frames([to_device_f32(pos, cuda)], np.arange(1))
+    culled = RdfEngine([n], [L] * 3, cutoff, nbins, device=cuda, spatial_sort=True)
+    culled.add_frames([to_device_f32(pos, cuda)], np.arange(1))
+    assert np.array_equal(plain.counts(), culled.counts())
+
+
 def _plan(A, T, data_range, ct, memory=60e9, scale=150):
     from oracle.planner import ArrayDatabase, plan_trajectory_calculator
 
@@ -184,7 +240,9 @@ def test_acf_matches_oracle(cuda, A, T, N, ct):
     np.testing.assert_allclose(sig, ref_sig, rtol=RTOL, atol=RTOL * np.abs(ref_sig).max())
 
 
-def test_unwrap_bit_exact_with_carry(cuda):
+@pytest.mark.parametrize("box", [[10.0, 11.5, 9.25],            # exactly representable in fp32
+                                 [10.1, 11.37, 9.2123456789]])    # fp64 path
+def test_unwrap_bit_exact_with_carry(cuda, box):
     import torch
     from lammps_analysis_b200 import kernels as K
     from lammps_analysis_b200.engine import to_device_f32
@@ -192,7 +250,7 @@ def test_unwrap_bit_exact_with_carry(cuda):
 
     rng = np.random.default_rng(21)
     A, T = 70, 333
-    box = np.array([10.0, 11.5, 9.25])
+    box = np.array(box)
     walk = np.cumsum(rng.normal(0, 1.5, size=(A, T, 3)), axis=1) + rng.random((A, 1, 3)) * box
     pos = np.mod(walk, box).astype(np.float32)
     ref = ot.run_unwrap(pos, box, batch_size=100)  # 3 batches + remainder, carry-over
@@ -215,6 +273,26 @@ def test_unwrap_bit_exact_with_carry(cuda):
     carry_img.zero_()
     K.unwrap(dev, box, carry_pos, carry_img, False, out2)
     assert np.array_equal(out2.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("T", [4, 128, 200, 260])
+def test_unwrap_vector_path(cuda, T):
+    """T % 4 == 0 takes the 16-byte vector path; chunk boundaries at 128 frames."""
+    import torch
+    from lammps_analysis_b200 import kernels as K
+    from lammps_analysis_b200.engine import to_device_f32
+    from oracle import transformations as ot
+
+    rng = np.random.default_rng(24)
+    A = 37
+    box = np.array([7.7, 8.0, 9.31])
+    walk = np.cumsum(rng.normal(0, 2.5, size=(A, T, 3)), axis=1) + rng.random((A, 1, 3)) * box
+    pos = np.mod(walk, box).astype(np.float32)
+    ref = ot.run_unwrap(pos, box, batch_size=T)
+    dev = to_device_f32(pos, cuda)
+    out = torch.empty_like(dev)
+    K.unwrap(dev, box, None, torch.zeros(A, 3, dtype=torch.float64, device=cuda), False, out)
+    assert np.array_equal(out.cpu().numpy(), ref)
 
 
 def test_unwrap_reference_known_answer(cuda):

@@ -248,6 +248,7 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     steps, warm = max(1, args.steps), max(3, args.warmup)

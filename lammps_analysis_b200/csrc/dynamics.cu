@@ -292,7 +292,7 @@ constexpr int GB_T = 64;      // tile edge
 constexpr int GB_NT = 64;     // threads per CTA (2 warps)
 constexpr int GB_KA = 8;      // atoms per pipeline stage
 constexpr int GB_ST = 3;      // pipeline stages
-constexpr int GB_FOLD = 2048; // atoms per fp32 accumulation run
+constexpr int GB_FOLD = 256;  // atoms per fp32 accumulation run
 constexpr int GB_ROW = GB_T + 12;        // padded SoA row: dims land 12 banks apart, so the
                                         // 4-byte cp.async scatter (lane -> frame q/3, dim q%3) is
                                         // (almost) conflict free; multiple of 4 for LDS.128

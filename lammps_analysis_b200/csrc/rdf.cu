@@ -191,6 +191,54 @@ __device__ __forceinline__ void bin_two(float2 d2, float cut2, float2 inv_step2,
 #undef MDK_BIN_ARGS
 }
 
+// Table-free variant for the common case (AM == 3).  The bin guess carries FRAC_BITS fraction
+// bits: tm = fma(sqrt.approx(d2), 1/step, 1.5 * 2^(23 - FRAC_BITS)) rounds t = d/step to the
+// nearest 1/128, so the mantissa holds (floor-or-carry(t) << 7) | f.  The exact bin (double-step
+// rule on the correctly rounded sqrt) differs from t by at most t * 2.4e-7 + 1/256 < 1/128 for
+// t <= 16000, hence for f != 0 the integer part IS the bin and only f == 0 (one lane in 128)
+// needs the threshold-table compare.  This removes the random shared-memory gather from the
+// hot path; the table lookup runs under a warp vote.
+constexpr int FRAC_BITS = 7;
+constexpr float FRAC_MAGIC = 98304.0f;  // 1.5 * 2^16: ulp = 2^-7
+constexpr int FRAC_MAX_BINS = 15000;
+
+template <bool DUMMY = true>
+__device__ __forceinline__ void bin_two_frac(float2 d2, float cut2, float2 inv_step2,
+                                             uint32_t thr_base, uint32_t cnt_base,
+                                             uint32_t dump_off) {
+  const float2 ee = make_float2(sqrt_approx(d2.x), sqrt_approx(d2.y));
+  const float2 tt = __ffma2_rn(ee, inv_step2, make_float2(FRAC_MAGIC, FRAC_MAGIC));
+  const uint32_t b0 = __float_as_uint(tt.x), b1 = __float_as_uint(tt.y);
+  uint32_t a0 = (b0 >> (FRAC_BITS - 2)) & 0x1fffcu;  // 4 * bin (byte offset)
+  uint32_t a1 = (b1 >> (FRAC_BITS - 2)) & 0x1fffcu;
+  const bool p0 = d2.x < cut2, p1 = d2.y < cut2;
+  const bool m0 = p0 && ((b0 & ((1u << FRAC_BITS) - 1u)) == 0u);
+  const bool m1 = p1 && ((b1 & ((1u << FRAC_BITS) - 1u)) == 0u);
+  if (__any_sync(0xffffffffu, m0 | m1)) {
+    if (m0) {
+      float g;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g) : "r"(thr_base + a0));
+      if (d2.x < g) a0 -= 4u;
+    }
+    if (m1) {
+      float g;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g) : "r"(thr_base + a1));
+      if (d2.y < g) a1 -= 4u;
+    }
+  }
+  a0 = p0 ? a0 : dump_off;
+  a1 = p1 ? a1 : dump_off;
+  asm volatile(
+      "{\n"
+      ".reg .u32 t0, t1;\n"
+      "add.u32 t0, %0, %2;\n"
+      "add.u32 t1, %1, %2;\n"
+      "red.shared.add.u32 [t0], 1;\n"
+      "red.shared.add.u32 [t1], 1;\n"
+      "}\n" ::"r"(a0), "r"(a1), "r"(cnt_base)
+      : "memory");
+}
+
 // Flush the CTA-private histogram to the global one and clear it.
 template <int NT>
 __device__ __forceinline__ void flush_hist(unsigned int* s_cnt, int nbins,
@@ -206,15 +254,74 @@ __device__ __forceinline__ void flush_hist(unsigned int* s_cnt, int nbins,
   __syncthreads();
 }
 
+// Loop-invariant operands of the pair arithmetic.
+struct GeoConst {
+  float invLx, invLy, invLz, nLx, nLy, nLz, inv_step;
+  float cut2;
+  uint32_t thr_c, cnt_delta, one, dump, thr_s, cnt_s, dump_off;
+};
+__device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
+
+// One 64-atom column sub-tile against the row groups selected by the compile-time mask M (bit r
+// = row group r of this warp is within reach).  The arithmetic is the reference's rounding
+// sequence; see the kernel header.
+template <bool MASKED, int R, int AM>
+__device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ sx,
+                                         const float* __restrict__ sy,
+                                         const float* __restrict__ sz, int jj0,
+                                         const float2 (&nxi)[R], const float2 (&nyi)[R],
+                                         const float2 (&nzi)[R], const GeoConst& c) {
+  const float2 magic2 = dup2(RINT_MAGIC), nmagic2 = dup2(-RINT_MAGIC);
+  const float2 inv_step2 = dup2(c.inv_step);
+#pragma unroll 2
+  for (int jj = jj0; jj < jj0 + SUB; jj += 2) {
+    const float2 xj = *reinterpret_cast<const float2*>(sx + jj);
+    const float2 yj = *reinterpret_cast<const float2*>(sy + jj);
+    const float2 zj = *reinterpret_cast<const float2*>(sz + jj);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (!MASKED || ((m >> r) & 1u)) {  // warp-uniform
+        const float2 dx = __fadd2_rn(xj, nxi[r]);
+        const float2 dy = __fadd2_rn(yj, nyi[r]);
+        const float2 dz = __fadd2_rn(zj, nzi[r]);
+        const float2 tx = __ffma2_rn(dx, dup2(c.invLx), magic2);
+        const float2 ty = __ffma2_rn(dy, dup2(c.invLy), magic2);
+        const float2 tz = __ffma2_rn(dz, dup2(c.invLz), magic2);
+        const float2 nx = __fadd2_rn(tx, nmagic2);
+        const float2 ny = __fadd2_rn(ty, nmagic2);
+        const float2 nz = __fadd2_rn(tz, nmagic2);
+        const float2 rx = __ffma2_rn(nx, dup2(c.nLx), dx);
+        const float2 ry = __ffma2_rn(ny, dup2(c.nLy), dy);
+        const float2 rz = __ffma2_rn(nz, dup2(c.nLz), dz);
+        // squares packed; the two adds stay scalar: ptxas 12.9 contracts mul.rn.f32x2 +
+        // add.rn.f32x2 into FFMA2, which would break the reference's rounding sequence
+        // (x*x + y*y) + z*z.
+        const float2 xx = __fmul2_rn(rx, rx);
+        const float2 yy = __fmul2_rn(ry, ry);
+        const float2 zz = __fmul2_rn(rz, rz);
+        float2 d2;
+        d2.x = __fadd_rn(__fadd_rn(xx.x, yy.x), zz.x);
+        d2.y = __fadd_rn(__fadd_rn(xx.y, yy.y), zz.y);
+        if (AM == 3)
+          bin_two_frac(d2, c.cut2, inv_step2, c.thr_s, c.cnt_s, c.dump_off);
+        else
+          bin_two<(AM == 3 ? 2 : AM)>(d2, c.cut2, inv_step2, c.thr_c, c.cnt_delta, c.one, c.dump);
+      }
+    }
+  }
+}
+
+// register budget: 768 resident threads per SM without culling (85 registers), 512 with it
 template <int NT, int R, bool EXACT, int AM, bool CULL>
-__global__ void __launch_bounds__(NT) rdf_pair_hist_kernel(const __grid_constant__ RdfParams P) {
+__global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_kernel(const __grid_constant__ RdfParams P) {
   constexpr int TI = NT * R;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // layout: [stage0 xyz | stage1 xyz | mbar x2 | item | thr (nbins+1) | cnt (nbins, padded
   // to 32) | 32 dump slots]
   float* s_tile = reinterpret_cast<float*>(smem_raw);                 // 2 * 3 * TJ floats
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tile + 2 * 3 * TJ); // 2 barriers
-  unsigned long long* s_item = reinterpret_cast<unsigned long long*>(s_bar + 2);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tile + 2 * 3 * TJ); // full[2], empty[2]
+  uint64_t* s_ebar = s_bar + 2;
+  unsigned long long* s_item = reinterpret_cast<unsigned long long*>(s_bar + 4);
   float* s_thr = reinterpret_cast<float*>(s_item + 2);
   const int thr_len = (P.nbins + 1 + 3) & ~3;
   unsigned int* s_cnt = reinterpret_cast<unsigned int*>(s_thr + thr_len);
@@ -225,11 +332,15 @@ __global__ void __launch_bounds__(NT) rdf_pair_hist_kernel(const __grid_constant
   if (tid == 0) {
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
+    mbar_init(&s_ebar[0], NT / 32);  // one arrival per warp
+    mbar_init(&s_ebar[1], NT / 32);
     fence_mbar_init();
   }
   __syncthreads();
 
   uint32_t phase[2] = {0u, 0u};
+  // "stage is free" barriers: waiting on parity 1 of a fresh barrier returns at once
+  uint32_t ephase[2] = {1u, 1u};
   int cur_pair = -1;
   unsigned int tiles_since_flush = 0;
 
@@ -241,6 +352,8 @@ __global__ void __launch_bounds__(NT) rdf_pair_hist_kernel(const __grid_constant
   const uint32_t one = P.one;
   // dump slot of this lane, expressed relative to the thr table (bin_two adds cnt_delta)
   const uint32_t dump = smem_u32(s_thr) + 4u * ((P.nbins + 31) & ~31) + 4u * (tid & 31);
+  const uint32_t thr_s = smem_u32(s_thr), cnt_s = smem_u32(s_cnt);
+  const uint32_t dump_off = 4u * ((P.nbins + 31) & ~31) + 4u * (tid & 31);  // relative to cnt
   const float2 magic2 = make_float2(RINT_MAGIC, RINT_MAGIC);
   const float2 nmagic2 = make_float2(-RINT_MAGIC, -RINT_MAGIC);
   const float2 invLx = make_float2(P.inv_box[0], P.inv_box[0]);
@@ -249,6 +362,9 @@ __global__ void __launch_bounds__(NT) rdf_pair_hist_kernel(const __grid_constant
   const float2 nLx = make_float2(-P.box[0], -P.box[0]);
   const float2 nLy = make_float2(-P.box[1], -P.box[1]);
   const float2 nLz = make_float2(-P.box[2], -P.box[2]);
+  const GeoConst geo = {P.inv_box[0], P.inv_box[1], P.inv_box[2], -P.box[0], -P.box[1],
+                        -P.box[2], inv_step, cut2, thr_c, cnt_delta, one, dump, thr_s, cnt_s,
+                        dump_off};
 
   for (;;) {
     if (tid == 0) s_item[0] = atomicAdd(P.counter, 1ull);
@@ -290,9 +406,9 @@ __global__ void __launch_bounds__(NT) rdf_pair_hist_kernel(const __grid_constant
     int irow[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      // a warp owns 32*R consecutive rows (R groups of 32): consecutive atoms are spatial
-      // neighbours after the Hilbert ordering, so the R culling masks of a warp mostly agree
-      const int i = row_base + ((tid >> 5) * R + r) * 32 + (tid & 31);
+      // the R row groups of a warp come from R different 256-row regions of the tile: their
+      // culling masks differ, which balances the live work across the warps of the CTA
+      const int i = row_base + r * NT + tid;
       irow[r] = i;
       float x = __int_as_float(0x7fc00000), y = x, z = x;  // NaN rows never pass d2 < cut2
       if (i < P.sp_hi[a]) {
@@ -306,7 +422,6 @@ __global__ void __launch_bounds__(NT) rdf_pair_hist_kernel(const __grid_constant
     }
 
     // ---- bounding boxes of this row tile (CTA) and of each warp's 32-row groups -----------
-    constexpr bool cull = CULL;  // P.bbox != nullptr
     const float* __restrict__ fbox = P.bbox + (size_t)f * P.boxes_per_frame * 6;
     float rbox[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
     float wbox[R][6];
@@ -356,10 +471,21 @@ __global__ void __launch_bounds__(NT) rdf_pair_hist_kernel(const __grid_constant
     int jt = next_live(j_tile0);
     if (jt >= j_tile1) continue;  // every column tile of this item is out of range
     int jn = next_live(jt + 1);
-    if (tid == 0) {
-      issue(jt, 0);
-      if (jn < j_tile1) issue(jn, 1);
+    // Column tiles flow through a two-stage ring.  Warps are NOT block-synchronised per tile:
+    // a warp signals "done with this stage" on the stage's empty barrier and moves on to the
+    // next tile as soon as its data has landed; only warp 0, which refills a stage, waits for
+    // all warps to have released it.  With block culling the work per (warp, tile) varies, and
+    // a per-tile __syncthreads made every warp wait for the slowest one.
+    if (tid < 32) {
+      mbar_wait(&s_ebar[0], ephase[0]);
+      if (tid == 0) issue(jt, 0);
+      if (jn < j_tile1) {
+        mbar_wait(&s_ebar[1], ephase[1]);
+        if (tid == 0) issue(jn, 1);
+      }
     }
+    ephase[0] ^= 1u;
+    if (jn < j_tile1) ephase[1] ^= 1u;
 
     for (int stage = 0; jt < j_tile1; stage ^= 1) {
       mbar_wait(&s_bar[stage], phase[stage]);
@@ -385,70 +511,13 @@ __global__ void __launch_bounds__(NT) rdf_pair_hist_kernel(const __grid_constant
 
       if (!EXACT && !diag) {
         constexpr unsigned FULL = (1u << R) - 1u;
+#pragma unroll 1
         for (int q = 0; q < NSUB; ++q) {
           const unsigned m = (rmask >> (q * R)) & FULL;
-          if (m == FULL) {
-#pragma unroll 2
-            for (int jj = q * SUB; jj < (q + 1) * SUB; jj += 2) {
-              const float2 xj = *reinterpret_cast<const float2*>(sx + jj);
-              const float2 yj = *reinterpret_cast<const float2*>(sy + jj);
-              const float2 zj = *reinterpret_cast<const float2*>(sz + jj);
-#pragma unroll
-              for (int r = 0; r < R; ++r) {
-                const float2 dx = __fadd2_rn(xj, nxi[r]);
-                const float2 dy = __fadd2_rn(yj, nyi[r]);
-                const float2 dz = __fadd2_rn(zj, nzi[r]);
-                const float2 tx = __ffma2_rn(dx, invLx, magic2);
-                const float2 ty = __ffma2_rn(dy, invLy, magic2);
-                const float2 tz = __ffma2_rn(dz, invLz, magic2);
-                const float2 nx = __fadd2_rn(tx, nmagic2);
-                const float2 ny = __fadd2_rn(ty, nmagic2);
-                const float2 nz = __fadd2_rn(tz, nmagic2);
-                const float2 rx = __ffma2_rn(nx, nLx, dx);
-                const float2 ry = __ffma2_rn(ny, nLy, dy);
-                const float2 rz = __ffma2_rn(nz, nLz, dz);
-                // squares packed; the two adds stay scalar: ptxas 12.9 contracts
-                // mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would break the reference's
-                // rounding sequence (x*x + y*y) + z*z.
-                const float2 xx = __fmul2_rn(rx, rx);
-                const float2 yy = __fmul2_rn(ry, ry);
-                const float2 zz = __fmul2_rn(rz, rz);
-                float2 d2;
-                d2.x = __fadd_rn(__fadd_rn(xx.x, yy.x), zz.x);
-                d2.y = __fadd_rn(__fadd_rn(xx.y, yy.y), zz.y);
-                bin_two<AM>(d2, cut2, inv_step2, thr_c, cnt_delta, one, dump);
-              }
-            }
-          } else if (m != 0u) {
-            // some row groups of this warp are provably out of range of this sub-tile: same
-            // arithmetic, the (warp-uniform) mask skips them
-            for (int jj = q * SUB; jj < (q + 1) * SUB; jj += 2) {
-              const float2 xj = *reinterpret_cast<const float2*>(sx + jj);
-              const float2 yj = *reinterpret_cast<const float2*>(sy + jj);
-              const float2 zj = *reinterpret_cast<const float2*>(sz + jj);
-#pragma unroll
-              for (int r = 0; r < R; ++r) {
-                if ((m >> r) & 1u) {
-                  const float2 dx = __fadd2_rn(xj, nxi[r]);
-                  const float2 dy = __fadd2_rn(yj, nyi[r]);
-                  const float2 dz = __fadd2_rn(zj, nzi[r]);
-                  const float2 nx = __fadd2_rn(__ffma2_rn(dx, invLx, magic2), nmagic2);
-                  const float2 ny = __fadd2_rn(__ffma2_rn(dy, invLy, magic2), nmagic2);
-                  const float2 nz = __fadd2_rn(__ffma2_rn(dz, invLz, magic2), nmagic2);
-                  const float2 rx = __ffma2_rn(nx, nLx, dx);
-                  const float2 ry = __ffma2_rn(ny, nLy, dy);
-                  const float2 rz = __ffma2_rn(nz, nLz, dz);
-                  const float2 xx = __fmul2_rn(rx, rx);
-                  const float2 yy = __fmul2_rn(ry, ry);
-                  const float2 zz = __fmul2_rn(rz, rz);
-                  float2 d2;
-                  d2.x = __fadd_rn(__fadd_rn(xx.x, yy.x), zz.x);
-                  d2.y = __fadd_rn(__fadd_rn(xx.y, yy.y), zz.y);
-                  bin_two<AM>(d2, cut2, inv_step2, thr_c, cnt_delta, one, dump);
-                }
-              }
-            }
-          }
+          if (!CULL || m == FULL)
+            sub_tile<false, R, AM>(m, sx, sy, sz, q * SUB, nxi, nyi, nzi, geo);
+          else if (m != 0u)
+            sub_tile<true, R, AM>(m, sx, sy, sz, q * SUB, nxi, nyi, nzi, geo);
         }
       } else {
         // diagonal tiles (j > i mask) and the exact-division fallback: scalar path
@@ -479,9 +548,16 @@ __global__ void __launch_bounds__(NT) rdf_pair_hist_kernel(const __grid_constant
           }
         }
       }
-      __syncthreads();  // everyone is done reading this stage
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&s_ebar[stage]);  // this warp is done reading the stage
       const int jnn = jn < j_tile1 ? next_live(jn + 1) : j_tile1;
-      if (tid == 0 && jnn < j_tile1) issue(jnn, stage);
+      if (jnn < j_tile1) {
+        if (tid < 32) {
+          mbar_wait(&s_ebar[stage], ephase[stage]);
+          if (tid == 0) issue(jnn, stage);
+        }
+        ephase[stage] ^= 1u;
+      }
       jt = jn;
       jn = jnn;
       if (++tiles_since_flush >= P.flush_tiles) {
@@ -576,10 +652,13 @@ int launch_rdf(const RdfParams& P, size_t smem, int grid, cudaStream_t s) {
 template <int NT, int R>
 int launch_rdf_cfg(const RdfParams& P, size_t smem, int grid, cudaStream_t s, bool exact, int am) {
   if (exact) return launch_rdf<NT, R, true, 0, false>(P, smem, grid, s);
-  if (P.bbox) return launch_rdf<NT, R, false, 2, true>(P, smem, grid, s);  // culling: AM 2 only
+  if (P.bbox)  // culling variants: AM 2 (table) and AM 3 (fraction bits)
+    return am == 3 ? launch_rdf<NT, R, false, 3, true>(P, smem, grid, s)
+                   : launch_rdf<NT, R, false, 2, true>(P, smem, grid, s);
   switch (am) {
     case 0: return launch_rdf<NT, R, false, 0, false>(P, smem, grid, s);
     case 1: return launch_rdf<NT, R, false, 1, false>(P, smem, grid, s);
+    case 3: return launch_rdf<NT, R, false, 3, false>(P, smem, grid, s);
     default: return launch_rdf<NT, R, false, 2, false>(P, smem, grid, s);
   }
 }
@@ -696,7 +775,8 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
   int am = (flags >> 12) & 0xf;   // 0 = auto, else AM = am - 1
   if (cfg == 0) cfg = max_len <= 8192 ? 1 : 4;
   am = am == 0 ? 2 : am - 1;  // auto: unconditional ATOMS.POPC.INC (fastest measured)
-  MDK_CHECK_ARG(cfg >= 1 && cfg <= 4 && am >= 0 && am <= 2, "rdf_hist: bad tuning flags");
+  MDK_CHECK_ARG(cfg >= 1 && cfg <= 4 && am >= 0 && am <= 3, "rdf_hist: bad tuning flags");
+  if (am == 3 && nbins > FRAC_MAX_BINS) am = 2;  // fraction-bit binning needs nbins <= 15000
   const int NT = (cfg <= 2) ? 128 : 256;
   const int R = (cfg == 1 || cfg == 3) ? 2 : 4;
   const int TI = NT * R;
@@ -722,7 +802,7 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
   P.hist = hist;
   P.counter = reinterpret_cast<unsigned long long*>(work_counter);
 
-  const size_t smem = (size_t)2 * 3 * TJ * sizeof(float) + 2 * sizeof(uint64_t) +
+  const size_t smem = (size_t)2 * 3 * TJ * sizeof(float) + 4 * sizeof(uint64_t) +
                       2 * sizeof(unsigned long long) +
                       (size_t)((nbins + 1 + 3) & ~3) * sizeof(float) +
                       (size_t)(((nbins + 31) & ~31) + 32) * sizeof(unsigned);

@@ -21,15 +21,30 @@ import numpy as np
 from .config import config
 
 
+def _cuda_available() -> bool:
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:  # pragma: no cover
+        return False
+
+
 def join_path(*args) -> str:
     """meta_functions.join_path (:73-93): database paths always use '/'."""
     return "/".join(args)
 
 
 class TrajectoryStore:
-    def __init__(self, directory: Optional[str] = None):
+    def __init__(self, directory: Optional[str] = None, pinned: Optional[bool] = None):
         self.directory = directory
         self._arrays: Dict[str, np.ndarray] = {}
+        # in-memory stores live in page-locked host memory when a GPU is present: uploads and
+        # downloads are then single DMA transfers without a staging copy
+        if pinned is None:
+            pinned = directory is None and _cuda_available()
+        self.pinned = bool(pinned) and directory is None
+        self._pinned: Dict[str, object] = {}
         self._device_cache: "OrderedDict[Tuple, object]" = OrderedDict()
         self._device_bytes = 0
         self.h2d_bytes = 0  # bytes uploaded so far (bench.py reads this)
@@ -68,6 +83,12 @@ class TrajectoryStore:
         if self.directory is not None:
             arr = np.lib.format.open_memmap(self._file_of(path), mode="w+", dtype=np.float32,
                                             shape=tuple(int(s) for s in shape))
+        elif self.pinned:
+            import torch
+
+            t = torch.zeros(tuple(int(s) for s in shape), dtype=torch.float32, pin_memory=True)
+            self._pinned[path] = t
+            arr = t.numpy()
         else:
             arr = np.zeros(shape, dtype=np.float32)
         self._arrays[path] = arr
@@ -81,6 +102,7 @@ class TrajectoryStore:
             return old
         data = np.array(old)
         del self._arrays[path]
+        self._pinned.pop(path, None)
         self.invalidate(path)
         new = self.add_dataset(path, (old.shape[0], n_frames, old.shape[2]))
         new[:, : data.shape[1]] = data
@@ -101,6 +123,7 @@ class TrajectoryStore:
             raise ValueError("datasets are (n_rows, n_frames, n_dims)")
         if path in self._arrays:
             del self._arrays[path]
+            self._pinned.pop(path, None)
             self.invalidate(path)
         arr = self.add_dataset(path, array.shape)
         arr[...] = array.astype(np.float32, copy=False)
@@ -172,7 +195,13 @@ class TrajectoryStore:
             _, old = self._device_cache.popitem(last=False)
             self._device_bytes -= old.numel() * old.element_size()
         out = torch.empty(src.shape, dtype=torch.float32, device=dev)
-        self._upload(src, out)
+        pin = self._pinned.get(path)
+        if pin is not None and row_index is None:
+            out.copy_(pin[lo:hi], non_blocking=True)     # one DMA from page-locked memory
+            torch.cuda.current_stream().synchronize()
+            self.h2d_bytes += nbytes
+        else:
+            self._upload(src, out)
         self._device_cache[key] = out
         self._device_bytes += nbytes
         return out
@@ -203,10 +232,24 @@ class TrajectoryStore:
         self._upload(np.ascontiguousarray(src), out)
         return out
 
+    def write_from_device(self, path: str, tensor, t0: int = 0):
+        """Device tensor (n_rows, k, n_dims) -> frames [t0, t0 + k) of the host dataset."""
+        import torch
+
+        arr = self._arrays[path]
+        k = tensor.shape[1]
+        pin = self._pinned.get(path)
+        if pin is not None:
+            pin[:, t0:t0 + k].copy_(tensor, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        else:
+            arr[:, t0:t0 + k] = tensor.cpu().numpy()
+
     def remove(self, path: str):
         """Delete a dataset (host, disk and device copies)."""
         self.invalidate(path)
         arr = self._arrays.pop(path, None)
+        self._pinned.pop(path, None)
         del arr
         if self.directory is not None and os.path.exists(self._file_of(path)):
             os.remove(self._file_of(path))

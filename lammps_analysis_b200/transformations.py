@@ -62,7 +62,7 @@ class _SingleSpeciesTrafo(Transformations):
                 continue  # transformations.py:466-473
             paths = [self._require(sp, p) for p in self.input_properties]
             n_atoms, n_frames, _ = exp.store.shape(paths[0])
-            out_host = exp.store.add_dataset(out_path, (n_atoms, n_frames, self.output_dims))
+            exp.store.add_dataset(out_path, (n_atoms, n_frames, self.output_dims))
             per_frame = n_atoms * 12 * (len(paths) + 1)
             frames_per_chunk = max(1, min(n_frames, self.chunk_bytes // max(per_frame, 1)))
             carry = None
@@ -76,7 +76,7 @@ class _SingleSpeciesTrafo(Transformations):
                               .cuda() for p in paths]
                 out_dev = torch.empty_like(inputs[0])
                 carry = self.transform_batch(inputs, out_dev, carry)
-                out_host[:, t0:t1] = out_dev.cpu().numpy()
+                exp.store.write_from_device(out_path, out_dev, t0)
                 whole = out_dev if (t0 == 0 and t1 == n_frames) else None
             exp.store.invalidate(out_path)
             if whole is not None:

@@ -56,7 +56,8 @@ def test_rdf_counts_bit_exact(cuda, n_atoms, n_frames, box):
     assert got.sum() > 0
 
 
-@pytest.mark.parametrize("tuning", [0x100, 0x200, 0x300, 0x400, 0x1100, 0x2100, 0x3100])
+@pytest.mark.parametrize("tuning", [0x100, 0x200, 0x300, 0x400, 0x1100, 0x2100, 0x3100,
+                                    0x4100, 0x4400])
 def test_rdf_kernel_variants_agree(cuda, tuning):
     """Every tile configuration / atomic mode yields the same integers."""
     from lammps_analysis_b200.engine import RdfEngine, to_device_f32
@@ -108,7 +109,8 @@ def test_rdf_single_species_and_empty(cuda):
     assert eng2.counts().sum() == 0
 
 
-def test_rdf_sorted_culled_matches_oracle(cuda):
+@pytest.mark.parametrize("tuning", [0, 0x4000])
+def test_rdf_sorted_culled_matches_oracle(cuda, tuning):
     """Morton-ordered pack + block culling: same integers as the oracle (two species, so the
     cross-species tiles and the diagonal tiles are both exercised)."""
     from lammps_analysis_b200.engine import RdfEngine, to_device_f32
@@ -123,14 +125,15 @@ def test_rdf_sorted_culled_matches_oracle(cuda):
     ref = orc.rdf_counts(pos, ["A", "B"], box, np.arange(1), cutoff, nbins, 100, 1)
     eng = RdfEngine([n, n + 37], box, cutoff, nbins, device=cuda, spatial_sort=True)
     assert eng.spatial_sort
-    eng.add_frames([to_device_f32(pos[s], cuda) for s in ("A", "B")], np.arange(1))
+    eng.add_frames([to_device_f32(pos[s], cuda) for s in ("A", "B")], np.arange(1), tuning=tuning)
     got = eng.counts()
     for p, key in enumerate(["A_A", "A_B", "B_B"]):
         assert np.array_equal(got[p], ref[key]), key
 
 
+@pytest.mark.parametrize("tuning", [0, 0x4000])
 @pytest.mark.parametrize("cutoff_frac", [0.12, 0.3, 0.4999])
-def test_rdf_culling_is_exact_at_scale(cuda, cutoff_frac):
+def test_rdf_culling_is_exact_at_scale(cuda, cutoff_frac, tuning):
     """Size-independent property: the culled, spatially sorted pass returns exactly the
     histogram of the plain all-pairs pass (100,000 atoms, 5e9 pairs per frame)."""
     import torch
@@ -144,7 +147,7 @@ def test_rdf_culling_is_exact_at_scale(cuda, cutoff_frac):
     plain = RdfEngine([n], [L] * 3, cutoff, nbins, device=cuda, spatial_sort=False)
     plain.add_frames([traj], np.arange(2))
     culled = RdfEngine([n], [L] * 3, cutoff, nbins, device=cuda, spatial_sort=True)
-    culled.add_frames([traj], np.arange(2))
+    culled.add_frames([traj], np.arange(2), tuning=tuning)
     a, b = plain.counts(), culled.counts()
     assert a.sum() > 0 and np.array_equal(a, b)
 

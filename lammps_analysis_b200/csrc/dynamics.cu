@@ -88,44 +88,56 @@ msd_windowed_kernel(const float* __restrict__ traj, long long T, long long a_lo,
 }
 
 // ---- Einstein MSD, dense lags (tau = 0 .. n_lags-1, correlation_time 1) ----------------------
-// Thread k owns the MD_R consecutive lags k*MD_R .. k*MD_R+MD_R-1 and slides over the window
-// origins: the MD_R positions x(w + lag) it needs at origin w are kept in a register ring, so
-// one origin costs ONE new position load (plus the broadcast origin) for MD_R updates instead
-// of one load per update.  MD_R is odd, which makes the lane stride (MD_R positions) conflict
-// free for the float2 {x,y} array and the z array in shared memory.  Differences and squares
-// run on FADD2/FFMA2 for {x,y} and FADD/FFMA for z; fp32 partial sums over MD_FOLD origins are
-// folded into fp64.
-constexpr int MD_R = 9;
+// A thread owns R consecutive lags and slides over window origins: the R positions x(w + lag) it
+// needs at origin w are kept in a register ring, so one origin costs ONE new position load (plus
+// the broadcast origin) for R updates instead of one load per update.  Threads are arranged as
+// G = ceil(lags / R) lag-threads x NG = NT / G window groups, so that short lag ranges (the
+// reference's default data_range is 100) still fill the CTA: group g sweeps its own slice of the
+// window chunk.  The lane stride is R = 9 positions: odd, hence bank-conflict free (a skewed
+// index for R = 8 was measured slower).
+// Differences and squares run on FADD2/FFMA2 for {x,y} and FADD/FFMA for z; fp32 partial sums
+// over MD_FOLD * R origins are folded into fp64.
 constexpr int MD_NT = 64;
-constexpr int MD_FOLD = 3;  // outer iterations (of MD_R origins) between fp64 folds
+constexpr int MD_FOLD = 3;  // outer iterations (of R origins) between fp64 folds
 
+constexpr int MD_R = 9;  // odd: the lane stride of MD_R positions is bank-conflict free
+
+template <bool GROUPS>
 __global__ void __launch_bounds__(MD_NT)
 msd_dense_kernel(const float* __restrict__ traj, long long T, long long a_lo, long long a_hi,
                  int atoms_per_cta, long long t0, int W, int n_lags, int Wc, int len_alloc,
                  double* __restrict__ msd_sum) {
-  extern __shared__ __align__(16) float md_smem[];  // xy: 2*len_alloc floats, z: len_alloc floats
+  constexpr int R = MD_R;
+  extern __shared__ __align__(16) float md_smem[];
+  // layout: xy (float2 x len_alloc) | z (len_alloc floats) | origin copies for lag blocks > 0
   float2* s_xy = reinterpret_cast<float2*>(md_smem);
   float* s_z = md_smem + 2 * len_alloc;
+  float* s_oxy = s_z + len_alloc;  // xy (2*Wc) then z (Wc)
   const int tid = threadIdx.x;
   const int w0 = blockIdx.x * Wc;
   const int w1 = min(W, w0 + Wc);
   if (w0 >= w1) return;
   const int nw = w1 - w0;
-  const int lag0 = (blockIdx.z * MD_NT + tid) * MD_R;  // first lag of this thread
-  const int lag_blk0 = blockIdx.z * MD_NT * MD_R;
-  const int lags_here = min(n_lags - lag_blk0, MD_NT * MD_R);
-  const int len = nw + lags_here - 1;                  // frames staged per atom
-  const long long t_begin = t0 + w0 + lag_blk0;        // smem index 0 <-> this frame ...
-  // ... but origins start at lag_blk0 frames *before* it: stage origins separately when the
-  // lag block is not the first one.
+  const int lag_blk0 = blockIdx.z * MD_NT * R;
+  const int lags_here = min(n_lags - lag_blk0, MD_NT * R);
+  // GROUPS: G lag-threads x NG window groups; otherwise every thread is a lag-thread and sweeps
+  // the whole window chunk (the lag range fills the CTA)
+  const int G = GROUPS ? (lags_here + R - 1) / R : MD_NT;
+  const int NG = GROUPS ? MD_NT / G : 1;
+  const int k = GROUPS ? tid % G : tid, wg = GROUPS ? tid / G : 0;
+  const bool active = wg < NG;
+  const int nwg = GROUPS ? (nw + NG - 1) / NG : nw;  // origins per group
+  const int ws_lo = GROUPS ? min(wg * nwg, nw) : 0;
+  const int ws_hi = GROUPS ? (active ? min(nw, ws_lo + nwg) : ws_lo) : nw;
+  const int len = nw + lags_here - 1;             // frames staged per atom
+  const long long t_begin = t0 + w0 + lag_blk0;   // slab index 0 <-> this frame
   const long long a0 = a_lo + (long long)blockIdx.y * atoms_per_cta;
   const long long a1 = min(a_hi, a0 + atoms_per_cta);
-  const int kR = tid * MD_R;  // local lag offset inside the block
-  float* s_oxy = s_z + len_alloc;  // origin copies for lag blocks > 0: xy (2*Wc) then z (Wc)
+  const int kR = k * R;
 
-  double acc64[MD_R];
+  double acc64[R];
 #pragma unroll
-  for (int b = 0; b < MD_R; ++b) acc64[b] = 0.0;
+  for (int b = 0; b < R; ++b) acc64[b] = 0.0;
 
   for (long long a = a0; a < a1; ++a) {
     const float* __restrict__ row = traj + (size_t)a * T * 3;
@@ -147,42 +159,44 @@ msd_dense_kernel(const float* __restrict__ traj, long long T, long long a_lo, lo
       }
     }
     __syncthreads();
-    const float2* __restrict__ o_xy = lag_blk0 > 0 ? reinterpret_cast<const float2*>(s_oxy) : s_xy;
+    const float2* __restrict__ o_xy =
+        lag_blk0 > 0 ? reinterpret_cast<const float2*>(s_oxy) : s_xy;
     const float* __restrict__ o_z = lag_blk0 > 0 ? s_oxy + 2 * Wc : s_z;
 
-    float2 qxy[MD_R];
-    float qz[MD_R];
+    float2 qxy[R];
+    float qz[R];
 #pragma unroll
-    for (int b = 0; b < MD_R; ++b) {
-      qxy[b] = s_xy[kR + b];
-      qz[b] = s_z[kR + b];
+    for (int b = 0; b < R; ++b) {
+      const int p = min(ws_lo + kR + b, len_alloc - 1);
+      qxy[b] = s_xy[p];
+      qz[b] = s_z[p];
     }
-    float2 axy[MD_R];
-    float az[MD_R];
+    float2 axy[R];
+    float az[R];
 #pragma unroll
-    for (int b = 0; b < MD_R; ++b) {
+    for (int b = 0; b < R; ++b) {
       axy[b] = make_float2(0.f, 0.f);
       az[b] = 0.f;
     }
     int fold = 0;
-    for (int w = 0; w < nw; w += MD_R) {
+    for (int w = ws_lo; w < ws_lo + nwg; w += R) {
 #pragma unroll
-      for (int s = 0; s < MD_R; ++s) {
+      for (int s = 0; s < R; ++s) {
         const int ws = w + s;
-        if (ws < nw) {
+        if (ws < ws_hi) {
           const float2 oxy = o_xy[ws];
           const float2 noxy = make_float2(-oxy.x, -oxy.y);
           const float noz = -o_z[ws];
 #pragma unroll
-          for (int b = 0; b < MD_R; ++b) {
-            const int slot = (s + b) % MD_R;
+          for (int b = 0; b < R; ++b) {
+            const int slot = (s + b) % R;
             const float2 d = __fadd2_rn(qxy[slot], noxy);
             const float dz = qz[slot] + noz;
             axy[b] = __ffma2_rn(d, d, axy[b]);
             az[b] = fmaf(dz, dz, az[b]);
           }
-          // slot s held frame ws + lag0: dead now; refill with frame ws + lag0 + MD_R
-          const int nx = min(ws + kR + MD_R, len_alloc - 1);
+          // slot s held frame ws + lag: dead now; refill with frame ws + lag + R
+          const int nx = min(ws + kR + R, len_alloc - 1);
           qxy[s] = s_xy[nx];
           qz[s] = s_z[nx];
         }
@@ -190,7 +204,7 @@ msd_dense_kernel(const float* __restrict__ traj, long long T, long long a_lo, lo
       if (++fold == MD_FOLD) {
         fold = 0;
 #pragma unroll
-        for (int b = 0; b < MD_R; ++b) {
+        for (int b = 0; b < R; ++b) {
           acc64[b] += (double)((axy[b].x + axy[b].y) + az[b]);
           axy[b] = make_float2(0.f, 0.f);
           az[b] = 0.f;
@@ -198,12 +212,14 @@ msd_dense_kernel(const float* __restrict__ traj, long long T, long long a_lo, lo
       }
     }
 #pragma unroll
-    for (int b = 0; b < MD_R; ++b) acc64[b] += (double)((axy[b].x + axy[b].y) + az[b]);
+    for (int b = 0; b < R; ++b) acc64[b] += (double)((axy[b].x + axy[b].y) + az[b]);
   }
+  if (active) {
 #pragma unroll
-  for (int b = 0; b < MD_R; ++b) {
-    const int k = lag0 + b;
-    if (k < n_lags) atomicAdd(msd_sum + k, acc64[b]);
+    for (int b = 0; b < R; ++b) {
+      const int lag = lag_blk0 + kR + b;
+      if (kR + b < lags_here && lag < n_lags) atomicAdd(msd_sum + lag, acc64[b]);
+    }
   }
 }
 
@@ -549,23 +565,33 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
   if (W == 0 || a_lo == a_hi) return MDK_OK;
   MDK_CHECK_ARG(t0 >= 0 && t0 + (long long)(W - 1) + n_lags <= T,
                 "msd_dense: windows [t0=%lld, W=%d, n_lags=%d] exceed T=%lld", t0, W, n_lags, T);
-  const int lag_span = MD_NT * MD_R;
+  constexpr int R = MD_R;
+  const int lag_span = MD_NT * R;
   const int lag_blocks = (n_lags + lag_span - 1) / lag_span;
   const int Wc = W < 512 ? W : 512;
   // every thread may read up to one ring refill past its last lag: size the tile for the full
   // lag span of a block so that those (discarded) reads stay inside the allocation
-  const int len_alloc = (Wc + lag_span + MD_R + 3) & ~3;  // multiple of 4: float2 views stay aligned
+  const int len_alloc = (Wc + lag_span + R + 3) & ~3;  // multiple of 4: float2 views stay aligned
   const size_t smem = ((size_t)3 * len_alloc + (lag_blocks > 1 ? (size_t)3 * Wc : 0)) * sizeof(float);
   const int chunks = (W + Wc - 1) / Wc;
   // 64-thread CTAs: aim for several waves of ~11 resident CTAs per SM
   const int apc = pick_atoms_per_cta(a_hi - a_lo, (long long)chunks * lag_blocks, 48);
   const long long groups = (a_hi - a_lo + apc - 1) / apc;
   MDK_CHECK_ARG(groups <= 65535 && lag_blocks <= 65535, "msd_dense: grid too large");
-  MDK_CUDA(cudaFuncSetAttribute(msd_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
   dim3 grid(chunks, (unsigned)groups, lag_blocks);
-  msd_dense_kernel<<<grid, MD_NT, smem, as_stream(stream)>>>(traj, T, a_lo, a_hi, apc, t0, W,
-                                                             n_lags, Wc, len_alloc, msd_sum);
+  // window groups only pay off when the lag range leaves at least half of the CTA idle
+  const bool grouped = lag_blocks == 1 && (n_lags + R - 1) / R <= MD_NT / 2;
+  if (grouped) {
+    MDK_CUDA(cudaFuncSetAttribute(msd_dense_kernel<true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    msd_dense_kernel<true><<<grid, MD_NT, smem, as_stream(stream)>>>(
+        traj, T, a_lo, a_hi, apc, t0, W, n_lags, Wc, len_alloc, msd_sum);
+  } else {
+    MDK_CUDA(cudaFuncSetAttribute(msd_dense_kernel<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    msd_dense_kernel<false><<<grid, MD_NT, smem, as_stream(stream)>>>(
+        traj, T, a_lo, a_hi, apc, t0, W, n_lags, Wc, len_alloc, msd_sum);
+  }
   MDK_LAUNCH_CHECK();
   return MDK_OK;
 }

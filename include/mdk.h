@@ -189,6 +189,24 @@ int mdk_ionic_current(const float* vel, long long A, long long T, const void* q,
                       double* J, mdk_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
+ * Ingest (HOST code, no GPU involved): LAMMPS text dump tokenizer
+ * ------------------------------------------------------------------------- */
+
+/* Scans the first frame header and counts the lines of a LAMMPS dump.
+ *   steps[2] : TIMESTEP of the first two frames (sample rate = steps[1] - steps[0])
+ *   box[6]   : xlo xhi ylo yhi zlo zhi;  columns: the names after "ITEM: ATOMS"
+ * Replaces: file_io/lammps_trajectory_files.py:100-243 (metadata). */
+int mdk_lammps_scan(const char* path, long long* n_atoms, long long* n_frames, long long* steps,
+                    double* box, char* columns, int columns_cap);
+
+/* Reads n frames starting at byte *offset (0 first; updated) into out[n][n_atoms][n_cols]
+ * float64.  Numbers via strtod (== Python float()), non-numeric tokens -> NaN, rows stably
+ * sorted by column id_col per frame unless `sorted`.
+ * Replaces: file_io/tabular_text_files.py:122-220 (_read_process_n_configurations). */
+int mdk_lammps_read(const char* path, long long n_atoms, int n_cols, int id_col, int sorted,
+                    long long n, long long* offset, double* out);
+
+/* ------------------------------------------------------------------------- *
  * Measurement helpers (bench.py / tests only)
  * ------------------------------------------------------------------------- */
 

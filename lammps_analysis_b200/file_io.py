@@ -109,15 +109,69 @@ class LAMMPSTrajectoryFile:
 
     n_header_lines = 9
 
-    def __init__(self, file_path: str, trajectory_is_sorted_by_ids: bool = False):
+    def __init__(self, file_path: str, trajectory_is_sorted_by_ids: bool = False,
+                 native: bool = True):
         self.file_path = str(file_path)
         self.sorted_by_ids = trajectory_is_sorted_by_ids
+        # native=True parses with the C++ tokenizer of libmdk (mdk_lammps_scan / mdk_lammps_read);
+        # native=False keeps the pure-Python parser (used to cross-check the two in the tests)
+        self.native = native
         self._meta = None
 
     def _read_header(self, fh):
         return [fh.readline() for _ in range(self.n_header_lines)]
 
+    def _scan_native(self):
+        import ctypes as C
+
+        from . import _lib
+
+        lib = _lib.load()
+        n_atoms, n_frames = C.c_longlong(), C.c_longlong()
+        steps = (C.c_longlong * 2)()
+        box = (C.c_double * 6)()
+        cols = C.create_string_buffer(4096)
+        _lib.check(lib.mdk_lammps_scan(self.file_path.encode(), C.byref(n_atoms), C.byref(n_frames),
+                                       steps, box, cols, 4096), "mdk_lammps_scan")
+        columns = cols.value.decode().split()
+        first = self._read_native(0, 1, int(n_atoms.value), columns)[0][0]  # id-sorted frame 0
+        return (int(n_atoms.value), int(n_frames.value), columns,
+                [box[2 * d + 1] - box[2 * d] for d in range(3)], int(steps[1] - steps[0]), first)
+
+    def _read_native(self, offset: int, n: int, n_atoms: int, columns):
+        import ctypes as C
+
+        from . import _lib
+
+        out = np.empty((n, n_atoms, len(columns)), dtype=np.float64)
+        off = C.c_longlong(offset)
+        _lib.check(_lib.load().mdk_lammps_read(self.file_path.encode(), n_atoms, len(columns),
+                                               columns.index("id"), int(self.sorted_by_ids), n,
+                                               C.byref(off), out.ctypes.data_as(C.c_void_p)),
+                   "mdk_lammps_read")
+        return out, int(off.value)
+
+    def _species_names_of_first_frame(self, columns, sp_col, n_atoms):
+        """Species labels (strings) of the id-sorted first frame."""
+        with open(self.file_path) as fh:
+            for _ in range(self.n_header_lines):
+                fh.readline()
+            rows = [fh.readline().split() for _ in range(n_atoms)]
+        ids = np.array([float(r[columns.index("id")]) for r in rows])
+        order = np.arange(n_atoms) if self.sorted_by_ids else np.argsort(ids, kind="stable")
+        return [rows[i][columns.index(sp_col)] for i in order]
+
     def _scan(self):
+        if self.native:
+            n_atoms, n_cfg, columns, box_l, sample_rate, _first = self._scan_native()
+            if "id" not in columns:
+                raise ValueError("LAMMPS dump needs an 'id' column")
+            sp_col = "element" if "element" in columns else ("type" if "type" in columns else None)
+            if sp_col is None:
+                raise ValueError("LAMMPS dump needs an 'element' or 'type' column")
+            names = self._species_names_of_first_frame(columns, sp_col, n_atoms)
+            self._finish_scan(columns, n_atoms, n_cfg, names, box_l, sample_rate)
+            return
         with open(self.file_path) as fh:
             header = self._read_header(fh)
             n_atoms = int(header[3].split()[0])
@@ -144,6 +198,9 @@ class LAMMPSTrajectoryFile:
         ids = np.array([float(r[columns.index("id")]) for r in first])
         order = np.arange(n_atoms) if self.sorted_by_ids else np.argsort(ids, kind="stable")
         names = [first[i][columns.index(sp_col)] for i in order]
+        self._finish_scan(columns, n_atoms, n_cfg, names, box_l, sample_rate)
+
+    def _finish_scan(self, columns, n_atoms, n_cfg, names, box_l, sample_rate):
         species_rows: Dict[str, List[int]] = {}
         for sorted_pos, nm in enumerate(names):
             species_rows.setdefault(nm, []).append(sorted_pos)
@@ -170,6 +227,14 @@ class LAMMPSTrajectoryFile:
         """Yields TrajectoryChunkData (tabular_text_files.py:122-220)."""
         self.metadata
         id_col = self._columns.index("id")
+        if self.native:
+            done, offset = 0, 0
+            while done < self._n_cfg:
+                k = min(batch_size, self._n_cfg - done)
+                block, offset = self._read_native(offset, k, self._n_atoms, self._columns)
+                yield self._chunk_from_block(block, k)
+                done += k
+            return
         with open(self.file_path) as fh:
             done = 0
             while done < self._n_cfg:
@@ -183,14 +248,18 @@ class LAMMPSTrajectoryFile:
                     if not self.sorted_by_ids:
                         tab = tab[np.argsort(tab[:, id_col], kind="stable")]
                     block[f] = tab
-                chunk = TrajectoryChunkData(k)
-                for sp, rows in self._species_rows.items():
-                    chunk.data[sp] = {
-                        prop: np.swapaxes(block[:, rows][:, :, cols], 0, 1)
-                        for prop, cols in self._props.items()
-                    }
                 done += k
-                yield chunk
+                yield self._chunk_from_block(block, k)
+
+    def _chunk_from_block(self, block, k):
+        """(k, n_atoms, n_columns) id-sorted table -> per species / property arrays."""
+        chunk = TrajectoryChunkData(k)
+        for sp, rows in self._species_rows.items():
+            chunk.data[sp] = {
+                prop: np.swapaxes(block[:, rows][:, :, cols], 0, 1)
+                for prop, cols in self._props.items()
+            }
+        return chunk
 
 
 def _to_float(tok: str) -> float:

@@ -149,15 +149,34 @@ def test_lammps_dump_roundtrip_with_unsorted_ids(tmp_path):
         rng.shuffle(rows)
         out += blk[:9] + list(rows)
     open(path, "w").write("\n".join(out) + "\n")
-    reader = LAMMPSTrajectoryFile(path)
-    meta = reader.metadata
-    assert meta.n_configurations == 4 and meta.sample_rate == 5 and meta.box_l == [12.0] * 3
-    assert [(s.name, s.n_particles) for s in meta.species_list] == [("Na", 32), ("Cl", 32)]
-    chunks = list(reader.get_configurations_generator(3))
-    for sp in ("Na", "Cl"):
-        for prop in ("Positions", "Velocities"):
-            got = np.concatenate([c.data[sp][prop] for c in chunks], axis=1)
-            assert np.array_equal(got.astype(np.float32), data[sp][prop])
+    results = {}
+    for native in (True, False):     # C++ tokenizer of libmdk and the pure-Python parser
+        reader = LAMMPSTrajectoryFile(path, native=native)
+        meta = reader.metadata
+        assert meta.n_configurations == 4 and meta.sample_rate == 5 and meta.box_l == [12.0] * 3
+        assert [(s.name, s.n_particles) for s in meta.species_list] == [("Na", 32), ("Cl", 32)]
+        chunks = list(reader.get_configurations_generator(3))
+        for sp in ("Na", "Cl"):
+            for prop in ("Positions", "Velocities"):
+                got = np.concatenate([c.data[sp][prop] for c in chunks], axis=1)
+                assert np.array_equal(got.astype(np.float32), data[sp][prop])
+                results[(native, sp, prop)] = got
+    for (native, sp, prop), got in results.items():
+        assert np.array_equal(got, results[(not native, sp, prop)])   # bit-identical float64
+
+
+def test_native_lammps_reader_rejects_truncated_file(tmp_path):
+    from lammps_analysis_b200._lib import MdkError
+    from lammps_analysis_b200.file_io import LAMMPSTrajectoryFile, write_lammps_dump
+    from lammps_analysis_b200.synthetic import nacl_trajectory
+
+    data, box = nacl_trajectory(8, 3, 6.0, 1)
+    path = str(tmp_path / "t.lammpstraj")
+    write_lammps_dump(path, data, box)
+    lines = open(path).read().splitlines()
+    open(path, "w").write("\n".join(lines[:-3]) + "\n")
+    with pytest.raises(MdkError):
+        LAMMPSTrajectoryFile(path).metadata
 
 
 def test_closed_form_einstein_fit_matches_curve_fit():

@@ -265,3 +265,126 @@ def test_two_gpu_sharding_matches_single_rank(cuda):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "multigpu_check ok on 2 ranks" in res.stdout
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------
+def _small_project(tmp_path, name, data, box, **kw):
+    from lammps_analysis_b200.config import config
+    from lammps_analysis_b200.file_io import ScriptInput
+    from lammps_analysis_b200.project import Project
+
+    config.planner_memory_bytes = MEM
+    project = Project(name, storage_path=str(tmp_path))
+    exp = project.add_experiment("X", timestep=0.001, temperature=300.0, units="real")
+    exp.add_data(ScriptInput(data, box, atom_major=True, **kw))
+    return project, exp
+
+
+def test_rdf_three_species_noncubic_box_and_tiny_species(tmp_path, cuda):
+    """3 species (6 pairs), orthorhombic box, one species with a single atom (after the
+    reference's first-atom drop it contributes nothing), explicit cutoff / bins / frame range."""
+    from oracle import rdf as orc
+
+    rng = np.random.default_rng(51)
+    box = np.array([21.0, 17.5, 25.0])
+    counts = {"A": 150, "B": 1, "C": 77}
+    data = {s: {"Positions": (rng.random((n, 9, 3)) * box).astype(np.float32)}
+            for s, n in counts.items()}
+    project, exp = _small_project(tmp_path, "rdf3", data, box)
+    res = exp.run.RadialDistributionFunction(number_of_configurations=4, start=1, stop=7,
+                                             cutoff=8.0, number_of_bins=123, plot=False)
+    frames = orc.sample_configurations(1, 7, 4)
+    ref_counts = orc.rdf_counts({s: data[s]["Positions"] for s in counts}, list(counts), box,
+                                frames, 8.0, 123, 4, 4)
+    ref = orc.rdf_normalise(ref_counts, counts, box, 8.0, 123, 4, 1e-10)
+    assert res.keys() == ["A_A", "A_B", "A_C", "B_B", "B_C", "C_C"]
+    for key in res.keys():
+        y, yr = np.array(res[key]["y"])[1:], np.array(ref[key]["y"])[1:]
+        np.testing.assert_allclose(y, yr, rtol=RTOL)
+    assert np.all(np.array(res["A_B"]["y"])[1:] == 0) and np.all(np.array(res["B_B"]["y"])[1:] == 0)
+
+
+def test_rdf_atom_selection_and_species_subset(tmp_path, cuda):
+    from oracle import rdf as orc
+
+    rng = np.random.default_rng(52)
+    box = np.array([15.0, 15.0, 15.0])
+    data = {s: {"Positions": (rng.random((90, 5, 3)) * 15).astype(np.float32)} for s in "AB"}
+    project, exp = _small_project(tmp_path, "rdfsel", data, box)
+    sel = {"A": [3, 5, 8, 13, 21, 34, 55, 89], "B": list(range(10, 40))}
+    res = exp.run.RadialDistributionFunction(number_of_configurations=5, atom_selection=sel,
+                                             plot=False)
+    picked = {s: data[s]["Positions"][sel[s]] for s in "AB"}
+    cutoff = orc.default_cutoff(box)
+    nbins = orc.default_number_of_bins(cutoff)
+    ref_counts = orc.rdf_counts(picked, ["A", "B"], box, orc.sample_configurations(0, 4, 5),
+                                cutoff, nbins, 5, 5)
+    ref = orc.rdf_normalise(ref_counts, {"A": 8, "B": 30}, box, cutoff, nbins, 5, 1e-10)
+    for key in res.keys():
+        np.testing.assert_allclose(np.array(res[key]["y"])[1:], np.array(ref[key]["y"])[1:],
+                                   rtol=RTOL)
+    only_b = exp.run.RadialDistributionFunction(number_of_configurations=5, species=["B"],
+                                                plot=False)
+    assert only_b.keys() == ["B_B"]
+
+
+def test_rdf_duplicate_sample_frames_rejected(tmp_path, cuda):
+    rng = np.random.default_rng(53)
+    data = {"A": {"Positions": (rng.random((20, 10, 3)) * 9).astype(np.float32)}}
+    project, exp = _small_project(tmp_path, "rdfdup", data, [9.0] * 3)
+    with pytest.raises(ValueError):
+        # default number_of_configurations=500 > 10 frames (the reference fails in h5py here)
+        exp.run.RadialDistributionFunction(plot=False)
+
+
+def test_einstein_tau_resolution_and_correlation_time(tmp_path, cuda):
+    """tau_values as an int (sub-sampled lags) and correlation_time > 1 go through the generic
+    kernel; results follow the oracle."""
+    from oracle import dynamics as od
+
+    rng = np.random.default_rng(54)
+    A, T, N = 40, 500, 90
+    x = np.cumsum(rng.normal(0, 0.2, size=(A, T, 3)), axis=1).astype(np.float32)
+    project, exp = _small_project(tmp_path, "eintau", {"Ar": {"Unwrapped_Positions": x}},
+                                  [40.0] * 3)
+    # with 16 lags the default fit_range (data_range - 1) is never reached -- the reference
+    # crashes on that too -- so the fit end index is given explicitly
+    res = exp.run.EinsteinDiffusionCoefficients(data_range=N, correlation_time=3, tau_values=16,
+                                                fit_range=15, plot=False)
+    plan = _oracle_plan(A, T, N, 3, 150)
+    tau, dr, _, times = od.handle_tau_values(16, N, 0.001, 1)
+    msd_sum, count = od.einstein_msd(x, plan, dr, 3, tau)
+    np.testing.assert_allclose(res["Ar"]["msd"], np.array(msd_sum) / count * 1e-20, rtol=RTOL)
+    np.testing.assert_allclose(res["Ar"]["time"], times * 1e-15, rtol=1e-12)
+
+
+def test_missing_data_errors(tmp_path, cuda):
+    from lammps_analysis_b200.transformations import CannotFindPropertyError
+
+    rng = np.random.default_rng(55)
+    data = {"A": {"Positions": (rng.random((20, 30, 3)) * 9).astype(np.float32)}}
+    project, exp = _small_project(tmp_path, "missing", data, [9.0] * 3)
+    with pytest.raises(CannotFindPropertyError):
+        exp.run.GreenKuboIonicConductivity(data_range=10, plot=False)   # no velocities
+    with pytest.raises(KeyError):
+        exp.run.GreenKuboDiffusionCoefficients(data_range=10, plot=False)
+    # unwrapping works and is skipped the second time
+    exp.run.CoordinateUnwrapper()
+    first = exp.store.host("A/Unwrapped_Positions").copy()
+    exp.run.CoordinateUnwrapper()
+    assert np.array_equal(first, exp.store.host("A/Unwrapped_Positions"))
+
+
+def test_unwrap_via_indices_is_chosen_when_box_images_exist(tmp_path, cuda):
+    rng = np.random.default_rng(56)
+    pos = (rng.random((15, 40, 3)) * 7).astype(np.float32)
+    img = rng.integers(-2, 3, size=(15, 40, 3)).astype(np.float32)
+    project, exp = _small_project(tmp_path, "uvi", {"A": {"Positions": pos, "Box_Images": img}},
+                                  [7.0, 7.5, 8.0])
+    calc = exp.run.EinsteinDiffusionCoefficients
+    type(calc).__call__.__wrapped__(calc, data_range=10, plot=False)
+    calc.check_input()          # dependency resolution: trajectory_calculator.py:117-194
+    want = (pos.astype(np.float64) + img.astype(np.float64) * np.array([7.0, 7.5, 8.0]))
+    assert np.array_equal(exp.store.host("A/Unwrapped_Positions"), want.astype(np.float32))

@@ -306,7 +306,7 @@ acf_lagprod_kernel(const float* __restrict__ traj, long long T, long long a_lo, 
 // (3 * GB_FOLD products), then folds into the global fp64 P with atomicAdd(double).
 constexpr int GB_T = 64;      // tile edge
 constexpr int GB_NT = 64;     // threads per CTA (2 warps)
-constexpr int GB_KA = 8;      // atoms per pipeline stage
+constexpr int GB_KA = 4;      // atoms per pipeline stage (22 KB per CTA with 3 stages)
 constexpr int GB_ST = 3;      // pipeline stages
 constexpr int GB_FOLD = 256;  // atoms per fp32 accumulation run
 constexpr int GB_ROW = GB_T + 12;        // padded SoA row: dims land 12 banks apart, so the

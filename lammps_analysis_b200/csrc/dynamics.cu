@@ -628,7 +628,7 @@ extern "C" int mdk_acf_lagprod(const float* traj, long long A, long long T, long
   const int nbj = (GB_T - 1 + N - 1) / GB_T + 1;
   const long long tiles = (long long)n_bi * nbj;
   // atom split: enough CTAs to fill the machine several times over, at least GB_KA atoms each
-  long long want = ((long long)sm_count() * 24 + tiles - 1) / tiles;
+  long long want = ((long long)sm_count() * 96 + tiles - 1) / tiles;  // ~12 waves of 8 CTAs/SM
   if (want < 1) want = 1;
   long long apc = (n_atoms + want - 1) / want;
   if (apc < 64) apc = n_atoms < 64 ? n_atoms : 64;

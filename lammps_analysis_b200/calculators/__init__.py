@@ -1,8 +1,11 @@
 """Hot-path calculators behind the MDSuite names (mdsuite/calculators/__init__.py:29-87)."""
 from .coordination_number_calculation import CoordinationNumbers
 from .einstein_diffusion_coefficients import EinsteinDiffusionCoefficients
+from .einstein_helfand_ionic_conductivity import EinsteinHelfandIonicConductivity
 from .green_kubo_ionic_conductivity import GreenKuboIonicConductivity
 from .green_kubo_self_diffusion_coefficients import GreenKuboDiffusionCoefficients
+from .kirkwood_buff_integrals import KirkwoodBuffIntegral
+from .potential_of_mean_force import PotentialOfMeanForce
 from .radial_distribution_function import RadialDistributionFunction
 
 __all__ = [
@@ -11,4 +14,7 @@ __all__ = [
     "EinsteinDiffusionCoefficients",
     "GreenKuboDiffusionCoefficients",
     "GreenKuboIonicConductivity",
+    "EinsteinHelfandIonicConductivity",
+    "PotentialOfMeanForce",
+    "KirkwoodBuffIntegral",
 ]

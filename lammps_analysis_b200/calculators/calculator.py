@@ -131,6 +131,8 @@ class TrajectoryCalculator(Calculator):
                 run.CoordinateUnwrapper()
         elif dependency == "Ionic_Current":
             run.IonicCurrent()
+        elif dependency == "Translational_Dipole_Moment":
+            run.TranslationalDipoleMoment()
         else:
             raise KeyError("Data not in database and cannot be generated.")  # :171-174
 

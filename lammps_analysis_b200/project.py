@@ -373,7 +373,27 @@ class RunComputation:
         from .transformations import IonicCurrent
         return self._transformation(IonicCurrent)
 
+    @property
+    def TranslationalDipoleMoment(self):
+        from .transformations import TranslationalDipoleMoment
+        return self._transformation(TranslationalDipoleMoment)
+
     # calculators
+    @property
+    def EinsteinHelfandIonicConductivity(self):
+        from .calculators import EinsteinHelfandIonicConductivity
+        return EinsteinHelfandIonicConductivity(**self.kwargs)
+
+    @property
+    def PotentialOfMeanForce(self):
+        from .calculators import PotentialOfMeanForce
+        return PotentialOfMeanForce(**self.kwargs)
+
+    @property
+    def KirkwoodBuffIntegral(self):
+        from .calculators import KirkwoodBuffIntegral
+        return KirkwoodBuffIntegral(**self.kwargs)
+
     @property
     def RadialDistributionFunction(self):
         from .calculators import RadialDistributionFunction

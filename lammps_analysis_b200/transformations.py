@@ -126,6 +126,10 @@ class IonicCurrent(Transformations):
 
     input_properties = ["Velocities", "Charge"]
     output_property = "Ionic_Current"
+    vector_property = "Velocities"
+
+    def _ensure_inputs(self, species):
+        pass
 
     def run_transformation(self, species: list = None):
         import torch
@@ -136,10 +140,11 @@ class IonicCurrent(Transformations):
             log.info("%s already exists, skipping", self.output_property)
             return  # transformations.py:572-579
         species = list(exp.species) if species is None else species
+        self._ensure_inputs(species)
         n_frames = exp.number_of_configurations
         J = None
         for sp in species:
-            vpath = self._require(sp, "Velocities")
+            vpath = self._require(sp, self.vector_property)
             n_atoms = exp.store.shape(vpath)[0]
             lo, hi = D.shard_atoms(0, n_atoms)
             if J is None:
@@ -159,6 +164,27 @@ class IonicCurrent(Transformations):
         out = exp.store.add_dataset(out_path, (1, n_frames, 3))
         out[0] = J.cpu().numpy()  # float64 -> float32 store rounding
         exp.store.invalidate(out_path)
+
+
+class TranslationalDipoleMoment(IonicCurrent):
+    """M(t) = sum_species sum_atoms q r_unwrapped (translational_dipole_moment.py:52-62): the
+    same charge-weighted atom reduction as the ionic current, applied to unwrapped positions
+    (which are produced first when missing, transformations.py:352-388)."""
+
+    input_properties = ["Unwrapped_Positions", "Charge"]
+    output_property = "Translational_Dipole_Moment"
+    vector_property = "Unwrapped_Positions"
+
+    def _ensure_inputs(self, species):
+        exp = self.experiment
+        missing = [sp for sp in species
+                   if not exp.store.check_existence(join_path(sp, "Unwrapped_Positions"))]
+        if missing:
+            first = next(iter(exp.species))
+            if exp.store.check_existence(join_path(first, "Box_Images")):
+                exp.run.UnwrapViaIndices(species=missing)
+            else:
+                exp.run.CoordinateUnwrapper(species=missing)
 
 
 # calculators/transformations_reference.py:27-34 + transformation_dict.py:46-62

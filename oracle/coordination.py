@@ -75,3 +75,42 @@ def coordination_numbers(rdf_data_dict: dict, n_particles: dict, volume_nm3: flo
             data[f"CN_{i + 1}_error"] = np.std([lower, upper]) / np.sqrt(2)
         out[selected_species] = data
     return out
+
+
+# --- potential_of_mean_force.py:183-349 ---------------------------------------
+def potential_of_mean_force(rdf_data_dict: dict, temperature: float, savgol_order=2,
+                            savgol_window_length=17, number_of_shells=1):
+    boltzmann_constant = 1.380649e-23
+    out = {}
+    for selected_species, vals in rdf_data_dict.items():
+        radii = np.array(vals["x"]).astype(float)[1:]
+        rdf = np.array(vals["y"]).astype(float)[1:]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            pomf = -1 * boltzmann_constant * temperature * np.log(rdf)
+        pomf = pomf * 6.242e8
+        filtered = savgol_filter(pomf, savgol_window_length, savgol_order)
+        peaks = find_peaks(filtered)[0]
+        if len(peaks) < number_of_shells + 1:
+            raise ValueError("Not enough peaks")
+        data = {"r": radii[1:].tolist(), "pomf": pomf.tolist()}
+        for i in range(number_of_shells):
+            rng = golden_section_search([radii, pomf], radii[peaks[i + 1]], radii[peaks[i]])
+            idx = [int(np.where(radii == rng[j])[0][0]) for j in range(2)]
+            lower, upper = pomf[idx[0]], pomf[idx[1]]
+            data[f"POMF_{i + 1}"] = np.mean([lower, upper])
+            data[f"POMF_{i + 1}_error"] = np.std([lower, upper]) / np.sqrt(2)
+        out[selected_species] = data
+    return out
+
+
+# --- kirkwood_buff_integrals.py:160-203 ----------------------------------------
+def kirkwood_buff_integral(rdf_data_dict: dict, savgol_order=2, savgol_window_length=17):
+    out = {}
+    for selected_species, vals in rdf_data_dict.items():
+        radii = np.array(vals["x"]).astype(float)[1:]
+        rdf = np.array(vals["y"]).astype(float)[1:]
+        filtered = savgol_filter(rdf, savgol_window_length, savgol_order)
+        integral = cumulative_trapezoid(y=(filtered[1:] - 1) * radii[1:] ** 2, x=radii[1:])
+        out[selected_species] = {"r": radii[1:].tolist(),
+                                 "kb_integral": (4 * np.pi * integral).tolist()}
+    return out

@@ -208,3 +208,30 @@ def gk_ionic_finish(acf_sum, count, sigmas, time, prefactor, integration_range):
         "integral": sigma.tolist(),
         "integral_uncertainty": sigma_SEM.tolist(),
     }
+
+
+# --- einstein_helfand_ionic_conductivity.py:167-258 ---------------------------
+def eh_ionic_prefactor(units_length, units_time, temperature, volume):
+    numerator = (units_length**2) * (elementary_charge**2)
+    denominator = units_time * volume * units_length**3 * temperature * boltzmann_constant
+    return numerator / denominator
+
+
+def eh_ionic_msd(dipole: np.ndarray, plan: dict, data_range: int, correlation_time: int,
+                 tau_values: np.ndarray, prefactor: float):
+    """dipole: (1, T, 3) Observables/Translational_Dipole_Moment.  Returns the averaged msd
+    (ensemble_operation :192-209, _apply_averaging_factor :188-190).  Same axis-0 slicing of
+    the system observable as the ionic ACF (Q7)."""
+    msd_array = np.zeros(len(tau_values))
+    ensemble_loop = None
+    for _atom_sel, start, stop, data_size in iter_batches(plan, system=True):
+        batch = np.asarray(dipole[start:stop], dtype=np.float64)
+        if batch.shape[0] == 0:
+            raise ValueError("system observable requested with more than one batch (Q7)")
+        windows = list(iter_ensembles(data_size, data_range, correlation_time))
+        ensemble_loop = len(windows)
+        for s, e in windows:
+            ensemble = batch[:, s:e]
+            msd = (ensemble[:, tau_values] - ensemble[:, None, 0]) ** 2
+            msd_array += (prefactor * msd.sum(axis=2))[0, :]
+    return msd_array / (int(plan["n_batches"]) * ensemble_loop)

@@ -95,3 +95,16 @@ def run_ionic_current(vel_by_species: dict, charge_by_species: dict):
     }
     J = ionic_current_transform_batch(batch)  # (T, 3)
     return J[np.newaxis].astype(np.float32)  # transformations.py:204-207
+
+
+def dipole_moment_transform_batch(batch: dict):
+    """translational_dipole_moment.py:52-62: sum_species sum_atoms charge * unwrapped_pos."""
+    dipms = []
+    for properties in batch.values():
+        pos = np.asarray(properties["Unwrapped_Positions"], dtype=np.float64)
+        charge = np.asarray(properties["Charge"], dtype=np.float64)
+        dipms.append(np.sum(charge * pos, axis=0))
+    out = dipms[0]
+    for d in dipms[1:]:
+        out = out + d
+    return out

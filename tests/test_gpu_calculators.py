@@ -388,3 +388,77 @@ def test_unwrap_via_indices_is_chosen_when_box_images_exist(tmp_path, cuda):
     calc.check_input()          # dependency resolution: trajectory_calculator.py:117-194
     want = (pos.astype(np.float64) + img.astype(np.float64) * np.array([7.0, 7.5, 8.0]))
     assert np.array_equal(exp.store.host("A/Unwrapped_Positions"), want.astype(np.float32))
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" rows: consumers of the MSD kernel and of the RDF result
+# ---------------------------------------------------------------------------------------------
+def test_c1_pmf_and_kirkwood_buff(nacl_c1):
+    from oracle import coordination as oc
+
+    project, exp, data, box = nacl_c1
+    rdf = exp.run.RadialDistributionFunction(number_of_configurations=100, plot=False)
+    kb = exp.run.KirkwoodBuffIntegral(rdf_data=rdf, plot=False, savgol_window_length=31)
+    ref = oc.kirkwood_buff_integral(rdf.data_dict, savgol_window_length=31)
+    for key in ref:
+        np.testing.assert_allclose(kb[key]["kb_integral"], ref[key]["kb_integral"], rtol=1e-9)
+        np.testing.assert_allclose(kb[key]["r"], ref[key]["r"], rtol=1e-12)
+    # the measured g(r) is exactly zero inside the core, where ln g diverges (scipy's savgol
+    # filter rejects the infinities, as it does for the reference): the PMF is checked on a
+    # strictly positive model g(r) handed over as a Computation
+    from collections import OrderedDict
+
+    from lammps_analysis_b200.project import Computation
+
+    r = np.linspace(0.0, 1.5, 600)
+    g = 1.0 + 1.8 * np.exp(-3.0 * r) * np.cos(14.0 * r - 1.0)
+    model = Computation("Radial_Distribution_Function", "NaCl",
+                        {"number_of_bins": 600, "cutoff": 15.0, "number_of_configurations": 7},
+                        OrderedDict([("Na_Cl", {"x": r.tolist(), "y": g.tolist()})]))
+    pmf = exp.run.PotentialOfMeanForce(rdf_data=model, plot=False)
+    ref = oc.potential_of_mean_force(model.data_dict, 1400.0)
+    np.testing.assert_allclose(pmf["Na_Cl"]["pomf"], ref["Na_Cl"]["pomf"], rtol=1e-12)
+    assert pmf["Na_Cl"]["POMF_1"] == pytest.approx(ref["Na_Cl"]["POMF_1"], rel=1e-12)
+    assert pmf["Na_Cl"]["POMF_1_error"] == pytest.approx(ref["Na_Cl"]["POMF_1_error"], rel=1e-9,
+                                                          abs=1e-30)
+
+
+def test_einstein_helfand_ionic_conductivity(tmp_path, cuda):
+    from lammps_analysis_b200.config import config
+    from lammps_analysis_b200.file_io import ScriptInput
+    from lammps_analysis_b200.project import Project
+    from lammps_analysis_b200.synthetic import nacl_trajectory
+    from oracle import dynamics as od
+    from oracle import transformations as ot
+    from oracle.planner import ArrayDatabase, plan_trajectory_calculator
+
+    config.planner_memory_bytes = MEM
+    data, box = nacl_trajectory(512, 900, 26.0, seed=6, sigma_step=0.3)
+    project = Project("eh", storage_path=str(tmp_path))
+    exp = project.add_experiment("NaCl", timestep=0.002, temperature=1400.0, units="metal")
+    exp.add_data(ScriptInput({s: {"Positions": data[s]["Positions"]} for s in data}, box,
+                             sample_rate=10, atom_major=True))
+    exp.species["Na"].charge = 1.0
+    exp.species["Cl"].charge = -1.0
+    N = 120
+    res = exp.run.EinsteinHelfandIonicConductivity(data_range=N, plot=False)
+    # the transformation chain ran: unwrap -> dipole moment (stored as float32)
+    unw = {s: ot.run_unwrap(data[s]["Positions"], box, batch_size=900) for s in data}
+    M_ref = ot.dipole_moment_transform_batch({
+        "Na": {"Unwrapped_Positions": unw["Na"], "Charge": np.array([[[1.0]]])},
+        "Cl": {"Unwrapped_Positions": unw["Cl"], "Charge": np.array([[[-1.0]]])}})
+    M = exp.store.host("Observables/Translational_Dipole_Moment")
+    assert M.shape == (1, 900, 3)
+    np.testing.assert_allclose(M[0], M_ref, rtol=2e-7, atol=1e-4)
+
+    class _S:
+        shape = (1, 900, 3)
+
+    plan = plan_trajectory_calculator(ArrayDatabase({"x": _S()}), ["x"], N, 1,
+                                      {"linear": {"scale_factor": 5}}, MEM)
+    tau, _, _, times = od.handle_tau_values(np.s_[:], N, 0.002, 10)
+    pref = od.eh_ionic_prefactor(1e-10, 1e-12, 1400.0, float(np.prod(box)))
+    msd = od.eh_ionic_msd(M.astype(np.float64), plan, N, 1, tau, pref)
+    np.testing.assert_allclose(res["System"]["msd"], msd, rtol=RTOL, atol=1e-9 * np.abs(msd).max())
+    popt, pcov, _, _ = od.fit_einstein_curve(times, msd, N - 1)
+    assert res["System"]["ionic_conductivity"] == pytest.approx(popt[0] / 6, rel=1e-4)

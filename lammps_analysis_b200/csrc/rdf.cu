@@ -117,6 +117,21 @@ __device__ __forceinline__ void bin_one(float d2, bool valid, const float* __res
   }
 }
 
+// Same decision with the threshold table and the u64 histogram in GLOBAL memory: the fallback
+// for bin counts whose tables do not fit in shared memory (AM == 4).
+__device__ __forceinline__ void bin_one_global(float d2, bool valid, const float* __restrict__ thr,
+                                               unsigned long long* __restrict__ hist,
+                                               float inv_step) {
+  if (valid) {
+    const float d = sqrt_approx(d2);
+    const float t = fmaf(d, inv_step, RINT_MAGIC);
+    const unsigned g = __float_as_uint(t) - RINT_MAGIC_BITS;
+    const float tg = __ldg(thr + g);
+    const unsigned k = g - (d2 >= tg ? 0u : 1u);
+    atomicAdd(hist + k, 1ull);
+  }
+}
+
 // Same decision for two squared distances without divergent control flow:
 //   p  = d2 < cut2                       in cutoff
 //   g  = bits(fma(sqrt(d2), 1/step, 1.5*2^23)) - bits(1.5*2^23)
@@ -327,8 +342,11 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
   unsigned int* s_cnt = reinterpret_cast<unsigned int*>(s_thr + thr_len);
 
   const int tid = threadIdx.x;
-  for (int b = tid; b <= P.nbins; b += NT) s_thr[b] = __ldg(P.thr + b);
-  for (int b = tid; b < P.nbins; b += NT) s_cnt[b] = 0u;
+  constexpr bool GLOBAL_HIST = (AM == 4);  // tables too large for shared memory
+  if (!GLOBAL_HIST) {
+    for (int b = tid; b <= P.nbins; b += NT) s_thr[b] = __ldg(P.thr + b);
+    for (int b = tid; b < P.nbins; b += NT) s_cnt[b] = 0u;
+  }
   if (tid == 0) {
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
@@ -391,7 +409,8 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
     if (j_tile0 >= j_tile1) continue;                 // empty item (below the diagonal)
 
     if (p != cur_pair) {
-      if (cur_pair >= 0) flush_hist<NT>(s_cnt, P.nbins, P.hist + (size_t)cur_pair * P.nbins);
+      if (cur_pair >= 0 && !GLOBAL_HIST)
+        flush_hist<NT>(s_cnt, P.nbins, P.hist + (size_t)cur_pair * P.nbins);
       cur_pair = p;
       tiles_since_flush = 0;
     }
@@ -509,7 +528,7 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
         }
       }
 
-      if (!EXACT && !diag) {
+      if (!EXACT && !diag && !GLOBAL_HIST) {
         constexpr unsigned FULL = (1u << R) - 1u;
 #pragma unroll 1
         for (int q = 0; q < NSUB; ++q) {
@@ -543,8 +562,11 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
             }
             const float d2 =
                 __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
-            const bool ok = (d2 < cut2) && (!same || j > irow[r]);
-            bin_one(d2, ok, s_thr, s_cnt, inv_step);
+            const bool ok = (d2 < cut2) && (!same || !diag || j > irow[r]);
+            if (GLOBAL_HIST)
+              bin_one_global(d2, ok, P.thr, P.hist + (size_t)cur_pair * P.nbins, inv_step);
+            else
+              bin_one(d2, ok, s_thr, s_cnt, inv_step);
           }
         }
       }
@@ -560,13 +582,14 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
       }
       jt = jn;
       jn = jnn;
-      if (++tiles_since_flush >= P.flush_tiles) {
+      if (!GLOBAL_HIST && ++tiles_since_flush >= P.flush_tiles) {
         flush_hist<NT>(s_cnt, P.nbins, P.hist + (size_t)cur_pair * P.nbins);
         tiles_since_flush = 0;
       }
     }
   }
-  if (cur_pair >= 0) flush_hist<NT>(s_cnt, P.nbins, P.hist + (size_t)cur_pair * P.nbins);
+  if (cur_pair >= 0 && !GLOBAL_HIST)
+    flush_hist<NT>(s_cnt, P.nbins, P.hist + (size_t)cur_pair * P.nbins);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -651,6 +674,9 @@ int launch_rdf(const RdfParams& P, size_t smem, int grid, cudaStream_t s) {
 
 template <int NT, int R>
 int launch_rdf_cfg(const RdfParams& P, size_t smem, int grid, cudaStream_t s, bool exact, int am) {
+  if (am == 4)
+    return exact ? launch_rdf<NT, R, true, 4, false>(P, smem, grid, s)
+                 : launch_rdf<NT, R, false, 4, false>(P, smem, grid, s);
   if (exact) return launch_rdf<NT, R, true, 0, false>(P, smem, grid, s);
   if (P.bbox)  // culling variants: AM 2 (table) and AM 3 (fraction bits)
     return am == 3 ? launch_rdf<NT, R, false, 3, true>(P, smem, grid, s)
@@ -775,7 +801,7 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
   int am = (flags >> 12) & 0xf;   // 0 = auto, else AM = am - 1
   if (cfg == 0) cfg = max_len <= 8192 ? 1 : 4;
   am = am == 0 ? 2 : am - 1;  // auto: unconditional ATOMS.POPC.INC (fastest measured)
-  MDK_CHECK_ARG(cfg >= 1 && cfg <= 4 && am >= 0 && am <= 3, "rdf_hist: bad tuning flags");
+  MDK_CHECK_ARG(cfg >= 1 && cfg <= 4 && am >= 0 && am <= 4, "rdf_hist: bad tuning flags");
   if (am == 3 && nbins > FRAC_MAX_BINS) am = 2;  // fraction-bit binning needs nbins <= 15000
   const int NT = (cfg <= 2) ? 128 : 256;
   const int R = (cfg == 1 || cfg == 3) ? 2 : 4;
@@ -806,12 +832,16 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
                       2 * sizeof(unsigned long long) +
                       (size_t)((nbins + 1 + 3) & ~3) * sizeof(float) +
                       (size_t)(((nbins + 31) & ~31) + 32) * sizeof(unsigned);
-  if (smem > 227 * 1024) {
-    set_error("rdf_hist: nbins=%d needs %zu bytes of shared memory (> 227 KB)", nbins, smem);
-    return MDK_EUNSUPPORTED;
+  const bool global_hist = smem > 227 * 1024 || ((flags >> 12) & 0xf) == 5;
+  size_t smem_used = smem;
+  if (global_hist) {
+    // threshold table + private histogram do not fit: slow path with both in global memory
+    am = 4;
+    smem_used = (size_t)2 * 3 * TJ * sizeof(float) + 4 * sizeof(uint64_t) +
+                2 * sizeof(unsigned long long) + 64;
   }
   // resident CTAs per SM (shared-memory bound) -> persistent grid
-  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  int per_sm = (int)((227 * 1024) / (smem_used + 1024));
   const int max_by_threads = 2048 / NT;
   if (per_sm > max_by_threads) per_sm = max_by_threads;
   if (per_sm > 8) per_sm = 8;
@@ -858,9 +888,9 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
 
   MDK_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s));
   switch (cfg) {
-    case 1: return launch_rdf_cfg<128, 2>(P, smem, grid, s, exact, am);
-    case 2: return launch_rdf_cfg<128, 4>(P, smem, grid, s, exact, am);
-    case 3: return launch_rdf_cfg<256, 2>(P, smem, grid, s, exact, am);
-    default: return launch_rdf_cfg<256, 4>(P, smem, grid, s, exact, am);
+    case 1: return launch_rdf_cfg<128, 2>(P, smem_used, grid, s, exact, am);
+    case 2: return launch_rdf_cfg<128, 4>(P, smem_used, grid, s, exact, am);
+    case 3: return launch_rdf_cfg<256, 2>(P, smem_used, grid, s, exact, am);
+    default: return launch_rdf_cfg<256, 4>(P, smem_used, grid, s, exact, am);
   }
 }

@@ -91,6 +91,31 @@ def test_rdf_exact_division_mode(cuda):
         assert np.array_equal(got[p], ref[key]), key
 
 
+def test_rdf_bin_count_beyond_shared_memory(cuda):
+    """40,000 bins do not fit the shared-memory tables: the global-memory fallback gives the
+    oracle's counts (and the same kernel forced on a small bin count agrees with the default)."""
+    from lammps_analysis_b200.engine import RdfEngine, to_device_f32
+    from oracle import rdf as orc
+
+    rng = np.random.default_rng(61)
+    pos = {"A": (rng.random((400, 2, 3)) * 30.0).astype(np.float32),
+           "B": (rng.random((300, 2, 3)) * 30.0).astype(np.float32)}
+    box = np.array([30.0, 30.0, 30.0])
+    cutoff, nbins = 14.9, 40_000
+    ref = orc.rdf_counts(pos, ["A", "B"], box, np.arange(2), cutoff, nbins, 100, 2)
+    eng = RdfEngine([400, 300], box, cutoff, nbins, device=cuda)
+    trajs = [to_device_f32(pos[s], cuda) for s in ("A", "B")]
+    eng.add_frames(trajs, np.arange(2))
+    got = eng.counts()
+    for p, key in enumerate(["A_A", "A_B", "B_B"]):
+        assert np.array_equal(got[p], ref[key]), key
+    small = RdfEngine([400, 300], box, cutoff, 1490, device=cuda)
+    small.add_frames(trajs, np.arange(2))
+    forced = RdfEngine([400, 300], box, cutoff, 1490, device=cuda)
+    forced.add_frames(trajs, np.arange(2), tuning=0x5000)
+    assert np.array_equal(small.counts(), forced.counts())
+
+
 def test_rdf_single_species_and_empty(cuda):
     from lammps_analysis_b200.engine import RdfEngine, to_device_f32
     from oracle import rdf as orc

@@ -42,6 +42,7 @@ def golden_section_search(data, a, b, tol=1e-5):
     h = b - a
     c = d = fc = fd = None
     while h > tol:
+        a, b = min(a, b), max(a, b)  # the reference re-orders the bracket at every level
         if c is None:
             c = _closest(xs, a + phi_b * h)
             fc = ys[np.where(xs == c)]
@@ -53,7 +54,7 @@ def golden_section_search(data, a, b, tol=1e-5):
         else:
             a, c, fc, d, fd = c, d, fd, None, None
         h = h * phi_a
-    return a, b
+    return min(a, b), max(a, b)
 
 
 class CoordinationNumbers(Calculator):

@@ -26,9 +26,16 @@ Parity pinning status:
   - unwrap-with-carry, unwrap-via-indices, ionic current, memory-manager planner
     arithmetic and ``fit_einstein_curve`` are pinned against the reference's own
     known-answer unit tests (``tests/test_oracle_golden.py``).
-  - RDF bin counts and MSD/ACF series: the reference's golden JSONs are
-    downloaded from the network by its CI (zinchub) and are unreachable here;
-    TF cannot be imported to generate fixtures.  => "parity unpinned" for those
-    series beyond the analytic-model tests (random walk D, Langevin VACF) the
-    reference itself uses.
+  - RDF index / mask / minibatch logic and bin counts, the transformations, the
+    whole MemoryManager, the DataManager window and batch generators, the Einstein
+    ensemble operation, ``fit_einstein_curve`` and ``golden_section_search`` are
+    pinned against vectors produced by EXECUTING the reference's own Python source
+    under a NumPy TensorFlow shim (``tests/golden/make_reference_goldens.py`` ->
+    ``tests/golden/reference_run.json``).
+  - TensorFlow's / tfp's own numerics (histogram_fixed_width truncation rule,
+    norm summation order, FFT autocorrelation) cannot be executed here (no
+    tensorflow, no network for the reference's downloaded golden JSONs): for those
+    the oracle is a restatement of the published algorithms => "parity unpinned"
+    at that level, beyond the analytic-model tests (random walk D, Langevin VACF)
+    the reference itself uses.
 """

@@ -392,3 +392,68 @@ def test_ionic_current(cuda, mode):
     K.ionic_current(to_device_f32(v_na, cuda), d_na, J)
     K.ionic_current(to_device_f32(v_cl, cuda), d_cl, J)
     np.testing.assert_allclose(J.cpu().numpy(), ref, rtol=1e-12, atol=1e-11)
+
+
+# ---------------------------------------------------------------------------------------------
+# kernels vs vectors produced by executing the reference's own Python source
+# (tests/golden/reference_run.json, generator: tests/golden/make_reference_goldens.py)
+# ---------------------------------------------------------------------------------------------
+def _reference_run():
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_run.json")) as fh:
+        return json.load(fh)
+
+
+def test_reference_run_rdf_counts_on_gpu(cuda):
+    from lammps_analysis_b200.engine import RdfEngine, to_device_f32
+
+    g = _reference_run()["rdf"]
+    pos = [np.asarray(g["positions"][s], dtype=np.float32) for s in g["species"]]
+    n_frames = pos[0].shape[1]
+    eng = RdfEngine([p.shape[0] for p in pos], g["box"], g["cutoff"], g["nbins"], device=cuda)
+    eng.add_frames([to_device_f32(p, cuda) for p in pos], np.arange(n_frames))
+    got = eng.counts()
+    for p, key in enumerate(["Na_Na", "Na_Cl", "Cl_Cl"]):
+        assert np.array_equal(got[p], np.asarray(g["counts"][key])), key
+
+
+def test_reference_run_transformations_on_gpu(cuda):
+    import torch
+    from lammps_analysis_b200 import kernels as K
+    from lammps_analysis_b200.engine import to_device_f32
+
+    ref = _reference_run()
+    g = ref["unwrap"]
+    pos = np.asarray(g["positions"], dtype=np.float32)
+    box = np.asarray(g["box"])
+    dev = to_device_f32(pos, cuda)
+    A = pos.shape[0]
+    carry_pos = torch.zeros(A, 3, dtype=torch.float32, device=cuda)
+    carry_img = torch.zeros(A, 3, dtype=torch.float64, device=cuda)
+    out = torch.empty_like(dev)
+    have = False
+    for lo, hi in g["batches"]:                      # same batches, carry-over threaded through
+        chunk = dev[:, lo:hi].contiguous()
+        o = torch.empty_like(chunk)
+        K.unwrap(chunk, box, carry_pos, carry_img, have, o)
+        out[:, lo:hi] = o
+        have = True
+    want = np.asarray(g["unwrapped"]).astype(np.float32)   # the reference persists float32
+    assert np.array_equal(out.cpu().numpy(), want)
+    gi = ref["unwrap_indices"]
+    o = torch.empty_like(dev)
+    K.unwrap_indices(dev, to_device_f32(np.asarray(gi["images"], dtype=np.float32), cuda), box, o)
+    assert np.array_equal(o.cpu().numpy(), np.asarray(gi["unwrapped"]).astype(np.float32))
+    gc = ref["ionic_current"]
+    T = len(gc["current"])
+    J = torch.zeros(T, 3, dtype=torch.float64, device=cuda)
+    M = torch.zeros(T, 3, dtype=torch.float64, device=cuda)
+    for s, q in gc["charge"].items():
+        v = to_device_f32(np.asarray(gc["velocities"][s], dtype=np.float32), cuda)
+        K.ionic_current(v, q, J)
+        K.ionic_current(v, q, M)      # the dipole moment is the same reduction on positions
+    np.testing.assert_allclose(J.cpu().numpy(), np.asarray(gc["current"]), rtol=1e-13, atol=1e-14)
+    np.testing.assert_allclose(M.cpu().numpy(), np.asarray(ref["dipole_moment"]["moment"]),
+                               rtol=1e-13, atol=1e-14)

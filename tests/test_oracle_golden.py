@@ -156,3 +156,117 @@ def test_rdf_counts_independent_of_batch_plan():
     # Q1: the first atom of every species is dropped
     assert a["Na_Na"].sum() <= 3 * 29 * 28 // 2
     assert a["Na_Cl"].sum() <= 3 * 29 * 25
+
+
+# ---------------------------------------------------------------------------------------------
+# vectors produced by executing the reference's own Python source (tests/golden/
+# make_reference_goldens.py: ast-extracted upstream functions run under a NumPy TF shim)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ref_run():
+    return _load("reference_run.json")
+
+
+def test_reference_run_rdf_counts(ref_run):
+    from oracle import rdf as orc
+
+    g = ref_run["rdf"]
+    pos = {s: np.asarray(g["positions"][s], dtype=np.float32) for s in g["species"]}
+    n_frames = pos[g["species"][0]].shape[1]
+    got = orc.rdf_counts(pos, g["species"], np.asarray(g["box"]), np.arange(n_frames),
+                         g["cutoff"], g["nbins"], 7, n_frames)
+    for key, want in g["counts"].items():
+        assert np.array_equal(got[key], np.asarray(want)), key
+    assert sum(int(np.sum(v)) for v in g["counts"].values()) > 500
+
+
+def test_reference_run_transformations(ref_run):
+    g = ref_run["unwrap"]
+    pos = np.asarray(g["positions"], dtype=np.float32).astype(np.float64)
+    carry, pieces = None, []
+    for lo, hi in g["batches"]:
+        res, carry = ot.unwrap_transform_batch(pos[:, lo:hi], np.asarray(g["box"]), carry)
+        pieces.append(res)
+    assert np.array_equal(np.concatenate(pieces, axis=1), np.asarray(g["unwrapped"]))
+    gi = ref_run["unwrap_indices"]
+    assert np.array_equal(
+        ot.unwrap_via_indices_transform_batch(pos, np.asarray(gi["images"]), np.asarray(g["box"])),
+        np.asarray(gi["unwrapped"]))
+    gc = ref_run["ionic_current"]
+    batch = {s: {"Velocities": np.asarray(gc["velocities"][s], dtype=np.float32),
+                 "Charge": np.array([[[gc["charge"][s]]]])} for s in gc["velocities"]}
+    assert np.array_equal(ot.ionic_current_transform_batch(batch), np.asarray(gc["current"]))
+    batch = {s: {"Unwrapped_Positions": np.asarray(gc["velocities"][s], dtype=np.float32),
+                 "Charge": np.array([[[gc["charge"][s]]]])} for s in gc["velocities"]}
+    assert np.array_equal(ot.dipole_moment_transform_batch(batch),
+                          np.asarray(ref_run["dipole_moment"]["moment"]))
+
+
+def test_reference_run_planner(ref_run):
+    from lammps_analysis_b200.planner import plan_batches
+
+    n_minibatch = 0
+    for c in ref_run["planner"]:
+        db = _FakeDB(c["nbytes"], c["rows"], c["cols"])
+        mm = op.MemoryManager(data_path=["x"], database=db, memory_fraction=0.5,
+                              scale_function=c["scale_function"], memory=c["memory"])
+        assert list(mm.get_batch_size()) == c["get_batch_size"]
+        loops, minibatch = mm.get_ensemble_loop(c["data_range"], c["correlation_time"])
+        assert (loops, minibatch) == (c["ensemble_loop"], c["minibatch"])
+        assert (mm.batch_size, mm.n_batches, mm.remainder) == (
+            c["batch_size"], c["n_batches"], c["remainder"])
+        assert (mm.atom_batch_size, mm.n_atom_batches, mm.atom_remainder) == (
+            c["atom_batch_size"], c["n_atom_batches"], c["atom_remainder"])
+        # the product planner as well
+        p = plan_batches([(c["rows"], c["cols"], c["nbytes"])], c["data_range"],
+                         c["correlation_time"], c["scale_function"], memory=c["memory"],
+                         memory_fraction=0.5)
+        assert (p.batch_size, p.n_batches, p.remainder, p.ensemble_loop, p.minibatch) == (
+            c["batch_size"], c["n_batches"], c["remainder"], c["ensemble_loop"], c["minibatch"])
+        if c["minibatch"]:
+            assert (p.atom_batch_size, p.n_atom_batches, p.atom_remainder) == (
+                c["atom_batch_size"], c["n_atom_batches"], c["atom_remainder"])
+        n_minibatch += c["minibatch"]
+    assert 10 < n_minibatch < len(ref_run["planner"]) - 10
+
+
+def test_reference_run_windows_and_batch_slices(ref_run):
+    for w in ref_run["ensemble_windows"]:
+        got = [[s, min(e, w["data_size"])] for s, e in
+               op.iter_ensembles(w["data_size"], w["data_range"], w["correlation_time"])]
+        assert got == w["windows"]
+    plain, mini = ref_run["batch_slices"]
+    plan = dict(plain["plan"], minibatch=False)
+    got = [[[None, None], [start, stop]] for _, start, stop, _ in op.iter_batches(plan)]
+    assert got == plain["slices"]
+    got = [[[sel.start, sel.stop], [start, stop]] for sel, start, stop, _ in
+           op.iter_batches(mini["plan"])]
+    assert got == mini["slices"]
+
+
+def test_reference_run_fits(ref_run):
+    from lammps_analysis_b200.calculators.coordination_number_calculation import \
+        golden_section_search
+    from lammps_analysis_b200.calculators.einstein_diffusion_coefficients import \
+        fit_einstein_curve
+    from oracle import coordination as oc
+
+    g = ref_run["fit_einstein_curve"]
+    x, y = np.asarray(g["x"]), np.asarray(g["y"])
+    popt, pcov, grads, _ = od.fit_einstein_curve(x, y, g["fit_max_index"])
+    np.testing.assert_allclose(popt, g["popt"], rtol=1e-10)
+    np.testing.assert_allclose(grads, g["gradients"], rtol=1e-10)
+    popt2, pcov2, grads2, _ = fit_einstein_curve(x, y, g["fit_max_index"])   # closed form
+    np.testing.assert_allclose(popt2, g["popt"], rtol=1e-6)
+    np.testing.assert_allclose(np.diag(pcov2), np.diag(np.asarray(g["pcov"])), rtol=1e-4)
+    np.testing.assert_allclose(grads2, g["gradients"], rtol=1e-6)
+    s = ref_run["golden_section_search"]
+    data = [np.asarray(s["r"]), np.asarray(s["g"])]
+    assert list(oc.golden_section_search(data, s["a"], s["b"])) == s["result"]
+    assert list(golden_section_search(data, s["a"], s["b"])) == s["result"]
+    e = ref_run["einstein_ensemble_operation"]
+    ens = np.asarray(e["ensemble"])
+    plan = dict(batch_size=ens.shape[1], n_batches=1, remainder=0, minibatch=False)
+    msd, count = od.einstein_msd(ens, plan, ens.shape[1], 1, np.arange(ens.shape[1]))
+    np.testing.assert_allclose(msd, e["msd"], rtol=1e-13)
+    assert count == e["count"] + 1          # + 1 per window is added by run_calculator (:244)

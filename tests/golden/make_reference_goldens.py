@@ -428,6 +428,58 @@ def main():
     out["einstein_ensemble_operation"] = {"ensemble": ens.tolist(), "msd": np.asarray(msd).tolist(),
                                           "count": int(fake.count)}
 
+    # ---- RDF normalisation (:299-393, 719-826) and CN / PMF / KBI post-processing ------------
+    from scipy.integrate import cumulative_trapezoid
+    from scipy.signal import find_peaks
+
+    ns_n = {"np": np, "Union": typing.Union, "log": log}
+    extract("utils/meta_functions.py", ["split_array"], ns_n)
+    extract("calculators/radial_distribution_function.py",
+            ["ideal_correction", "_calculate_prefactor", "_ang_to_nm"], ns_n)
+    norm_cases = []
+    for box0, cut, nb in ((20.0, 9.9, 99), (10.0, 6.5, 65), (8.0, 6.9, 69)):  # beyond L/2 too
+        fake = types.SimpleNamespace(
+            args=types.SimpleNamespace(cutoff=cut, number_of_bins=nb, molecules=False,
+                                       atom_selection=np.s_[:], number_of_configurations=7),
+            experiment=types.SimpleNamespace(
+                box_array=[box0, box0 * 1.1, box0 * 0.9], volume=box0 * box0 * 1.1 * box0 * 0.9,
+                species={"Na": types.SimpleNamespace(n_particles=23),
+                         "Cl": types.SimpleNamespace(n_particles=17)},
+                units=types.SimpleNamespace(length=1e-10)))
+        with np.errstate(all="ignore"):
+            fake.ideal_correction = ns_n["ideal_correction"](fake)
+            pref = {k: ns_n["_calculate_prefactor"](fake, k) for k in ("Na_Na", "Na_Cl", "Cl_Cl")}
+            x = ns_n["_ang_to_nm"](fake, np.linspace(0.0, cut, nb))
+        norm_cases.append({"box": fake.experiment.box_array, "cutoff": cut, "nbins": nb,
+                           "n_configs": 7, "n_particles": {"Na": 23, "Cl": 17},
+                           "ideal_correction": np.nan_to_num(fake.ideal_correction, nan=-1.0,
+                                                             posinf=-2.0).tolist(),
+                           "prefactor": {k: np.nan_to_num(v, nan=-1.0, posinf=-2.0).tolist()
+                                         for k, v in pref.items()},
+                           "x": x.tolist()})
+    out["rdf_normalisation"] = norm_cases
+
+    ns_c = {"np": np, "cumulative_trapezoid": cumulative_trapezoid, "find_peaks": find_peaks,
+            "log": log, "golden_section_search": ns_g["golden_section_search"],
+            "apply_savgol_filter": ns_g["apply_savgol_filter"],
+            "CannotPerformThisAnalysis": ValueError}
+    extract("calculators/coordination_number_calculation.py",
+            ["_integrate_rdf", "_get_rdf_peaks", "_find_minima", "_get_coordination_numbers"],
+            ns_c)
+    rr = np.linspace(0.0, 1.2, 500)
+    gg = np.where(rr < 0.18, 0.0, 1 + 2.2 * np.exp(-4 * (rr - 0.18)) * np.cos(18 * (rr - 0.25)))
+    radii, rdf = rr[1:], gg[1:]
+    fake = types.SimpleNamespace(args=types.SimpleNamespace(savgol_order=2,
+                                                            savgol_window_length=17,
+                                                            number_of_shells=2))
+    fake._get_rdf_peaks = lambda r: ns_c["_get_rdf_peaks"](fake, r)
+    fake._find_minima = lambda a, b: ns_c["_find_minima"](fake, a, b)
+    density = 31.7
+    integral = ns_c["_integrate_rdf"](radii, rdf, density)
+    cn = ns_c["_get_coordination_numbers"](fake, integral, radii, rdf)
+    out["coordination_numbers"] = {"x": rr.tolist(), "y": gg.tolist(), "density": density,
+                                   "cn": integral.tolist(), "values": jsonable(cn)}
+
     with open(os.path.join(HERE, "reference_run.json"), "w") as fh:
         json.dump(jsonable(out), fh)
     print("written", os.path.join(HERE, "reference_run.json"))

@@ -270,3 +270,74 @@ def test_reference_run_fits(ref_run):
     msd, count = od.einstein_msd(ens, plan, ens.shape[1], 1, np.arange(ens.shape[1]))
     np.testing.assert_allclose(msd, e["msd"], rtol=1e-13)
     assert count == e["count"] + 1          # + 1 per window is added by run_calculator (:244)
+
+
+def test_reference_run_rdf_normalisation_and_cn(ref_run, tmp_path):
+    """ideal_correction / _calculate_prefactor / _ang_to_nm and the coordination-number
+    post-processing executed from upstream source vs the oracle AND the product calculators."""
+    from collections import OrderedDict
+    from types import SimpleNamespace
+
+    from lammps_analysis_b200.calculators.coordination_number_calculation import (
+        CoordinationNumbers)
+    from lammps_analysis_b200.calculators.radial_distribution_function import (
+        RadialDistributionFunction)
+    from lammps_analysis_b200.project import Computation, Species
+    from lammps_analysis_b200.units import REAL
+    from oracle import coordination as oc
+    from oracle import rdf as orc
+
+    def decode(v):
+        v = np.asarray(v, dtype=float)
+        out = v.copy()
+        out[v == -1.0] = np.nan
+        out[v == -2.0] = np.inf
+        return out
+
+    for c in ref_run["rdf_normalisation"]:
+        corr = orc.ideal_correction(c["cutoff"], c["nbins"], c["box"][0])
+        want = decode(c["ideal_correction"])
+        np.testing.assert_allclose(np.nan_to_num(corr, nan=-1.0), np.nan_to_num(want, nan=-1.0),
+                                   rtol=1e-13)
+        # product: prefactor and x axis
+        exp = SimpleNamespace(box_array=c["box"], volume=float(np.prod(c["box"])), units=REAL,
+                              species=OrderedDict((k, Species(k, n))
+                                                  for k, n in c["n_particles"].items()))
+        calc = RadialDistributionFunction.__new__(RadialDistributionFunction)
+        calc.experiment = exp
+        calc.args = SimpleNamespace(cutoff=c["cutoff"], number_of_bins=c["nbins"],
+                                    atom_selection=np.s_[:], number_of_configurations=c["n_configs"])
+        counts = {k: np.ones(c["nbins"], dtype=np.int64) for k in c["prefactor"]}
+        ref = orc.rdf_normalise(counts, c["n_particles"], c["box"], c["cutoff"], c["nbins"],
+                                c["n_configs"], 1e-10)
+        for key, pref in c["prefactor"].items():
+            want = decode(pref)
+            with np.errstate(all="ignore"):
+                got = calc._calculate_prefactor(key)
+            fin = np.isfinite(want)
+            np.testing.assert_allclose(got[fin], want[fin], rtol=1e-13)
+            assert np.array_equal(np.isfinite(got), fin)
+            np.testing.assert_allclose(np.asarray(ref[key]["y"])[fin], want[fin], rtol=1e-13)
+            np.testing.assert_allclose(ref[key]["x"], c["x"], rtol=1e-15)
+
+    g = ref_run["coordination_numbers"]
+    rdf_dict = {"Na_Cl": {"x": g["x"], "y": g["y"]}}
+    # oracle (density passed through n_particles / volume)
+    ref = oc.coordination_numbers(rdf_dict, {"Na": g["density"]}, 1.0, number_of_shells=2)
+    np.testing.assert_allclose(ref["Na_Cl"]["cn"], g["cn"], rtol=1e-13)
+    for k, v in g["values"].items():
+        assert ref["Na_Cl"][k] == pytest.approx(v, rel=1e-12, abs=1e-15)
+    # product calculator on the same RDF
+    calc = CoordinationNumbers.__new__(CoordinationNumbers)
+    calc._queued_data = []
+    calc.experiment = SimpleNamespace(volume=1.0, units=SimpleNamespace(length=1e-9),
+                                      species={"Na": Species("Na", g["density"])})
+    calc.args = SimpleNamespace(savgol_order=2, savgol_window_length=17, number_of_shells=2)
+    calc.rdf_data = Computation("Radial_Distribution_Function", "x", {},
+                                OrderedDict(rdf_dict))
+    calc.run_calculator()
+    key, data = calc._queued_data[0]
+    assert key == "Na_Cl"
+    np.testing.assert_allclose(data["cn"], g["cn"], rtol=1e-13)
+    for k, v in g["values"].items():
+        assert data[k] == pytest.approx(v, rel=1e-12, abs=1e-15)

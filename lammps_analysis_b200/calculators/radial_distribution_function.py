@@ -105,14 +105,20 @@ class RadialDistributionFunction(TrajectoryCalculator):
         trajs, frame_ids = [], frames
         paths = [join_path(s, self.loaded_property) for s in self.args.species]
         resident = all(store.is_resident(p) for p in paths) and not isinstance(sel, dict)
+        # page-locked host datasets are read in place by the pack kernels (zero-copy gather of
+        # the sampled frames over PCIe / NVLink-C2C): no host-side gather, no staging copy
+        zero_copy = (not resident and not isinstance(sel, dict)
+                     and all(store.pinned_tensor(p) is not None for p in paths))
         for s, path in zip(self.args.species, paths):
             if resident:
                 trajs.append(store.device(path))
+            elif zero_copy:
+                trajs.append(store.pinned_tensor(path))
             else:
                 # upload only the sampled frames of this rank
                 rows = np.asarray(sel[s]) if isinstance(sel, dict) else None
                 trajs.append(store.device_frames(path, frames, row_index=rows))
-        if not resident:
+        if not resident and not zero_copy:
             frame_ids = np.arange(len(frames))
         self.engine = RdfEngine(self.particles_list, exp.box_array, self.args.cutoff,
                                 self.args.number_of_bins, drop_first=self.parity_mode)

@@ -44,6 +44,17 @@ def _need_cuda(t: torch.Tensor, dtype, what: str):
         raise MdkError(f"{what}: tensor must be contiguous")
 
 
+def _need_device_readable(t: torch.Tensor, dtype, what: str):
+    """CUDA tensor, or page-locked host tensor (mapped into the device address space under
+    unified addressing: a gather kernel reads it in place over PCIe / NVLink-C2C)."""
+    if not (t.is_cuda or t.is_pinned()):
+        raise MdkError(f"{what}: expected a CUDA or pinned host tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise MdkError(f"{what}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise MdkError(f"{what}: tensor must be contiguous")
+
+
 def sm_count() -> int:
     return _lib.load().mdk_sm_count()
 
@@ -119,7 +130,7 @@ def rdf_pack(traj: torch.Tensor, frames: torch.Tensor, out: torch.Tensor, layout
     Replaces data_manager.py:195-201 (frame fancy index) and _format_data
     (radial_distribution_function.py:535-563).
     """
-    _need_cuda(traj, torch.float32, "rdf_pack traj")
+    _need_device_readable(traj, torch.float32, "rdf_pack traj")
     _need_cuda(frames, torch.int32, "rdf_pack frames")
     _need_cuda(out, torch.float32, "rdf_pack out")
     A, T, D = traj.shape
@@ -166,7 +177,7 @@ def rdf_pack_sorted(traj: torch.Tensor, frame: int, out: torch.Tensor, k: int, l
                     species_index: int, atom_first: int, atom_count: int, box,
                     workspace: torch.Tensor):
     """Morton-ordered pack of one frame of one species into slab k of ``out`` ([k][3][n_pad])."""
-    _need_cuda(traj, torch.float32, "rdf_pack_sorted traj")
+    _need_device_readable(traj, torch.float32, "rdf_pack_sorted traj")
     _need_cuda(out, torch.float32, "rdf_pack_sorted out")
     A, T, D = traj.shape
     if D != 3:

@@ -206,6 +206,10 @@ class TrajectoryStore:
         self._device_bytes += nbytes
         return out
 
+    def pinned_tensor(self, path: str):
+        """The page-locked host tensor behind a dataset of an in-memory store (or None)."""
+        return self._pinned.get(path)
+
     def is_resident(self, path: str) -> bool:
         return any(k[0] == path and k[1] == 0 and k[2] == self._arrays[path].shape[0]
                    for k in self._device_cache if k[1] != "idx")

@@ -462,3 +462,36 @@ def test_einstein_helfand_ionic_conductivity(tmp_path, cuda):
     np.testing.assert_allclose(res["System"]["msd"], msd, rtol=RTOL, atol=1e-9 * np.abs(msd).max())
     popt, pcov, _, _ = od.fit_einstein_curve(times, msd, N - 1)
     assert res["System"]["ionic_conductivity"] == pytest.approx(popt[0] / 6, rel=1e-4)
+
+
+def test_in_memory_pinned_store_matches_persistent_store(tmp_path, cuda):
+    """persist=False keeps datasets in page-locked host memory: the RDF pack kernels gather the
+    sampled frames from it in place (zero copy), uploads are single DMA transfers.  Same numbers
+    as the file-backed store."""
+    from lammps_analysis_b200.config import config
+    from lammps_analysis_b200.file_io import ScriptInput
+    from lammps_analysis_b200.project import Project
+    from lammps_analysis_b200.synthetic import nacl_trajectory
+
+    config.planner_memory_bytes = MEM
+    data, box = nacl_trajectory(512, 300, 26.0, seed=12, sigma_step=0.3)
+    results = []
+    for persist in (True, False):
+        project = Project(f"p{int(persist)}", storage_path=str(tmp_path), persist=persist)
+        exp = project.add_experiment("NaCl", timestep=0.002, temperature=1400.0, units="metal")
+        exp.add_data(ScriptInput(data, box, sample_rate=10, atom_major=True))
+        assert exp.store.pinned == (not persist)
+        rdf = exp.run.RadialDistributionFunction(number_of_configurations=23, start=5, plot=False)
+        exp.run.CoordinateUnwrapper()
+        ein = exp.run.EinsteinDiffusionCoefficients
+        type(ein).__call__.__wrapped__(ein, data_range=60, plot=False)
+        ein._handle_tau_values()
+        msd = {sp: ein.compute_msd(sp)[0] for sp in ("Na", "Cl")}
+        gk = exp.run.GreenKuboDiffusionCoefficients(data_range=60, plot=False)
+        results.append((rdf.data_dict, msd, gk.data_dict))
+    (r0, e0, g0), (r1, e1, g1) = results
+    for key in r0:
+        assert np.array_equal(np.array(r0[key]["y"])[1:], np.array(r1[key]["y"])[1:])
+    for sp in e0:
+        np.testing.assert_allclose(e0[sp], e1[sp], rtol=1e-12)   # fp64 atomics: order may differ
+        np.testing.assert_allclose(g0[sp]["acf"], g1[sp]["acf"], rtol=1e-12)

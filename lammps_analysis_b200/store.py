@@ -86,7 +86,9 @@ class TrajectoryStore:
         elif self.pinned:
             import torch
 
-            t = torch.zeros(tuple(int(s) for s in shape), dtype=torch.float32, pin_memory=True)
+            # not zero-filled: every writer (ingest, transformations) covers the whole dataset,
+            # and a memset of gigabytes of page-locked memory costs as much as the transfer
+            t = torch.empty(tuple(int(s) for s in shape), dtype=torch.float32, pin_memory=True)
             self._pinned[path] = t
             arr = t.numpy()
         else:

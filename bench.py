@@ -479,10 +479,10 @@ def run_gpu_arm(args):
         return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": traffic, "peak_source": hbm_src}
 
-    def fp32_roof(flops_per_launch, seconds_all_steps):
+    def fp32_roof(flops_per_launch, seconds_all_steps, traffic=None):
         ach = flops_per_launch * steps / seconds_all_steps * 1e-12
         return {"bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": ach / fp32_peak, "traffic": None, "peak_source": fp32_src}
+                "frac": ach / fp32_peak, "traffic": traffic, "peak_source": fp32_src}
 
     cores = os.cpu_count() or 1
     cpu = None
@@ -498,7 +498,12 @@ def run_gpu_arm(args):
         "config": workload_config(world, small),
         "phases_ms_per_step": {k: 1e3 * v / steps for k, v in t.items()},
         "wall_s_timed_region": wall,
-        "roofline": dict(fp32_roof(FLOP_PER_PAIR * pairs_per_frame, t["rdf_kernel"]),
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch on this workload
+        # shape (10^6 atoms, 1 frame), ncu --set full capture profiles/r01d_ncu_rdf_culled.md
+        "roofline": dict(fp32_roof(FLOP_PER_PAIR * pairs_per_frame, t["rdf_kernel"],
+                                   traffic=None if small else 12.67e6),
+                         traffic_unit="bytes per launch (ncu capture r01d; the kernel is "
+                                      "compute bound: 12 MB of coordinates per 5e11 pairs)",
                          kernel="rdf_pair_hist_kernel",
                          algorithmic="20 FLOP per pair-distance x 4.999995e11 pairs per launch "
                                      "(all i<j pairs count, including the blocks the kernel "
@@ -515,7 +520,7 @@ def run_gpu_arm(args):
             {"metric": "msd_atom_lag_updates_per_s", "unit": "atom-lag updates/s",
              "value": total_upd / t["msd_kernel"],
              "roofline": dict(fp32_roof(FLOP_PER_MSD * upd_per_step, t["msd_kernel"]),
-                              kernel="msd_windowed_kernel",
+                              kernel="msd_dense_kernel",
                               hbm=hbm_roof(12.0 * shard * n_frames, t["msd_kernel"])),
              "e2e": {"value": 2 * total_upd / e_dyn, "unit": "atom-lag updates/s (MSD+ACF)",
                      "h2d_bytes_per_step": h2d_dyn, "d2h_bytes_per_step": d2h_dyn,
@@ -525,7 +530,7 @@ def run_gpu_arm(args):
             {"metric": "acf_atom_lag_updates_per_s", "unit": "atom-lag updates/s",
              "value": total_upd / t["acf_kernels"],
              "roofline": dict(fp32_roof(FLOP_PER_ACF * upd_per_step, t["acf_kernels"]),
-                              kernel="acf_lagprod_kernel (+prefix, windows)",
+                              kernel="acf_band_kernel (+prefix, windows)",
                               hbm=hbm_roof(12.0 * shard * n_frames, t["acf_kernels"]))},
             {"metric": "unwrap_atom_frames_per_s", "unit": "atom-frames/s",
              "value": total_af / t["unwrap_kernel"],

@@ -568,10 +568,16 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
   constexpr int R = MD_R;
   const int lag_span = MD_NT * R;
   const int lag_blocks = (n_lags + lag_span - 1) / lag_span;
-  const int Wc = W < 512 ? W : 512;
-  // every thread may read up to one ring refill past its last lag: size the tile for the full
-  // lag span of a block so that those (discarded) reads stay inside the allocation
-  const int len_alloc = (Wc + lag_span + R + 3) & ~3;  // multiple of 4: float2 views stay aligned
+  // window groups only pay off when the lag range leaves at least half of the CTA idle
+  const bool grouped = lag_blocks == 1 && (n_lags + R - 1) / R <= MD_NT / 2;
+  // every thread may read up to one ring refill past its last lag: the slab covers the window
+  // chunk plus the lag span of the block (plus R), so those (discarded) reads stay inside it.
+  // Short lag ranges take long window chunks (up to ~4096 frames, 48 KB): with few lags per
+  // atom the staging, not the arithmetic, is the cost, and it amortises over more origins.
+  const int lag_alloc = grouped ? ((n_lags + R - 1) / R) * R + R : lag_span + R;
+  const int wc_max = grouped ? 4096 - lag_alloc : 512;
+  const int Wc = W < wc_max ? W : wc_max;
+  const int len_alloc = (Wc + lag_alloc + 3) & ~3;  // multiple of 4: float2 views stay aligned
   const size_t smem = ((size_t)3 * len_alloc + (lag_blocks > 1 ? (size_t)3 * Wc : 0)) * sizeof(float);
   const int chunks = (W + Wc - 1) / Wc;
   // 64-thread CTAs: aim for several waves of ~11 resident CTAs per SM
@@ -579,8 +585,6 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
   const long long groups = (a_hi - a_lo + apc - 1) / apc;
   MDK_CHECK_ARG(groups <= 65535 && lag_blocks <= 65535, "msd_dense: grid too large");
   dim3 grid(chunks, (unsigned)groups, lag_blocks);
-  // window groups only pay off when the lag range leaves at least half of the CTA idle
-  const bool grouped = lag_blocks == 1 && (n_lags + R - 1) / R <= MD_NT / 2;
   if (grouped) {
     MDK_CUDA(cudaFuncSetAttribute(msd_dense_kernel<true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -61,6 +61,7 @@ struct RdfParams {
   unsigned long long* counter;   // dynamic work counter
   unsigned int flush_tiles;      // flush after this many column tiles (u32 overflow guard)
   unsigned int one;              // == 1, kept opaque to the compiler (see bin_two)
+  float onef;                    // == 1.0f, opaque as well (packed exact adds, see sub_tile)
   // culling (optional): per (frame, 256-atom tile) bounding boxes {min xyz, max xyz}
   const float* bbox;             // [F][boxes_per_frame][6] (one per SUB atoms) or nullptr
   int boxes_per_frame;
@@ -272,7 +273,7 @@ __device__ __forceinline__ void flush_hist(unsigned int* s_cnt, int nbins,
 // Loop-invariant operands of the pair arithmetic.
 struct GeoConst {
   float invLx, invLy, invLz, nLx, nLy, nLz, inv_step;
-  float cut2;
+  float cut2, onef;
   uint32_t thr_c, cnt_delta, one, dump, thr_s, cnt_s, dump_off;
 };
 __device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
@@ -288,6 +289,7 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
                                          const float2 (&nzi)[R], const GeoConst& c) {
   const float2 magic2 = dup2(RINT_MAGIC), nmagic2 = dup2(-RINT_MAGIC);
   const float2 inv_step2 = dup2(c.inv_step);
+  const float2 one2 = dup2(c.onef);
 #pragma unroll 2
   for (int jj = jj0; jj < jj0 + SUB; jj += 2) {
     const float2 xj = *reinterpret_cast<const float2*>(sx + jj);
@@ -308,15 +310,15 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
         const float2 rx = __ffma2_rn(nx, dup2(c.nLx), dx);
         const float2 ry = __ffma2_rn(ny, dup2(c.nLy), dy);
         const float2 rz = __ffma2_rn(nz, dup2(c.nLz), dz);
-        // squares packed; the two adds stay scalar: ptxas 12.9 contracts mul.rn.f32x2 +
-        // add.rn.f32x2 into FFMA2, which would break the reference's rounding sequence
-        // (x*x + y*y) + z*z.
+        // (x*x + y*y) + z*z with every product and sum rounded separately, as the reference
+        // does.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even with explicit
+        // .rn), which would fuse a product into a sum; the packed adds are therefore written as
+        // fma(a, 1.0f, b) with a run-time 1.0f the compiler cannot see through: a * 1 is exact,
+        // so the result is the correctly rounded a + b, on two pairs per instruction.
         const float2 xx = __fmul2_rn(rx, rx);
         const float2 yy = __fmul2_rn(ry, ry);
         const float2 zz = __fmul2_rn(rz, rz);
-        float2 d2;
-        d2.x = __fadd_rn(__fadd_rn(xx.x, yy.x), zz.x);
-        d2.y = __fadd_rn(__fadd_rn(xx.y, yy.y), zz.y);
+        const float2 d2 = __ffma2_rn(zz, one2, __ffma2_rn(xx, one2, yy));
         if (AM == 3)
           bin_two_frac(d2, c.cut2, inv_step2, c.thr_s, c.cnt_s, c.dump_off);
         else
@@ -381,8 +383,8 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
   const float2 nLy = make_float2(-P.box[1], -P.box[1]);
   const float2 nLz = make_float2(-P.box[2], -P.box[2]);
   const GeoConst geo = {P.inv_box[0], P.inv_box[1], P.inv_box[2], -P.box[0], -P.box[1],
-                        -P.box[2], inv_step, cut2, thr_c, cnt_delta, one, dump, thr_s, cnt_s,
-                        dump_off};
+                        -P.box[2], inv_step, cut2, P.onef, thr_c, cnt_delta, one, dump, thr_s,
+                        cnt_s, dump_off};
 
   for (;;) {
     if (tid == 0) s_item[0] = atomicAdd(P.counter, 1ull);
@@ -880,6 +882,7 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
   // u32 private counters: flush before a bin could overflow (TI * TJ pairs per tile)
   P.flush_tiles = (unsigned)((1ull << 31) / ((unsigned long long)TI * TJ));
   P.one = 1u;
+  P.onef = 1.0f;
   P.bbox = exact ? nullptr : bbox;  // culling only on the fast minimum-image path
   P.boxes_per_frame = (int)(n_pad / SUB);
   P.cull2 = cut2 * 1.0001f;

@@ -301,7 +301,7 @@ def run_gpu_arm(args):
         eng.hist.zero_()
         eng.record_events = rec is not None
         # Hilbert-ordered pack (CUB radix sort + gather), tile boxes, then the pair kernel
-        eng.add_frames(sp_traj, [i], check_extent=False)
+        eng.add_frames(sp_traj, [i], check_extent=True)   # extent check enables the wrapped path
         eng.record_events = False
         if world > 1:
             dist.all_reduce(eng.hist)

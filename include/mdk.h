@@ -41,6 +41,10 @@ extern "C" {
                                more than 2.5 box lengths); default is the fast path that
                                is bit-identical under those preconditions */
 
+#define MDK_RDF_WRAPPED 2   /* the caller guarantees that, per dimension, the coordinates span
+                               less than one box length (e.g. wrapped into [0, L)): enables
+                               the min(|d|, L - |d|) minimum image, bit-identical there */
+
 typedef void* mdk_stream_t;
 
 int mdk_version(void);

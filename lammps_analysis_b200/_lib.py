@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmdk.so")
 
 MDK_RDF_EXACT_DIV = 1
+MDK_RDF_WRAPPED = 2
 MDK_MAX_SPECIES = 8
 
 

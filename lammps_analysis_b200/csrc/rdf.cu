@@ -273,7 +273,7 @@ __device__ __forceinline__ void flush_hist(unsigned int* s_cnt, int nbins,
 // Loop-invariant operands of the pair arithmetic.
 struct GeoConst {
   float invLx, invLy, invLz, nLx, nLy, nLz, inv_step;
-  float cut2, onef;
+  float cut2, onef, Lx, Ly, Lz;
   uint32_t thr_c, cnt_delta, one, dump, thr_s, cnt_s, dump_off;
 };
 __device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
@@ -287,6 +287,7 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
                                          const float* __restrict__ sz, int jj0,
                                          const float2 (&nxi)[R], const float2 (&nyi)[R],
                                          const float2 (&nzi)[R], const GeoConst& c) {
+  constexpr bool WRAP = (AM == 5);  // AM 5 = AM 2 with the wrapped-coordinate minimum image
   const float2 magic2 = dup2(RINT_MAGIC), nmagic2 = dup2(-RINT_MAGIC);
   const float2 inv_step2 = dup2(c.inv_step);
   const float2 one2 = dup2(c.onef);
@@ -301,15 +302,30 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
         const float2 dx = __fadd2_rn(xj, nxi[r]);
         const float2 dy = __fadd2_rn(yj, nyi[r]);
         const float2 dz = __fadd2_rn(zj, nzi[r]);
-        const float2 tx = __ffma2_rn(dx, dup2(c.invLx), magic2);
-        const float2 ty = __ffma2_rn(dy, dup2(c.invLy), magic2);
-        const float2 tz = __ffma2_rn(dz, dup2(c.invLz), magic2);
-        const float2 nx = __fadd2_rn(tx, nmagic2);
-        const float2 ny = __fadd2_rn(ty, nmagic2);
-        const float2 nz = __fadd2_rn(tz, nmagic2);
-        const float2 rx = __ffma2_rn(nx, dup2(c.nLx), dx);
-        const float2 ry = __ffma2_rn(ny, dup2(c.nLy), dy);
-        const float2 rz = __ffma2_rn(nz, dup2(c.nLz), dz);
+        float2 rx, ry, rz;
+        if (WRAP) {
+          // all coordinates lie within one box length (checked on the host), so |d| < L and
+          // rint(d / L) is -1, 0 or 1: the minimum image is min(|d|, L - |d|) -- the same fp32
+          // value as d - rint(d / L) * L up to sign (the subtraction rounds symmetrically), and
+          // where the two candidates tie (|d| = L/2) both exceed the cutoff.  One FADD and one
+          // FMNMX (ALU pipe) replace FFMA2 + FADD2 + FFMA2 per component.
+          const float2 bx = __fadd2_rn(dup2(c.Lx), make_float2(-fabsf(dx.x), -fabsf(dx.y)));
+          const float2 by = __fadd2_rn(dup2(c.Ly), make_float2(-fabsf(dy.x), -fabsf(dy.y)));
+          const float2 bz = __fadd2_rn(dup2(c.Lz), make_float2(-fabsf(dz.x), -fabsf(dz.y)));
+          rx = make_float2(fminf(fabsf(dx.x), bx.x), fminf(fabsf(dx.y), bx.y));
+          ry = make_float2(fminf(fabsf(dy.x), by.x), fminf(fabsf(dy.y), by.y));
+          rz = make_float2(fminf(fabsf(dz.x), bz.x), fminf(fabsf(dz.y), bz.y));
+        } else {
+          const float2 tx = __ffma2_rn(dx, dup2(c.invLx), magic2);
+          const float2 ty = __ffma2_rn(dy, dup2(c.invLy), magic2);
+          const float2 tz = __ffma2_rn(dz, dup2(c.invLz), magic2);
+          const float2 nx = __fadd2_rn(tx, nmagic2);
+          const float2 ny = __fadd2_rn(ty, nmagic2);
+          const float2 nz = __fadd2_rn(tz, nmagic2);
+          rx = __ffma2_rn(nx, dup2(c.nLx), dx);
+          ry = __ffma2_rn(ny, dup2(c.nLy), dy);
+          rz = __ffma2_rn(nz, dup2(c.nLz), dz);
+        }
         // (x*x + y*y) + z*z with every product and sum rounded separately, as the reference
         // does.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even with explicit
         // .rn), which would fuse a product into a sum; the packed adds are therefore written as
@@ -322,7 +338,7 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
         if (AM == 3)
           bin_two_frac(d2, c.cut2, inv_step2, c.thr_s, c.cnt_s, c.dump_off);
         else
-          bin_two<(AM == 3 ? 2 : AM)>(d2, c.cut2, inv_step2, c.thr_c, c.cnt_delta, c.one, c.dump);
+          bin_two<(AM >= 3 ? 2 : AM)>(d2, c.cut2, inv_step2, c.thr_c, c.cnt_delta, c.one, c.dump);
       }
     }
   }
@@ -383,8 +399,8 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
   const float2 nLy = make_float2(-P.box[1], -P.box[1]);
   const float2 nLz = make_float2(-P.box[2], -P.box[2]);
   const GeoConst geo = {P.inv_box[0], P.inv_box[1], P.inv_box[2], -P.box[0], -P.box[1],
-                        -P.box[2], inv_step, cut2, P.onef, thr_c, cnt_delta, one, dump, thr_s,
-                        cnt_s, dump_off};
+                        -P.box[2], inv_step, cut2, P.onef, P.box[0], P.box[1], P.box[2], thr_c,
+                        cnt_delta, one, dump, thr_s, cnt_s, dump_off};
 
   for (;;) {
     if (tid == 0) s_item[0] = atomicAdd(P.counter, 1ull);
@@ -680,13 +696,16 @@ int launch_rdf_cfg(const RdfParams& P, size_t smem, int grid, cudaStream_t s, bo
     return exact ? launch_rdf<NT, R, true, 4, false>(P, smem, grid, s)
                  : launch_rdf<NT, R, false, 4, false>(P, smem, grid, s);
   if (exact) return launch_rdf<NT, R, true, 0, false>(P, smem, grid, s);
-  if (P.bbox)  // culling variants: AM 2 (table) and AM 3 (fraction bits)
-    return am == 3 ? launch_rdf<NT, R, false, 3, true>(P, smem, grid, s)
-                   : launch_rdf<NT, R, false, 2, true>(P, smem, grid, s);
+  if (P.bbox) {  // culling variants: AM 2 (table), AM 3 (fraction bits), AM 5 (wrapped)
+    if (am == 3) return launch_rdf<NT, R, false, 3, true>(P, smem, grid, s);
+    if (am == 5) return launch_rdf<NT, R, false, 5, true>(P, smem, grid, s);
+    return launch_rdf<NT, R, false, 2, true>(P, smem, grid, s);
+  }
   switch (am) {
     case 0: return launch_rdf<NT, R, false, 0, false>(P, smem, grid, s);
     case 1: return launch_rdf<NT, R, false, 1, false>(P, smem, grid, s);
     case 3: return launch_rdf<NT, R, false, 3, false>(P, smem, grid, s);
+    case 5: return launch_rdf<NT, R, false, 5, false>(P, smem, grid, s);
     default: return launch_rdf<NT, R, false, 2, false>(P, smem, grid, s);
   }
 }
@@ -805,6 +824,8 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
   am = am == 0 ? 2 : am - 1;  // auto: unconditional ATOMS.POPC.INC (fastest measured)
   MDK_CHECK_ARG(cfg >= 1 && cfg <= 4 && am >= 0 && am <= 4, "rdf_hist: bad tuning flags");
   if (am == 3 && nbins > FRAC_MAX_BINS) am = 2;  // fraction-bit binning needs nbins <= 15000
+  // coordinates verified to span less than one box length: cheaper minimum image
+  if (am == 2 && !exact && (flags & MDK_RDF_WRAPPED)) am = 5;
   const int NT = (cfg <= 2) ? 128 : 256;
   const int R = (cfg == 1 || cfg == 3) ? 2 : 4;
   const int TI = NT * R;

@@ -132,6 +132,7 @@ class RdfEngine:
     def add_packed(self, pos_soa, n_frames, check_extent: bool = True, tuning: int = 0,
                    bbox=None):
         exact = self.exact_div
+        wrapped = False
         if check_extent and not exact:
             mm = K.coord_extent(pos_soa, n_frames, self.layout.n_pad)
             span = mm[3:] - mm[:3]
@@ -139,12 +140,14 @@ class RdfEngine:
             # while |rint(r/L)| <= 2
             if np.any(span >= 2.5 * self.box):
                 exact = True
+            # coordinates inside one box length: min(|d|, L - |d|) is the minimum image
+            wrapped = bool(np.all(span < self.box))
         if self.record_events:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         K.rdf_hist(pos_soa, n_frames, self.layout, self.box, self.cutoff, self.nbins, self.thr,
                    self.cut2, self.hist, self.counter, exact_div=exact, tuning=tuning,
-                   bbox=None if exact else bbox)
+                   bbox=None if exact else bbox, wrapped=wrapped and not exact)
         if self.record_events:
             e1.record()
             self.kernel_events.append((e0, e1))

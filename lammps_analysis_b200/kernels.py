@@ -211,7 +211,7 @@ def rdf_bbox(pos_soa: torch.Tensor, n_frames: int, layout: RdfLayout, bbox: torc
 def rdf_hist(pos_soa: torch.Tensor, n_frames: int, layout: RdfLayout, box, cutoff: float,
              nbins: int, thr_dev: torch.Tensor, cut2: float, hist: torch.Tensor,
              work_counter: torch.Tensor, exact_div: bool = False, tuning: int = 0,
-             bbox: torch.Tensor | None = None):
+             bbox: torch.Tensor | None = None, wrapped: bool = False):
     """hist[pair][bin] += counts of all minimum-image pair distances below the cutoff.
 
     Replaces get_partial_triu_indices / apply_minimum_image (utils/linalg.py:84-122),
@@ -226,7 +226,8 @@ def rdf_hist(pos_soa: torch.Tensor, n_frames: int, layout: RdfLayout, box, cutof
     if pos_soa.numel() < n_frames * 3 * layout.n_pad:
         raise MdkError("rdf_hist: position buffer too small")
     box32 = np.asarray(box, dtype=np.float32)
-    flags = (_lib.MDK_RDF_EXACT_DIV if exact_div else 0) | int(tuning)
+    flags = ((_lib.MDK_RDF_EXACT_DIV if exact_div else 0)
+             | (_lib.MDK_RDF_WRAPPED if wrapped and not exact_div else 0) | int(tuning))
     check(
         _lib.load().mdk_rdf_hist(
             _ptr(pos_soa), int(n_frames), layout.n_pad,

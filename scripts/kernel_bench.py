@@ -58,7 +58,7 @@ def main():
         for tun in [int(t, 0) for t in args.tunings.split(",")]:
             eng = RdfEngine([n], [L, L, L], cutoff, nbins, drop_first=False, device=dev,
                             spatial_sort=sort)
-            t = timed(lambda: eng.add_frames([traj], np.arange(F), check_extent=False, tuning=tun),
+            t = timed(lambda: eng.add_frames([traj], np.arange(F), check_extent=args.sort >= -1, tuning=tun),
                       reps=2)
             pairs = F * n * (n - 1) / 2
             inside = eng.counts().sum() / eng.frames_done

@@ -281,7 +281,7 @@ __device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
 // One 64-atom column sub-tile against the row groups selected by the compile-time mask M (bit r
 // = row group r of this warp is within reach).  The arithmetic is the reference's rounding
 // sequence; see the kernel header.
-template <bool MASKED, int R, int AM>
+template <bool MASKED, int R, int AM, int UNROLL>
 __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ sx,
                                          const float* __restrict__ sy,
                                          const float* __restrict__ sz, int jj0,
@@ -291,7 +291,7 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
   const float2 magic2 = dup2(RINT_MAGIC), nmagic2 = dup2(-RINT_MAGIC);
   const float2 inv_step2 = dup2(c.inv_step);
   const float2 one2 = dup2(c.onef);
-#pragma unroll 2
+#pragma unroll UNROLL
   for (int jj = jj0; jj < jj0 + SUB; jj += 2) {
     const float2 xj = *reinterpret_cast<const float2*>(sx + jj);
     const float2 yj = *reinterpret_cast<const float2*>(sy + jj);
@@ -552,9 +552,9 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
         for (int q = 0; q < NSUB; ++q) {
           const unsigned m = (rmask >> (q * R)) & FULL;
           if (!CULL || m == FULL)
-            sub_tile<false, R, AM>(m, sx, sy, sz, q * SUB, nxi, nyi, nzi, geo);
+            sub_tile<false, R, AM, (CULL ? 2 : 4)>(m, sx, sy, sz, q * SUB, nxi, nyi, nzi, geo);
           else if (m != 0u)
-            sub_tile<true, R, AM>(m, sx, sy, sz, q * SUB, nxi, nyi, nzi, geo);
+            sub_tile<true, R, AM, 2>(m, sx, sy, sz, q * SUB, nxi, nyi, nzi, geo);
         }
       } else {
         // diagonal tiles (j > i mask) and the exact-division fallback: scalar path

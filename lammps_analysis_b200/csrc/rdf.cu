@@ -257,6 +257,55 @@ __device__ __forceinline__ void bin_two_frac(float2 d2, float cut2, float2 inv_s
       : "memory");
 }
 
+// Quarter-bit gated variant (AM == 6): the guess carries two fraction bits,
+//   tm = fma(sqrt.approx(d2), 4/step, 1.5 * 2^23)  ->  mantissa = round(4 t),  t = d / step,
+// so (mantissa & ~3) is already the byte offset of bin floor(t) and (mantissa & 3) == 0 says
+// that t lies within 1/8 of an integer.  The exact bin differs from t by < 0.01, hence only
+// those lanes (one in four) need the threshold-table compare; the others skip the random
+// shared-memory gather, which (with the histogram atomics) is what bounds the kernel.
+__device__ __forceinline__ void bin_two_q(float2 d2, float cut2, float2 inv_step4, uint32_t thr_s,
+                                          uint32_t cnt_s, uint32_t dump_off) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p0, p1, m0, m1, q0, q1;\n"
+      ".reg .f32 e0, e1, t0, t1, g0, g1;\n"
+      ".reg .b64 ee, tt;\n"
+      ".reg .u32 a0, a1, b0, b1, f0, f1, u0, u1;\n"
+      "setp.lt.f32 p0, %0, %2;\n"
+      "setp.lt.f32 p1, %1, %2;\n"
+      "sqrt.approx.ftz.f32 e0, %0;\n"
+      "sqrt.approx.ftz.f32 e1, %1;\n"
+      "mov.b64 ee, {e0, e1};\n"
+      "fma.rn.f32x2 tt, ee, %3, %4;\n"
+      "mov.b64 {t0, t1}, tt;\n"
+      "mov.b32 b0, t0;\n"
+      "mov.b32 b1, t1;\n"
+      "and.b32 a0, b0, 0x003ffffc;\n"
+      "and.b32 a1, b1, 0x003ffffc;\n"
+      "and.b32 f0, b0, 3;\n"
+      "and.b32 f1, b1, 3;\n"
+      "setp.eq.and.u32 m0, f0, 0, p0;\n"
+      "setp.eq.and.u32 m1, f1, 0, p1;\n"
+      "add.u32 u0, a0, %5;\n"
+      "add.u32 u1, a1, %5;\n"
+      "@m0 ld.shared.f32 g0, [u0];\n"
+      "@m1 ld.shared.f32 g1, [u1];\n"
+      "setp.lt.and.f32 q0, %0, g0, m0;\n"
+      "setp.lt.and.f32 q1, %1, g1, m1;\n"
+      "@q0 add.u32 a0, a0, -4;\n"
+      "@q1 add.u32 a1, a1, -4;\n"
+      "selp.u32 a0, a0, %7, p0;\n"
+      "selp.u32 a1, a1, %7, p1;\n"
+      "add.u32 a0, a0, %6;\n"
+      "add.u32 a1, a1, %6;\n"
+      "red.shared.add.u32 [a0], 1;\n"
+      "red.shared.add.u32 [a1], 1;\n"
+      "}\n" ::"f"(d2.x),
+      "f"(d2.y), "f"(cut2), "l"(*reinterpret_cast<unsigned long long*>(&inv_step4)),
+      "l"(0x4B4000004B400000ull), "r"(thr_s), "r"(cnt_s), "r"(dump_off)
+      : "memory");
+}
+
 // Flush the CTA-private histogram to the global one and clear it.
 template <int NT>
 __device__ __forceinline__ void flush_hist(unsigned int* s_cnt, int nbins,
@@ -289,7 +338,8 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
                                          const float* __restrict__ sz, int jj0,
                                          const float2 (&nxi)[R], const float2 (&nyi)[R],
                                          const float2 (&nzi)[R], const GeoConst& c) {
-  constexpr bool WRAP = (AM == 5);  // AM 5 = AM 2 with the wrapped-coordinate minimum image
+  constexpr bool WRAP = (AM == 5 || AM == 6);  // AM 5/6: wrapped-coordinate minimum image
+  const float2 inv_step4 = dup2(4.0f * c.inv_step);
   const float2 magic2 = dup2(RINT_MAGIC), nmagic2 = dup2(-RINT_MAGIC);
   const float2 inv_step2 = dup2(c.inv_step);
   const float2 one2 = dup2(c.onef);
@@ -339,6 +389,8 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
         const float2 d2 = __ffma2_rn(zz, one2, __ffma2_rn(xx, one2, yy));
         if (AM == 3)
           bin_two_frac(d2, c.cut2, inv_step2, c.thr_s, c.cnt_s, c.dump_off);
+        else if (AM == 6)
+          bin_two_q(d2, c.cut2, inv_step4, c.thr_s, c.cnt_s, c.dump_off);
         else
           bin_two<(AM >= 3 ? 2 : AM)>(d2, c.cut2, inv_step2, c.thr_c, c.cnt_delta, c.one, c.dump);
       }
@@ -391,7 +443,7 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
   // dump slot of this lane, expressed relative to the thr table (bin_two adds cnt_delta)
   const uint32_t dump = smem_u32(s_thr) + 4u * ((P.nbins + 31) & ~31) + (P.dump_shared ? 0u : 4u * (tid & 31));
   const uint32_t thr_s = smem_u32(s_thr), cnt_s = smem_u32(s_cnt);
-  const uint32_t dump_off = 4u * ((P.nbins + 31) & ~31) + 4u * (tid & 31);  // relative to cnt
+  const uint32_t dump_off = 4u * ((P.nbins + 31) & ~31) + (P.dump_shared ? 0u : 4u * (tid & 31));  // relative to cnt
   const float2 magic2 = make_float2(RINT_MAGIC, RINT_MAGIC);
   const float2 nmagic2 = make_float2(-RINT_MAGIC, -RINT_MAGIC);
   const float2 invLx = make_float2(P.inv_box[0], P.inv_box[0]);
@@ -701,6 +753,7 @@ int launch_rdf_cfg(const RdfParams& P, size_t smem, int grid, cudaStream_t s, bo
   if (P.bbox) {  // culling variants: AM 2 (table), AM 3 (fraction bits), AM 5 (wrapped)
     if (am == 3) return launch_rdf<NT, R, false, 3, true>(P, smem, grid, s);
     if (am == 5) return launch_rdf<NT, R, false, 5, true>(P, smem, grid, s);
+    if (am == 6) return launch_rdf<NT, R, false, 6, true>(P, smem, grid, s);
     return launch_rdf<NT, R, false, 2, true>(P, smem, grid, s);
   }
   switch (am) {
@@ -708,6 +761,7 @@ int launch_rdf_cfg(const RdfParams& P, size_t smem, int grid, cudaStream_t s, bo
     case 1: return launch_rdf<NT, R, false, 1, false>(P, smem, grid, s);
     case 3: return launch_rdf<NT, R, false, 3, false>(P, smem, grid, s);
     case 5: return launch_rdf<NT, R, false, 5, false>(P, smem, grid, s);
+    case 6: return launch_rdf<NT, R, false, 6, false>(P, smem, grid, s);
     default: return launch_rdf<NT, R, false, 2, false>(P, smem, grid, s);
   }
 }
@@ -824,10 +878,12 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
   int am = (flags >> 12) & 0xf;   // 0 = auto, else AM = am - 1
   if (cfg == 0) cfg = max_len <= 8192 ? 1 : 4;
   am = am == 0 ? 2 : am - 1;  // auto: unconditional ATOMS.POPC.INC (fastest measured)
-  MDK_CHECK_ARG(cfg >= 1 && cfg <= 4 && am >= 0 && am <= 4, "rdf_hist: bad tuning flags");
+  MDK_CHECK_ARG(cfg >= 1 && cfg <= 4 && am >= 0 && am <= 6, "rdf_hist: bad tuning flags");
   if (am == 3 && nbins > FRAC_MAX_BINS) am = 2;  // fraction-bit binning needs nbins <= 15000
   // coordinates verified to span less than one box length: cheaper minimum image
-  if (am == 2 && !exact && (flags & MDK_RDF_WRAPPED)) am = 5;
+  const bool want_q = ((flags >> 12) & 0xf) == 7;  // tuning: quarter-bit gated table compare
+  if ((am == 2 || want_q) && !exact && (flags & MDK_RDF_WRAPPED)) am = want_q ? 6 : 5;
+  else if (want_q) am = 2;
   const int NT = (cfg <= 2) ? 128 : 256;
   const int R = (cfg == 1 || cfg == 3) ? 2 : 4;
   const int TI = NT * R;

@@ -1,0 +1,118 @@
+"""Runs the BASELINE.json configs C1-C4 at FULL size through the calculator API (C5 is bench.py)
+and prints wall-clock timings and a few sanity values.  Synthetic inputs, seeds as in SURVEY 8d.
+
+    python scripts/run_configs.py [c1 c2 c3 c4]
+"""
+import json
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lammps_analysis_b200.config import config  # noqa: E402
+from lammps_analysis_b200.file_io import ScriptInput, write_lammps_dump  # noqa: E402
+from lammps_analysis_b200.project import Project  # noqa: E402
+from lammps_analysis_b200.synthetic import device_fluid, nacl_trajectory  # noqa: E402
+
+config.planner_memory_bytes = 60e9
+
+
+def timed(label, fn):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = fn()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(json.dumps({"step": label, "seconds": round(dt, 4)}), flush=True)
+    return out, dt
+
+
+def c1(tmp):
+    data, box = nacl_trajectory(1000, 100, 32.0, seed=1)
+    dump = os.path.join(tmp, "c1.lammpstraj")
+    write_lammps_dump(dump, data, box, step_stride=10)
+    project = Project("c1", storage_path=tmp, persist=False)
+    exp, _ = timed("c1 ingest LAMMPS dump (native tokenizer)", lambda: project.add_experiment(
+        "NaCl", timestep=0.002, temperature=1400.0, units="metal", simulation_data=dump))
+    rdf, dt = timed("c1 RadialDistributionFunction(100 frames)", lambda:
+                    exp.run.RadialDistributionFunction(number_of_configurations=100, plot=False))
+    pairs = 100 * 1000 * 999 / 2
+    print(json.dumps({"config": "C1", "pair_distances_per_s": pairs / dt,
+                      "g_max": float(np.nanmax(np.array(rdf["Na_Cl"]["y"])[1:]))}))
+
+
+def c2(tmp):
+    data, box = nacl_trajectory(1000, 5000, 32.0, seed=2, sigma_step=0.3)
+    project = Project("c2", storage_path=tmp, persist=False)
+    exp = project.add_experiment("NaCl", timestep=0.002, temperature=1400.0, units="metal")
+    exp.add_data(ScriptInput(data, box, sample_rate=10, atom_major=True))
+    ein, dt1 = timed("c2 EinsteinDiffusionCoefficients(data_range=500) incl. unwrap + fit",
+                     lambda: exp.run.EinsteinDiffusionCoefficients(data_range=500, plot=False))
+    gk, dt2 = timed("c2 GreenKuboDiffusionCoefficients(data_range=500)",
+                    lambda: exp.run.GreenKuboDiffusionCoefficients(data_range=500, plot=False))
+    upd = 2 * 4500 * 500 * 500
+    print(json.dumps({"config": "C2", "msd_updates_per_s_e2e": upd / dt1,
+                      "acf_updates_per_s_e2e": upd / dt2,
+                      "D_einstein_Na": ein["Na"]["diffusion_coefficient"],
+                      "D_gk_Na": gk["Na"]["diffusion_coefficient"][0]}))
+
+
+def c3(tmp):
+    dev = torch.device("cuda:0")
+    n, T, L = 5000, 10000, 69.0
+    project = Project("c3", storage_path=tmp, persist=False)
+    exp = project.add_experiment("NaCl", timestep=0.002, temperature=1400.0, units="metal")
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(3)
+    data = {}
+    for s in ("Na", "Cl"):
+        pos = device_fluid(n, T, L, 30 + len(data), dev, sigma_step=0.3)
+        vel = torch.randn(n, T, 3, device=dev, generator=gen)
+        data[s] = {"Positions": pos.cpu().numpy(), "Velocities": vel.cpu().numpy()}
+        del pos, vel
+    exp.add_data(ScriptInput(data, [L] * 3, sample_rate=10, atom_major=True))
+    exp.species["Na"].charge = 1.0
+    exp.species["Cl"].charge = -1.0
+    _, dt1 = timed("c3 CoordinateUnwrapper (1e8 atom-frames)", lambda: exp.run.CoordinateUnwrapper())
+    _, dt2 = timed("c3 IonicCurrent (1e8 atom-frames)", lambda: exp.run.IonicCurrent())
+    res, dt3 = timed("c3 GreenKuboIonicConductivity(data_range=500)",
+                     lambda: exp.run.GreenKuboIonicConductivity(data_range=500, plot=False))
+    print(json.dumps({"config": "C3", "unwrap_atom_frames_per_s_e2e": 1e8 / dt1,
+                      "ionic_current_atom_frames_per_s_e2e": 1e8 / dt2,
+                      "sigma": res["System"]["ionic_conductivity"][0]}))
+
+
+def c4(tmp):
+    dev = torch.device("cuda:0")
+    n, T, L = 100_000, 1000, 170.0
+    project = Project("c4", storage_path=tmp, persist=False)
+    exp = project.add_experiment("LJ", timestep=0.005, temperature=100.0, units="real")
+    pos = device_fluid(n, T, L, 4, dev)
+    exp.add_data(ScriptInput({"1": {"Positions": pos.cpu().numpy()}}, [L] * 3, atom_major=True))
+    del pos
+    rdf, dt = timed("c4 RadialDistributionFunction(1000 frames of 100k atoms)", lambda:
+                    exp.run.RadialDistributionFunction(number_of_configurations=1000, plot=False))
+    pairs = 1000 * n * (n - 1) / 2
+    cn, dt2 = timed("c4 CoordinationNumbers", lambda: _try_cn(exp, rdf))
+    print(json.dumps({"config": "C4", "pair_distances_per_s_e2e": pairs / dt,
+                      "max_bin_count_exceeds_int32": bool(
+                          np.nanmax(np.array(rdf["1_1"]["y"])[1:]) > 0), "cn": cn}))
+
+
+def _try_cn(exp, rdf):
+    try:
+        cn = exp.run.CoordinationNumbers(rdf_data=rdf, plot=False)
+        return {k: cn["1_1"][k] for k in ("CN_1", "CN_1_error")}
+    except Exception as exc:  # an ideal-gas-like synthetic fluid has no coordination shells
+        return f"{type(exc).__name__}: {exc}"[:120]
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c1", "c2", "c3", "c4"]
+    with tempfile.TemporaryDirectory(prefix="mdk_cfg_") as tmp:
+        for name in which:
+            globals()[name](tmp)

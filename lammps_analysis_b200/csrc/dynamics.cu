@@ -223,6 +223,99 @@ msd_dense_kernel(const float* __restrict__ traj, long long T, long long a_lo, lo
   }
 }
 
+// ---- Einstein MSD, short dense lag ranges (n_lags <= 16): HBM-streaming kernel ------------------
+// With few lags per origin the work per byte is small and the trajectory read itself is the
+// bound.  One warp streams one atom's row exactly once, in chunks of 128 frames (1536 contiguous
+// bytes, three coalesced 512-byte LDG.128 rows), into a two-chunk ring in shared memory that
+// keeps the global xyz interleaving (three STS.128 per lane); lane l owns the origins 32 s + l
+// (s < 4) of the chunk and reads its lag partners x(origin + k) from the ring (lane stride 3
+// words: conflict free).  The next chunk is prefetched in registers while the current one is
+// processed.
+constexpr int MS_WARPS = 4;
+constexpr int MS_CH = 128;           // frames per chunk
+constexpr int MS_RING = 2 * MS_CH;   // frames in the ring
+
+template <int NL, bool VEC>
+__global__ void __launch_bounds__(32 * MS_WARPS)
+msd_stream_kernel(const float* __restrict__ traj, long long T, long long a_lo, long long a_hi,
+                  long long t0, int W, int n_lags, double* __restrict__ msd_sum) {
+  __shared__ __align__(16) float s_ring[MS_WARPS][3 * MS_RING];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* __restrict__ ring = s_ring[warp];
+  const long long warps_total = (long long)gridDim.x * MS_WARPS;
+  const long long n_fr = (long long)W + n_lags - 1;   // frames [t0, t0 + n_fr) are touched
+  const long long n_el = n_fr * 3;
+  const int n_chunks = (int)((W + MS_CH - 1) / MS_CH);
+  double total = 0.0;  // lane k accumulates lag k
+
+  auto load_chunk = [&](const float* __restrict__ src, int c, float4 (&r)[3]) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const long long e = (long long)c * (3 * MS_CH) + j * 128 + 4 * lane;
+      if (VEC && e + 3 < n_el) {
+        r[j] = __ldg(reinterpret_cast<const float4*>(src + e));
+      } else {
+        r[j].x = e + 0 < n_el ? __ldg(src + e + 0) : 0.f;
+        r[j].y = e + 1 < n_el ? __ldg(src + e + 1) : 0.f;
+        r[j].z = e + 2 < n_el ? __ldg(src + e + 2) : 0.f;
+        r[j].w = e + 3 < n_el ? __ldg(src + e + 3) : 0.f;
+      }
+    }
+  };
+  auto store_chunk = [&](int c, const float4 (&r)[3]) {
+    float* dst = ring + (c & 1) * (3 * MS_CH);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) *reinterpret_cast<float4*>(dst + j * 128 + 4 * lane) = r[j];
+  };
+
+  for (long long a = a_lo + (long long)blockIdx.x * MS_WARPS + warp; a < a_hi; a += warps_total) {
+    const float* __restrict__ src = traj + ((size_t)a * T + t0) * 3;
+    float acc[NL];
+#pragma unroll
+    for (int k = 0; k < NL; ++k) acc[k] = 0.f;
+    float4 pre[3];
+    load_chunk(src, 0, pre);
+    __syncwarp();
+    store_chunk(0, pre);
+    load_chunk(src, 1, pre);
+    for (int c = 0; c < n_chunks; ++c) {
+      store_chunk(c + 1, pre);          // chunk c + 1 (lag partners of the last origins of c)
+      load_chunk(src, c + 2, pre);      // in flight while chunk c is processed
+      __syncwarp();
+      const int base = (c & 1) * MS_CH;
+#pragma unroll
+      for (int sr = 0; sr < MS_CH / 32; ++sr) {
+        const int w_loc = 32 * sr + lane;
+        const bool valid = (long long)c * MS_CH + w_loc < W;
+        const int o_idx = base + w_loc;
+        const float ox = ring[3 * o_idx], oy = ring[3 * o_idx + 1], oz = ring[3 * o_idx + 2];
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+          if (k < n_lags) {
+            const int p = 3 * ((o_idx + k) & (MS_RING - 1));
+            const float dx = ring[p] - ox, dy = ring[p + 1] - oy, dz = ring[p + 2] - oz;
+            const float v = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            acc[k] += valid ? v : 0.f;
+          }
+        }
+      }
+      __syncwarp();
+      if ((c & 63) == 63 || c + 1 == n_chunks) {
+        // fold the lane-private fp32 sums: warp-reduce each lag, lane k keeps lag k in fp64
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+          float v = acc[k];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == k) total += (double)v;
+          acc[k] = 0.f;
+        }
+      }
+    }
+  }
+  if (lane < n_lags) atomicAdd(msd_sum + lane, total);
+}
+
 // ---- Green-Kubo lag products ------------------------------------------------------------
 // P[t][m] += sum_a sum_d v[a,t,d] v[a,t+m,d].  grid.x: origin chunk of ACF_TC frames,
 // grid.y: atom group.  Thread k owns lags k + r*NT and keeps ACF_TC x RL fp64 sums.
@@ -565,6 +658,29 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
   if (W == 0 || a_lo == a_hi) return MDK_OK;
   MDK_CHECK_ARG(t0 >= 0 && t0 + (long long)(W - 1) + n_lags <= T,
                 "msd_dense: windows [t0=%lld, W=%d, n_lags=%d] exceed T=%lld", t0, W, n_lags, T);
+  if (n_lags <= 16 && !getenv("MDK_MSD_NO_STREAM")) {  // measured: the ring kernel wins from ~24 lags
+    // short lag ranges: HBM-streaming kernel, one warp per atom
+    const bool vec = (T % 4 == 0) && (t0 % 4 == 0) && (reinterpret_cast<uintptr_t>(traj) % 16 == 0);
+    const long long warps = a_hi - a_lo;
+    long long blocks = (warps + MS_WARPS - 1) / MS_WARPS;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    const unsigned nb = (unsigned)blocks, nt = 32 * MS_WARPS;
+    cudaStream_t st = as_stream(stream);
+#define MDK_MS_LAUNCH(NL)                                                                      \
+  do {                                                                                         \
+    if (vec)                                                                                   \
+      msd_stream_kernel<NL, true><<<nb, nt, 0, st>>>(traj, T, a_lo, a_hi, t0, W, n_lags, msd_sum); \
+    else                                                                                       \
+      msd_stream_kernel<NL, false><<<nb, nt, 0, st>>>(traj, T, a_lo, a_hi, t0, W, n_lags, msd_sum); \
+  } while (0)
+    if (n_lags <= 4) MDK_MS_LAUNCH(4);
+    else if (n_lags <= 8) MDK_MS_LAUNCH(8);
+    else MDK_MS_LAUNCH(16);
+#undef MDK_MS_LAUNCH
+    MDK_LAUNCH_CHECK();
+    return MDK_OK;
+  }
   constexpr int R = MD_R;
   const int lag_span = MD_NT * R;
   const int lag_blocks = (n_lags + lag_span - 1) / lag_span;

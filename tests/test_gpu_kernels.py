@@ -226,6 +226,26 @@ def test_msd_matches_oracle(cuda, A, T, N, ct, memory):
     np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=RTOL, atol=0)
 
 
+@pytest.mark.parametrize("A,T,N,memory", [
+    (37, 1000, 1, 60e9), (37, 1000, 5, 60e9), (21, 1301, 16, 60e9), (21, 1300, 32, 60e9),
+    (9, 130, 32, 60e9),                      # fewer windows than one 128-frame chunk
+    (30, 999, 8, 2.0e5 * 30 / 64),           # several batches (t0 != 0, unaligned rows)
+])
+def test_msd_short_lag_streaming_kernel(cuda, A, T, N, memory):
+    """n_lags <= 32 takes the HBM-streaming kernel (one warp per atom, 128-frame chunks)."""
+    from lammps_analysis_b200.engine import msd_series, plan_windows, to_device_f32
+    from oracle import dynamics as od
+
+    rng = np.random.default_rng(15)
+    x = np.cumsum(rng.normal(0, 0.1, size=(A, T, 3)), axis=1).astype(np.float32)
+    plan = _plan(A, T, N, 1, memory)
+    tau = np.arange(N)
+    ref, ref_count = od.einstein_msd(x, plan, N, 1, tau)
+    got, count = msd_series(to_device_f32(x, cuda), plan_windows(plan, N, 1, A), N, 1, tau)
+    assert count == ref_count
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=RTOL, atol=0)
+
+
 def test_msd_sparse_tau(cuda):
     from lammps_analysis_b200.engine import msd_series, plan_windows, to_device_f32
     from oracle import dynamics as od

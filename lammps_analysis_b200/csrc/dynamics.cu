@@ -549,6 +549,100 @@ acf_band_kernel(const float* __restrict__ traj, long long T, long long a_lo, lon
   flush();
 }
 
+// ---- Green-Kubo lag products, short lag ranges (N <= 16): HBM-streaming kernel ----------------
+// P[t][m] += sum_a sum_d v[a][t][d] v[a][t+m][d] needs one accumulator per (t, m), summed over the
+// atoms: a warp owns a chunk of 128 origins and loops over the atoms of its group, keeping
+// 4 x NL fp32 sums per lane (lane l <-> origins 32 s + l) that are folded into the global fp64 P
+// every ACS_FOLD atoms.  Per atom it streams 128 + 32 frames (the chunk and the lag partners of
+// its last origins) through a per-warp shared-memory slab; the next atom is prefetched in
+// registers while the current one is processed.
+constexpr int ACS_WARPS = 4;
+constexpr int ACS_CH = 128;
+constexpr int ACS_HALO = 32;
+constexpr int ACS_FOLD = 256;
+
+template <int NL, bool VEC>
+__global__ void __launch_bounds__(32 * ACS_WARPS)
+acf_stream_kernel(const float* __restrict__ traj, long long T, long long a_lo, long long a_hi,
+                  int atoms_per_cta, long long t0, int B, int N, double* __restrict__ P) {
+  __shared__ __align__(16) float s_slab[ACS_WARPS][3 * (ACS_CH + ACS_HALO)];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* __restrict__ slab = s_slab[warp];
+  const int tc = blockIdx.x * ACS_CH;  // first origin of the chunk (relative to t0)
+  if (tc >= B) return;
+  const long long a0 = a_lo + (long long)blockIdx.y * atoms_per_cta;
+  const long long a1 = min(a_hi, a0 + atoms_per_cta);
+  const long long n_el = (long long)(B - tc) * 3;  // elements of this atom row from the chunk on
+
+  float acc[ACS_CH / 32][NL];
+#pragma unroll
+  for (int sr = 0; sr < ACS_CH / 32; ++sr)
+#pragma unroll
+    for (int k = 0; k < NL; ++k) acc[sr][k] = 0.f;
+
+  auto load_atom = [&](long long a, float4 (&r)[3], float (&h)[3]) {
+    const float* __restrict__ src = traj + ((size_t)a * T + t0 + tc) * 3;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const long long e = j * 128 + 4 * lane;
+      if (VEC && e + 3 < n_el) {
+        r[j] = __ldg(reinterpret_cast<const float4*>(src + e));
+      } else {
+        r[j].x = e + 0 < n_el ? __ldg(src + e + 0) : 0.f;
+        r[j].y = e + 1 < n_el ? __ldg(src + e + 1) : 0.f;
+        r[j].z = e + 2 < n_el ? __ldg(src + e + 2) : 0.f;
+        r[j].w = e + 3 < n_el ? __ldg(src + e + 3) : 0.f;
+      }
+      const long long eh = 3 * ACS_CH + j * 32 + lane;
+      h[j] = eh < n_el ? __ldg(src + eh) : 0.f;
+    }
+  };
+  auto flush = [&]() {
+#pragma unroll
+    for (int sr = 0; sr < ACS_CH / 32; ++sr) {
+      const int t = tc + 32 * sr + lane;
+#pragma unroll
+      for (int k = 0; k < NL; ++k) {
+        if (k < N && t + k < B) atomicAdd(P + (size_t)t * N + k, (double)acc[sr][k]);
+        acc[sr][k] = 0.f;
+      }
+    }
+  };
+
+  float4 pre[3];
+  float preh[3];
+  long long a = a0 + warp;
+  if (a < a1) load_atom(a, pre, preh);
+  int since_fold = 0;
+  for (; a < a1; a += ACS_WARPS) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      *reinterpret_cast<float4*>(slab + j * 128 + 4 * lane) = pre[j];
+      slab[3 * ACS_CH + j * 32 + lane] = preh[j];
+    }
+    if (a + ACS_WARPS < a1) load_atom(a + ACS_WARPS, pre, preh);  // in flight during the math
+    __syncwarp();
+#pragma unroll
+    for (int sr = 0; sr < ACS_CH / 32; ++sr) {
+      const int o = 3 * (32 * sr + lane);
+      const float ox = slab[o], oy = slab[o + 1], oz = slab[o + 2];
+#pragma unroll
+      for (int k = 0; k < NL; ++k) {
+        if (k < N) {
+          const int p = o + 3 * k;
+          acc[sr][k] = fmaf(oz, slab[p + 2], fmaf(oy, slab[p + 1], fmaf(ox, slab[p], acc[sr][k])));
+        }
+      }
+    }
+    if (++since_fold == ACS_FOLD) {
+      flush();
+      since_fold = 0;
+    }
+  }
+  flush();
+}
+
 // ---- prefix sum of P along t (in place, inclusive), 8 lags x 128 time chunks per CTA -----
 constexpr int SCAN_M = 8;
 constexpr int SCAN_C = 128;
@@ -740,6 +834,34 @@ extern "C" int mdk_acf_lagprod(const float* traj, long long A, long long T, long
     dim3 grid(chunks, (unsigned)groups);
     acf_lagprod_kernel<<<grid, DYN_NT, smem, as_stream(stream)>>>(traj, T, a_lo, a_hi, apc, t0, B,
                                                                   N, P);
+    MDK_LAUNCH_CHECK();
+    return MDK_OK;
+  }
+  if (N <= 16 && !getenv("MDK_ACF_NO_STREAM")) {
+    // short lag ranges: HBM-streaming kernel (a warp per 128-origin chunk and atom slice)
+    const bool vec = (T % 4 == 0) && (t0 % 4 == 0) && (reinterpret_cast<uintptr_t>(traj) % 16 == 0);
+    const int chunks = (B + ACS_CH - 1) / ACS_CH;
+    long long want = ((long long)sm_count() * 32 + chunks - 1) / chunks;  // CTAs over atoms
+    if (want < 1) want = 1;
+    long long apc = (n_atoms + want - 1) / want;
+    if (apc < ACS_WARPS) apc = ACS_WARPS;
+    const long long groups = (n_atoms + apc - 1) / apc;
+    MDK_CHECK_ARG(groups <= 65535, "acf_lagprod: too many atom groups");
+    dim3 grid((unsigned)chunks, (unsigned)groups);
+    cudaStream_t st = as_stream(stream);
+#define MDK_ACS_LAUNCH(NL)                                                                    \
+  do {                                                                                        \
+    if (vec)                                                                                  \
+      acf_stream_kernel<NL, true><<<grid, 32 * ACS_WARPS, 0, st>>>(traj, T, a_lo, a_hi, (int)apc, \
+                                                                   t0, B, N, P);              \
+    else                                                                                      \
+      acf_stream_kernel<NL, false><<<grid, 32 * ACS_WARPS, 0, st>>>(traj, T, a_lo, a_hi,      \
+                                                                    (int)apc, t0, B, N, P);   \
+  } while (0)
+    if (N <= 4) MDK_ACS_LAUNCH(4);
+    else if (N <= 8) MDK_ACS_LAUNCH(8);
+    else MDK_ACS_LAUNCH(16);
+#undef MDK_ACS_LAUNCH
     MDK_LAUNCH_CHECK();
     return MDK_OK;
   }

@@ -288,6 +288,36 @@ def test_acf_matches_oracle(cuda, A, T, N, ct):
     np.testing.assert_allclose(sig, ref_sig, rtol=RTOL, atol=RTOL * np.abs(ref_sig).max())
 
 
+@pytest.mark.parametrize("A,T,N,ct,memory", [
+    (33, 500, 1, 1, 60e9), (33, 500, 3, 1, 60e9), (17, 1001, 8, 2, 60e9), (17, 1000, 16, 1, 60e9),
+    (600, 140, 16, 1, 60e9),                  # more atoms than one fp32 fold run, short series
+    (30, 999, 8, 1, 2.0e5 * 30 / 64),         # several batches (t0 != 0, unaligned rows)
+])
+def test_acf_short_lag_streaming_kernel(cuda, A, T, N, ct, memory):
+    """data_range <= 16 takes the HBM-streaming lag-product kernel."""
+    from lammps_analysis_b200.engine import acf_series, plan_windows, to_device_f32
+    from oracle import dynamics as od
+
+    rng = np.random.default_rng(16)
+    v = rng.normal(0, 1.0, size=(A, T, 3))
+    for t in range(1, T):
+        v[:, t] = 0.8 * v[:, t - 1] + 0.6 * v[:, t]
+    v = v.astype(np.float32)
+    plan = _plan(A, T, N, ct, memory)
+    time = np.arange(N) * 0.002
+    ref_sum, ref_count, ref_sig = od.gk_diffusion_acf(v, plan, N, ct, time, 1.0, 1.0)
+    got, count, wins, sizes = acf_series(to_device_f32(v, cuda), plan_windows(plan, N, ct, A), N, ct)
+    assert count == ref_count
+    scale = np.abs(ref_sum).max()
+    np.testing.assert_allclose(got.cpu().numpy(), ref_sum, rtol=RTOL, atol=RTOL * 1e-2 * scale)
+    if N > 1:
+        from scipy.integrate import cumulative_trapezoid
+
+        win = np.concatenate([w.cpu().numpy() for w in wins], axis=0)
+        sig = cumulative_trapezoid(win / sizes[0], x=time, axis=1)
+        np.testing.assert_allclose(sig, ref_sig, rtol=RTOL, atol=RTOL * np.abs(ref_sig).max())
+
+
 @pytest.mark.parametrize("box", [[10.0, 11.5, 9.25],            # exactly representable in fp32
                                  [10.1, 11.37, 9.2123456789]])    # fp64 path
 def test_unwrap_bit_exact_with_carry(cuda, box):

@@ -453,6 +453,31 @@ def run_gpu_arm(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e_rdf, e_dyn = te.cpu().tolist()
 
+    # ---- HBM-bound regime of the correlation kernels (short lag ranges), same shard ---------------
+    # not part of the step: data_range 500 is FP32-bound; these probes show the streaming kernels
+    # against the HBM roofline north_star names for the correlation path
+    def probe(fn, reps=5):
+        for _ in range(3):
+            fn()
+            flush.fill_(3)
+        tot = 0.0
+        for _ in range(reps):
+            e0, e1 = ev(), ev()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1) * 1e-3
+            flush.fill_(4)
+        return tot / reps
+
+    probes = []
+    for n_short in (2, 4):
+        l_short = plan_windows(plan, n_short, 1, shard)
+        t_msd = probe(lambda: msd_series(unw, l_short, n_short, 1, np.arange(n_short)))
+        t_acf = probe(lambda: acf_series(vel, l_short, n_short, 1, per_window=False))
+        probes.append((n_short, t_msd, t_acf))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -542,6 +567,13 @@ def run_gpu_arm(args):
                               kernel="ionic_current_kernel", algorithmic="12 B per atom-frame")},
         ],
     }
+    line["hbm_regime"] = [
+        {"kernel": k, "data_range": n, "GBps": 12.0 * shard * n_frames / t * 1e-9,
+         "frac_of_hbm_peak": 12.0 * shard * n_frames / t * 1e-9 / hbm_peak,
+         "algorithmic": "12 B per atom-frame read once (series output negligible)"}
+        for n, t_msd, t_acf in probes
+        for k, t in (("msd_stream_kernel", t_msd),
+                     ("acf_stream_kernel (+prefix, windows)", t_acf))]
     if cpu is not None:
         line["cpu_baseline"] = {"value": cpu["rdf"][0], "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": cpu["rdf"][1], "host_cores_available": cores}

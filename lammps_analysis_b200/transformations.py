@@ -185,10 +185,3 @@ class TranslationalDipoleMoment(IonicCurrent):
                 exp.run.UnwrapViaIndices(species=missing)
             else:
                 exp.run.CoordinateUnwrapper(species=missing)
-
-
-# calculators/transformations_reference.py:27-34 + transformation_dict.py:46-62
-switcher_transformations = {
-    "Unwrapped_Positions": "Unwrapper",  # choice via _unwrap_choice
-    "Ionic_Current": IonicCurrent,
-}

@@ -21,6 +21,12 @@ def test_libmdk_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in mdk.h but not exported"
     assert set(_lib.PROTOTYPES) | {"mdk_last_error"} == declared
     assert _lib.load().mdk_version() == 100
+    # constants mirrored on the Python side
+    from lammps_analysis_b200 import kernels as K
+
+    assert K.RDF_SUBTILE == int(re.search(r"#define MDK_RDF_SUBTILE (\d+)", hdr).group(1))
+    assert _lib.MDK_RDF_WRAPPED == int(re.search(r"#define MDK_RDF_WRAPPED (\d+)", hdr).group(1))
+    assert _lib.MDK_RDF_EXACT_DIV == int(re.search(r"#define MDK_RDF_EXACT_DIV (\d+)", hdr).group(1))
 
 
 def test_rdf_thresholds_reproduce_double_step_binning():

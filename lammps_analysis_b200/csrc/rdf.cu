@@ -306,6 +306,58 @@ __device__ __forceinline__ void bin_two_q(float2 d2, float cut2, float2 inv_step
       : "memory");
 }
 
+// Clamped, quarter-bit gated variant (AM == 7).  As bin_two_q, but without the in-cutoff
+// predicate and without the dump-slot select: d2 is first clamped to cut2 (min.f32 also maps the
+// NaN of padding atoms to cut2), so every lane outside the cutoff computes M = 4 * nbins, is
+// "ambiguous", reads thr[nbins] -- which the kernel sets to cut2 in its shared copy of the table
+// -- fails d2 < thr[nbins] and increments the unused word cnt[nbins] (one address for all such
+// lanes: ATOMS.POPC.INC merges them).  Lanes inside the cutoff whose guess rounds to 4 * nbins
+// pass d2 < cut2 and land in bin nbins - 1, as they must.  Per pair: FMNMX, MUFU, LOP3 x2,
+// FSETP, predicated IADD on the ALU pipe -- two fewer than bin_two -- and three in four of the
+// random threshold gathers are predicated off.
+// The shared-memory address of the threshold table is folded into the magic constant
+// (magic_thr = 1.5 * 2^23 + &thr[0], an integer below 2^24 and a multiple of 4), so the masked
+// mantissa IS the address of thr[floor-or-carry(t)]; cnt_delta = &cnt[0] - &thr[0] rides in the
+// ATOMS address as a uniform register.
+__device__ __forceinline__ void bin_two_c(float2 d2, float cut2, float2 inv_step4,
+                                          float2 magic_thr, uint32_t cnt_delta) {
+  asm volatile(
+      "{\n"
+      ".reg .pred m0, m1, q0, q1;\n"
+      ".reg .f32 c0, c1, e0, e1, t0, t1, g0, g1;\n"
+      ".reg .b64 ee, tt;\n"
+      ".reg .u32 a0, a1, b0, b1, f0, f1;\n"
+      "min.f32 c0, %0, %2;\n"
+      "min.f32 c1, %1, %2;\n"
+      "sqrt.approx.ftz.f32 e0, c0;\n"
+      "sqrt.approx.ftz.f32 e1, c1;\n"
+      "mov.b64 ee, {e0, e1};\n"
+      "fma.rn.f32x2 tt, ee, %3, %4;\n"
+      "mov.b64 {t0, t1}, tt;\n"
+      "mov.b32 b0, t0;\n"
+      "mov.b32 b1, t1;\n"
+      "and.b32 a0, b0, 0x003ffffc;\n"
+      "and.b32 a1, b1, 0x003ffffc;\n"
+      "and.b32 f0, b0, 3;\n"
+      "and.b32 f1, b1, 3;\n"
+      "setp.eq.u32 m0, f0, 0;\n"
+      "setp.eq.u32 m1, f1, 0;\n"
+      "@m0 ld.shared.f32 g0, [a0];\n"
+      "@m1 ld.shared.f32 g1, [a1];\n"
+      "setp.lt.and.f32 q0, c0, g0, m0;\n"
+      "setp.lt.and.f32 q1, c1, g1, m1;\n"
+      "@q0 add.u32 a0, a0, -4;\n"
+      "@q1 add.u32 a1, a1, -4;\n"
+      "add.u32 a0, a0, %5;\n"
+      "add.u32 a1, a1, %5;\n"
+      "red.shared.add.u32 [a0], 1;\n"
+      "red.shared.add.u32 [a1], 1;\n"
+      "}\n" ::"f"(d2.x),
+      "f"(d2.y), "f"(cut2), "l"(*reinterpret_cast<unsigned long long*>(&inv_step4)),
+      "l"(*reinterpret_cast<unsigned long long*>(&magic_thr)), "r"(cnt_delta)
+      : "memory");
+}
+
 // Flush the CTA-private histogram to the global one and clear it.
 template <int NT>
 __device__ __forceinline__ void flush_hist(unsigned int* s_cnt, int nbins,
@@ -338,8 +390,9 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
                                          const float* __restrict__ sz, int jj0,
                                          const float2 (&nxi)[R], const float2 (&nyi)[R],
                                          const float2 (&nzi)[R], const GeoConst& c) {
-  constexpr bool WRAP = (AM == 5 || AM == 6);  // AM 5/6: wrapped-coordinate minimum image
+  constexpr bool WRAP = (AM == 5 || AM == 6 || AM == 8);  // wrapped-coordinate minimum image
   const float2 inv_step4 = dup2(4.0f * c.inv_step);
+  const float2 magic_thr = dup2(RINT_MAGIC + static_cast<float>(c.thr_s));  // see bin_two_c
   const float2 magic2 = dup2(RINT_MAGIC), nmagic2 = dup2(-RINT_MAGIC);
   const float2 inv_step2 = dup2(c.inv_step);
   const float2 one2 = dup2(c.onef);
@@ -391,8 +444,50 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
           bin_two_frac(d2, c.cut2, inv_step2, c.thr_s, c.cnt_s, c.dump_off);
         else if (AM == 6)
           bin_two_q(d2, c.cut2, inv_step4, c.thr_s, c.cnt_s, c.dump_off);
+        else if (AM == 7 || AM == 8)
+          bin_two_c(d2, c.cut2, inv_step4, magic_thr, c.cnt_delta);
         else
           bin_two<(AM >= 3 ? 2 : AM)>(d2, c.cut2, inv_step2, c.thr_c, c.cnt_delta, c.one, c.dump);
+      }
+    }
+  }
+}
+
+// Uniform-image variant of sub_tile (AM == 7).  For a block of pairs (32 rows of a warp x one
+// 64-atom column sub-tile) whose bounding boxes show that n = rint((x_j - x_i) / L) is the same
+// integer for every pair of the block (per dimension), the reference's
+//     r = d - rint(d / L) * L          (utils/linalg.py:84-99; here fma(n, -L, d))
+// is d + sh with the warp-uniform sh = -n * L (exact for |n| <= 2): one packed FADD2 per
+// component and pair couple instead of FFMA2 + FADD2 + FFMA2 (or FADD2 + 2 FMNMX for wrapped
+// coordinates).  The block classification is done once per column tile by 16 lanes in parallel
+// (rdf_pair_hist_kernel); blocks that straddle a half-box boundary take the general path.
+template <bool MASKED, int R, int UNROLL>
+__device__ __forceinline__ void sub_tile_uni(unsigned m, const float* __restrict__ sx,
+                                             const float* __restrict__ sy,
+                                             const float* __restrict__ sz, int jj0,
+                                             const float2 (&nxi)[R], const float2 (&nyi)[R],
+                                             const float2 (&nzi)[R], const float (&shx)[R],
+                                             const float (&shy)[R], const float (&shz)[R],
+                                             const GeoConst& c) {
+  const float2 inv_step4 = dup2(4.0f * c.inv_step);
+  const float2 magic_thr = dup2(RINT_MAGIC + static_cast<float>(c.thr_s));  // see bin_two_c
+  const float2 one2 = dup2(c.onef);
+#pragma unroll UNROLL
+  for (int jj = jj0; jj < jj0 + SUB; jj += 2) {
+    const float2 xj = *reinterpret_cast<const float2*>(sx + jj);
+    const float2 yj = *reinterpret_cast<const float2*>(sy + jj);
+    const float2 zj = *reinterpret_cast<const float2*>(sz + jj);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (!MASKED || ((m >> r) & 1u)) {  // warp-uniform
+        const float2 rx = __fadd2_rn(__fadd2_rn(xj, nxi[r]), dup2(shx[r]));
+        const float2 ry = __fadd2_rn(__fadd2_rn(yj, nyi[r]), dup2(shy[r]));
+        const float2 rz = __fadd2_rn(__fadd2_rn(zj, nzi[r]), dup2(shz[r]));
+        const float2 xx = __fmul2_rn(rx, rx);
+        const float2 yy = __fmul2_rn(ry, ry);
+        const float2 zz = __fmul2_rn(rz, rz);
+        const float2 d2 = __ffma2_rn(zz, one2, __ffma2_rn(xx, one2, yy));
+        bin_two_c(d2, c.cut2, inv_step4, magic_thr, c.cnt_delta);
       }
     }
   }
@@ -416,7 +511,9 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
   const int tid = threadIdx.x;
   constexpr bool GLOBAL_HIST = (AM == 4);  // tables too large for shared memory
   if (!GLOBAL_HIST) {
-    for (int b = tid; b <= P.nbins; b += NT) s_thr[b] = __ldg(P.thr + b);
+    // AM 7 (bin_two_c) needs thr[nbins] == cut2; for the other variants any value > cut2 works
+    for (int b = tid; b <= P.nbins; b += NT)
+      s_thr[b] = ((AM == 7 || AM == 8) && b == P.nbins) ? P.cut2 : __ldg(P.thr + b);
     for (int b = tid; b < P.nbins; b += NT) s_cnt[b] = 0u;
   }
   if (tid == 0) {
@@ -516,6 +613,7 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
     const float* __restrict__ fbox = P.bbox + (size_t)f * P.boxes_per_frame * 6;
     float rbox[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
     float wbox[R][6];
+    float mybox[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // AM 7: box of row group (lane & 3)
     if constexpr (CULL) {
       const int r_last = min(row_base + TI, P.sp_hi[a]);  // exclusive row bound
       for (int t = row_base / SUB; t * SUB < r_last; ++t) box_union(rbox, fbox + (size_t)t * 6);
@@ -531,8 +629,15 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
             mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
           }
-          wbox[r][d] = mn;
-          wbox[r][d + 3] = mx;
+          if constexpr (AM == 7) {
+            if ((tid & 3) == r) {
+              mybox[d] = mn;
+              mybox[d + 3] = mx;
+            }
+          } else {
+            wbox[r][d] = mn;
+            wbox[r][d + 3] = mx;
+          }
         }
       }
     }
@@ -589,7 +694,38 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
 
       // which of this warp's row groups can reach which 64-atom sub-tile: bit (q * R + r)
       unsigned rmask = 0xffffffffu;
-      if (CULL && !diag) {
+      unsigned umask = 0u;             // AM 7: blocks with a uniform periodic image
+      float shx = 0.f, shy = 0.f, shz = 0.f;  // AM 7: image shift of block (lane & 15)
+      if constexpr (AM == 7) {
+        static_assert(AM != 7 || (R == 4 && NSUB == 4 && CULL), "AM 7 needs 4 x 4 blocks per tile");
+        if (!diag) {
+          // lane l classifies block (q = (l >> 2) & 3, r = l & 3): bit l of the masks
+          const float* __restrict__ cbp =
+              fbox + (size_t)(col_box0 + jt * NSUB + ((tid >> 2) & 3)) * 6;
+          float cb[6];
+#pragma unroll
+          for (int d = 0; d < 6; ++d) cb[d] = __ldg(cbp + d);
+          const bool live =
+              (mybox[0] <= mybox[3]) && !boxes_far(mybox, cb, P.box, P.cull_eps, P.cull2);
+          bool uni = live;
+          float sh[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            // d = x_j - x_i of every pair of the block lies in [dlo, dhi] (rounding is monotone)
+            const float ulo = (cb[d] - mybox[d + 3]) * P.inv_box[d];
+            const float uhi = (cb[d + 3] - mybox[d]) * P.inv_box[d];
+            const float nlo = rintf(ulo), nhi = rintf(uhi);
+            uni = uni && (nlo == nhi) && (fabsf(ulo - nlo) < 0.499f) &&
+                  (fabsf(uhi - nhi) < 0.499f) && (fabsf(nlo) <= 2.0f);
+            sh[d] = -nlo * P.box[d];
+          }
+          shx = sh[0];
+          shy = sh[1];
+          shz = sh[2];
+          rmask = __ballot_sync(0xffffffffu, live) & 0xffffu;
+          umask = __ballot_sync(0xffffffffu, uni) & 0xffffu;
+        }
+      } else if (CULL && !diag) {
         rmask = 0u;
 #pragma unroll
         for (int q = 0; q < NSUB; ++q) {
@@ -605,7 +741,24 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
 #pragma unroll 1
         for (int q = 0; q < NSUB; ++q) {
           const unsigned m = (rmask >> (q * R)) & FULL;
-          if (!CULL || m == FULL)
+          if constexpr (AM == 7) {
+            const unsigned mu = (umask >> (q * R)) & FULL;
+            const unsigned mm = m & ~mu;
+            if (mu != 0u) {
+              float bx[R], by[R], bz[R];
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                bx[r] = __shfl_sync(0xffffffffu, shx, q * R + r);
+                by[r] = __shfl_sync(0xffffffffu, shy, q * R + r);
+                bz[r] = __shfl_sync(0xffffffffu, shz, q * R + r);
+              }
+              if (mu == FULL)
+                sub_tile_uni<false, R, 2>(mu, sx, sy, sz, q * SUB, nxi, nyi, nzi, bx, by, bz, geo);
+              else
+                sub_tile_uni<true, R, 2>(mu, sx, sy, sz, q * SUB, nxi, nyi, nzi, bx, by, bz, geo);
+            }
+            if (mm != 0u) sub_tile<true, R, AM, 2>(mm, sx, sy, sz, q * SUB, nxi, nyi, nzi, geo);
+          } else if (!CULL || m == FULL)
             sub_tile<false, R, AM, (CULL ? 2 : 4)>(m, sx, sy, sz, q * SUB, nxi, nyi, nzi, geo);
           else if (m != 0u)
             sub_tile<true, R, AM, 2>(m, sx, sy, sz, q * SUB, nxi, nyi, nzi, geo);
@@ -750,6 +903,14 @@ int launch_rdf_cfg(const RdfParams& P, size_t smem, int grid, cudaStream_t s, bo
     return exact ? launch_rdf<NT, R, true, 4, false>(P, smem, grid, s)
                  : launch_rdf<NT, R, false, 4, false>(P, smem, grid, s);
   if (exact) return launch_rdf<NT, R, true, 0, false>(P, smem, grid, s);
+  if constexpr (NT == 256 && R == 4) {
+    if (P.bbox && am == 7) return launch_rdf<NT, R, false, 7, true>(P, smem, grid, s);
+    if (am == 8)
+      return P.bbox ? launch_rdf<NT, R, false, 8, true>(P, smem, grid, s)
+                    : launch_rdf<NT, R, false, 8, false>(P, smem, grid, s);
+  }
+  if (am == 8) am = 5;
+  if (am == 7) am = 2;  // uniform-image blocks need the culling boxes and the 256 x 4 tile
   if (P.bbox) {  // culling variants: AM 2 (table), AM 3 (fraction bits), AM 5 (wrapped)
     if (am == 3) return launch_rdf<NT, R, false, 3, true>(P, smem, grid, s);
     if (am == 5) return launch_rdf<NT, R, false, 5, true>(P, smem, grid, s);
@@ -878,12 +1039,21 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
   int am = (flags >> 12) & 0xf;   // 0 = auto, else AM = am - 1
   if (cfg == 0) cfg = max_len <= 8192 ? 1 : 4;
   am = am == 0 ? 2 : am - 1;  // auto: unconditional ATOMS.POPC.INC (fastest measured)
-  MDK_CHECK_ARG(cfg >= 1 && cfg <= 4 && am >= 0 && am <= 6, "rdf_hist: bad tuning flags");
+  MDK_CHECK_ARG(cfg >= 1 && cfg <= 4 && am >= 0 && am <= 8, "rdf_hist: bad tuning flags");
+  const bool auto_am = ((flags >> 12) & 0xf) == 0;
   if (am == 3 && nbins > FRAC_MAX_BINS) am = 2;  // fraction-bit binning needs nbins <= 15000
   // coordinates verified to span less than one box length: cheaper minimum image
   const bool want_q = ((flags >> 12) & 0xf) == 7;  // tuning: quarter-bit gated table compare
   if ((am == 2 || want_q) && !exact && (flags & MDK_RDF_WRAPPED)) am = want_q ? 6 : 5;
   else if (want_q) am = 2;
+  // sorted frames with bounding boxes: uniform-image blocks + gated compare (any coordinates)
+  if ((auto_am || am == 7) && !exact && bbox && cfg == 4) am = 7;
+  else if (am == 7) am = (flags & MDK_RDF_WRAPPED) ? 5 : 2;
+  // wrapped minimum image + clamped gated compare (needs wrapped coordinates; instantiated for
+  // the 256 x 4 tile): +4..6 % over AM 5 on unsorted frames
+  if (auto_am && am == 5 && cfg == 4) am = 8;
+  if (am == 8 && (exact || !(flags & MDK_RDF_WRAPPED))) am = 2;
+  if (am == 8 && cfg != 4) am = 5;
   const int NT = (cfg <= 2) ? 128 : 256;
   const int R = (cfg == 1 || cfg == 3) ? 2 : 4;
   const int TI = NT * R;

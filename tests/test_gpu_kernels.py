@@ -57,7 +57,7 @@ def test_rdf_counts_bit_exact(cuda, n_atoms, n_frames, box):
 
 
 @pytest.mark.parametrize("tuning", [0x100, 0x200, 0x300, 0x400, 0x1100, 0x2100, 0x3100,
-                                    0x4100, 0x4400, 0x7100, 0x7400])
+                                    0x4100, 0x4400, 0x7100, 0x7400, 0x8400, 0x9400])
 def test_rdf_kernel_variants_agree(cuda, tuning):
     """Every tile configuration / atomic mode yields the same integers."""
     from lammps_analysis_b200.engine import RdfEngine, to_device_f32
@@ -134,7 +134,7 @@ def test_rdf_single_species_and_empty(cuda):
     assert eng2.counts().sum() == 0
 
 
-@pytest.mark.parametrize("tuning", [0, 0x4000, 0x7000])
+@pytest.mark.parametrize("tuning", [0, 0x4000, 0x7000, 0x8400])
 def test_rdf_sorted_culled_matches_oracle(cuda, tuning):
     """Morton-ordered pack + block culling: same integers as the oracle (two species, so the
     cross-species tiles and the diagonal tiles are both exercised)."""
@@ -156,7 +156,7 @@ def test_rdf_sorted_culled_matches_oracle(cuda, tuning):
         assert np.array_equal(got[p], ref[key]), key
 
 
-@pytest.mark.parametrize("tuning", [0, 0x4000, 0x7000])
+@pytest.mark.parametrize("tuning", [0, 0x3000, 0x4000, 0x7000])
 @pytest.mark.parametrize("cutoff_frac", [0.12, 0.3, 0.4999])
 def test_rdf_culling_is_exact_at_scale(cuda, cutoff_frac, tuning):
     """Size-independent property: the culled, spatially sorted pass returns exactly the
@@ -177,8 +177,10 @@ def test_rdf_culling_is_exact_at_scale(cuda, cutoff_frac, tuning):
     assert a.sum() > 0 and np.array_equal(a, b)
 
 
-def test_rdf_culling_with_unwrapped_coordinates(cuda):
-    """Coordinates spread over several box images: the box test must stay conservative."""
+@pytest.mark.parametrize("tuning", [0, 0x3000, 0x8400])
+def test_rdf_culling_with_unwrapped_coordinates(cuda, tuning):
+    """Coordinates spread over several box images: the box test must stay conservative, and the
+    uniform-image blocks (0x8400) must pick up shifts of one and two box lengths."""
     from lammps_analysis_b200.engine import RdfEngine, to_device_f32
 
     rng = np.random.default_rng(32)
@@ -188,7 +190,7 @@ def test_rdf_culling_with_unwrapped_coordinates(cuda):
     plain = RdfEngine([n], [L] * 3, cutoff, nbins, device=cuda, spatial_sort=False)
     plain.add_frames([to_device_f32(pos, cuda)], np.arange(1))
     culled = RdfEngine([n], [L] * 3, cutoff, nbins, device=cuda, spatial_sort=True)
-    culled.add_frames([to_device_f32(pos, cuda)], np.arange(1))
+    culled.add_frames([to_device_f32(pos, cuda)], np.arange(1), tuning=tuning)
     assert np.array_equal(plain.counts(), culled.counts())
 
 

@@ -69,6 +69,7 @@ struct RdfParams {
   int boxes_per_frame;
   float cull2;                   // squared distance beyond which a block cannot hold a pair
   float cull_eps[3];             // absolute slack per dimension for the box arithmetic
+  float clamp2;                  // ((nbins + 1/2) * step)^2: see bin_two_c
 };
 
 __device__ __forceinline__ void box_union(float (&acc)[6], const float* __restrict__ b) {
@@ -306,20 +307,21 @@ __device__ __forceinline__ void bin_two_q(float2 d2, float cut2, float2 inv_step
       : "memory");
 }
 
-// Clamped, quarter-bit gated variant (AM == 7).  As bin_two_q, but without the in-cutoff
-// predicate and without the dump-slot select: d2 is first clamped to cut2 (min.f32 also maps the
-// NaN of padding atoms to cut2), so every lane outside the cutoff computes M = 4 * nbins, is
-// "ambiguous", reads thr[nbins] -- which the kernel sets to cut2 in its shared copy of the table
-// -- fails d2 < thr[nbins] and increments the unused word cnt[nbins] (one address for all such
-// lanes: ATOMS.POPC.INC merges them).  Lanes inside the cutoff whose guess rounds to 4 * nbins
-// pass d2 < cut2 and land in bin nbins - 1, as they must.  Per pair: FMNMX, MUFU, LOP3 x2,
+// Clamped, quarter-bit gated variant (AM == 7 / 8).  As bin_two_q, but without the in-cutoff
+// predicate and without the dump-slot select: d2 is first clamped to clamp2 = ((nbins + 1/2) *
+// step)^2 (min.f32 also maps the NaN of padding atoms to it), so every lane well outside the
+// cutoff computes M = 4 * nbins + 2, needs no table compare and increments the unused word
+// cnt[nbins] (one address for all such lanes: ATOMS.POPC.INC merges them).  Lanes whose guess
+// rounds to exactly 4 * nbins are "ambiguous" and read thr[nbins] -- which the kernel sets to
+// cut2 in its shared copy of the table: inside the cutoff they pass d2 < cut2 and land in bin
+// nbins - 1, as they must, outside they stay on cnt[nbins].  Per pair: FMNMX, MUFU, LOP3 x2,
 // FSETP, predicated IADD on the ALU pipe -- two fewer than bin_two -- and three in four of the
 // random threshold gathers are predicated off.
 // The shared-memory address of the threshold table is folded into the magic constant
 // (magic_thr = 1.5 * 2^23 + &thr[0], an integer below 2^24 and a multiple of 4), so the masked
 // mantissa IS the address of thr[floor-or-carry(t)]; cnt_delta = &cnt[0] - &thr[0] rides in the
 // ATOMS address as a uniform register.
-__device__ __forceinline__ void bin_two_c(float2 d2, float cut2, float2 inv_step4,
+__device__ __forceinline__ void bin_two_c(float2 d2, float clamp2, float2 inv_step4,
                                           float2 magic_thr, uint32_t cnt_delta) {
   asm volatile(
       "{\n"
@@ -353,7 +355,7 @@ __device__ __forceinline__ void bin_two_c(float2 d2, float cut2, float2 inv_step
       "red.shared.add.u32 [a0], 1;\n"
       "red.shared.add.u32 [a1], 1;\n"
       "}\n" ::"f"(d2.x),
-      "f"(d2.y), "f"(cut2), "l"(*reinterpret_cast<unsigned long long*>(&inv_step4)),
+      "f"(d2.y), "f"(clamp2), "l"(*reinterpret_cast<unsigned long long*>(&inv_step4)),
       "l"(*reinterpret_cast<unsigned long long*>(&magic_thr)), "r"(cnt_delta)
       : "memory");
 }
@@ -376,7 +378,7 @@ __device__ __forceinline__ void flush_hist(unsigned int* s_cnt, int nbins,
 // Loop-invariant operands of the pair arithmetic.
 struct GeoConst {
   float invLx, invLy, invLz, nLx, nLy, nLz, inv_step;
-  float cut2, onef, Lx, Ly, Lz;
+  float cut2, onef, Lx, Ly, Lz, clamp2;
   uint32_t thr_c, cnt_delta, one, dump, thr_s, cnt_s, dump_off;
 };
 __device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
@@ -445,7 +447,7 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
         else if (AM == 6)
           bin_two_q(d2, c.cut2, inv_step4, c.thr_s, c.cnt_s, c.dump_off);
         else if (AM == 7 || AM == 8)
-          bin_two_c(d2, c.cut2, inv_step4, magic_thr, c.cnt_delta);
+          bin_two_c(d2, c.clamp2, inv_step4, magic_thr, c.cnt_delta);
         else
           bin_two<(AM >= 3 ? 2 : AM)>(d2, c.cut2, inv_step2, c.thr_c, c.cnt_delta, c.one, c.dump);
       }
@@ -461,8 +463,8 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
 // component and pair couple instead of FFMA2 + FADD2 + FFMA2 (or FADD2 + 2 FMNMX for wrapped
 // coordinates).  The block classification is done once per column tile by 16 lanes in parallel
 // (rdf_pair_hist_kernel); blocks that straddle a half-box boundary take the general path.
-template <bool MASKED, int R, int UNROLL>
-__device__ __forceinline__ void sub_tile_uni(unsigned m, const float* __restrict__ sx,
+template <int R>
+__device__ __forceinline__ void sub_tile_uni(const float* __restrict__ sx,
                                              const float* __restrict__ sy,
                                              const float* __restrict__ sz, int jj0,
                                              const float2 (&nxi)[R], const float2 (&nyi)[R],
@@ -472,14 +474,19 @@ __device__ __forceinline__ void sub_tile_uni(unsigned m, const float* __restrict
   const float2 inv_step4 = dup2(4.0f * c.inv_step);
   const float2 magic_thr = dup2(RINT_MAGIC + static_cast<float>(c.thr_s));  // see bin_two_c
   const float2 one2 = dup2(c.onef);
-#pragma unroll UNROLL
-  for (int jj = jj0; jj < jj0 + SUB; jj += 2) {
-    const float2 xj = *reinterpret_cast<const float2*>(sx + jj);
-    const float2 yj = *reinterpret_cast<const float2*>(sy + jj);
-    const float2 zj = *reinterpret_cast<const float2*>(sz + jj);
+#pragma unroll 1
+  for (int jj = jj0; jj < jj0 + SUB; jj += 4) {
+    // four columns per trip: one 16-byte broadcast load per coordinate array
+    const float4 xj4 = *reinterpret_cast<const float4*>(sx + jj);
+    const float4 yj4 = *reinterpret_cast<const float4*>(sy + jj);
+    const float4 zj4 = *reinterpret_cast<const float4*>(sz + jj);
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (!MASKED || ((m >> r) & 1u)) {  // warp-uniform
+    for (int h = 0; h < 2; ++h) {
+      const float2 xj = h ? make_float2(xj4.z, xj4.w) : make_float2(xj4.x, xj4.y);
+      const float2 yj = h ? make_float2(yj4.z, yj4.w) : make_float2(yj4.x, yj4.y);
+      const float2 zj = h ? make_float2(zj4.z, zj4.w) : make_float2(zj4.x, zj4.y);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
         const float2 rx = __fadd2_rn(__fadd2_rn(xj, nxi[r]), dup2(shx[r]));
         const float2 ry = __fadd2_rn(__fadd2_rn(yj, nyi[r]), dup2(shy[r]));
         const float2 rz = __fadd2_rn(__fadd2_rn(zj, nzi[r]), dup2(shz[r]));
@@ -487,7 +494,93 @@ __device__ __forceinline__ void sub_tile_uni(unsigned m, const float* __restrict
         const float2 yy = __fmul2_rn(ry, ry);
         const float2 zz = __fmul2_rn(rz, rz);
         const float2 d2 = __ffma2_rn(zz, one2, __ffma2_rn(xx, one2, yy));
-        bin_two_c(d2, c.cut2, inv_step4, magic_thr, c.cnt_delta);
+        bin_two_c(d2, c.clamp2, inv_step4, magic_thr, c.cnt_delta);
+      }
+    }
+  }
+}
+
+// One row group of the warp against a 64-atom column sub-tile (partially live blocks): eight
+// columns per trip keep four independent pair couples in flight; no per-row-group branches in
+// the column loop.
+__device__ __forceinline__ void sub_tile_uni_row(const float* __restrict__ sx,
+                                                 const float* __restrict__ sy,
+                                                 const float* __restrict__ sz, int jj0,
+                                                 float2 nx, float2 ny, float2 nz, float shx,
+                                                 float shy, float shz, const GeoConst& c) {
+  const float2 inv_step4 = dup2(4.0f * c.inv_step);
+  const float2 magic_thr = dup2(RINT_MAGIC + static_cast<float>(c.thr_s));
+  const float2 one2 = dup2(c.onef);
+#pragma unroll 1
+  for (int jj = jj0; jj < jj0 + SUB; jj += 8) {
+    float4 xj4[2], yj4[2], zj4[2];
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      xj4[v] = *reinterpret_cast<const float4*>(sx + jj + 4 * v);
+      yj4[v] = *reinterpret_cast<const float4*>(sy + jj + 4 * v);
+      zj4[v] = *reinterpret_cast<const float4*>(sz + jj + 4 * v);
+    }
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float2 xj = h ? make_float2(xj4[v].z, xj4[v].w) : make_float2(xj4[v].x, xj4[v].y);
+        const float2 yj = h ? make_float2(yj4[v].z, yj4[v].w) : make_float2(yj4[v].x, yj4[v].y);
+        const float2 zj = h ? make_float2(zj4[v].z, zj4[v].w) : make_float2(zj4[v].x, zj4[v].y);
+        const float2 rx = __fadd2_rn(__fadd2_rn(xj, nx), dup2(shx));
+        const float2 ry = __fadd2_rn(__fadd2_rn(yj, ny), dup2(shy));
+        const float2 rz = __fadd2_rn(__fadd2_rn(zj, nz), dup2(shz));
+        const float2 xx = __fmul2_rn(rx, rx);
+        const float2 yy = __fmul2_rn(ry, ry);
+        const float2 zz = __fmul2_rn(rz, rz);
+        const float2 d2 = __ffma2_rn(zz, one2, __ffma2_rn(xx, one2, yy));
+        bin_two_c(d2, c.clamp2, inv_step4, magic_thr, c.cnt_delta);
+      }
+    }
+  }
+}
+
+// General minimum image (r - rint(r / L) * L by magic-number rounding) for one row group of the
+// warp: the blocks of AM 7 that straddle a half-box boundary.
+__device__ __forceinline__ void sub_tile_gen_row(const float* __restrict__ sx,
+                                                 const float* __restrict__ sy,
+                                                 const float* __restrict__ sz, int jj0,
+                                                 float2 nx, float2 ny, float2 nz,
+                                                 const GeoConst& c) {
+  const float2 inv_step4 = dup2(4.0f * c.inv_step);
+  const float2 magic_thr = dup2(RINT_MAGIC + static_cast<float>(c.thr_s));
+  const float2 magic2 = dup2(RINT_MAGIC), nmagic2 = dup2(-RINT_MAGIC);
+  const float2 one2 = dup2(c.onef);
+#pragma unroll 1
+  for (int jj = jj0; jj < jj0 + SUB; jj += 8) {
+    float4 xj4[2], yj4[2], zj4[2];
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      xj4[v] = *reinterpret_cast<const float4*>(sx + jj + 4 * v);
+      yj4[v] = *reinterpret_cast<const float4*>(sy + jj + 4 * v);
+      zj4[v] = *reinterpret_cast<const float4*>(sz + jj + 4 * v);
+    }
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float2 xj = h ? make_float2(xj4[v].z, xj4[v].w) : make_float2(xj4[v].x, xj4[v].y);
+        const float2 yj = h ? make_float2(yj4[v].z, yj4[v].w) : make_float2(yj4[v].x, yj4[v].y);
+        const float2 zj = h ? make_float2(zj4[v].z, zj4[v].w) : make_float2(zj4[v].x, zj4[v].y);
+        const float2 dx = __fadd2_rn(xj, nx);
+        const float2 dy = __fadd2_rn(yj, ny);
+        const float2 dz = __fadd2_rn(zj, nz);
+        const float2 qx = __fadd2_rn(__ffma2_rn(dx, dup2(c.invLx), magic2), nmagic2);
+        const float2 qy = __fadd2_rn(__ffma2_rn(dy, dup2(c.invLy), magic2), nmagic2);
+        const float2 qz = __fadd2_rn(__ffma2_rn(dz, dup2(c.invLz), magic2), nmagic2);
+        const float2 rx = __ffma2_rn(qx, dup2(c.nLx), dx);
+        const float2 ry = __ffma2_rn(qy, dup2(c.nLy), dy);
+        const float2 rz = __ffma2_rn(qz, dup2(c.nLz), dz);
+        const float2 xx = __fmul2_rn(rx, rx);
+        const float2 yy = __fmul2_rn(ry, ry);
+        const float2 zz = __fmul2_rn(rz, rz);
+        const float2 d2 = __ffma2_rn(zz, one2, __ffma2_rn(xx, one2, yy));
+        bin_two_c(d2, c.clamp2, inv_step4, magic_thr, c.cnt_delta);
       }
     }
   }
@@ -550,7 +643,7 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
   const float2 nLy = make_float2(-P.box[1], -P.box[1]);
   const float2 nLz = make_float2(-P.box[2], -P.box[2]);
   const GeoConst geo = {P.inv_box[0], P.inv_box[1], P.inv_box[2], -P.box[0], -P.box[1],
-                        -P.box[2], inv_step, cut2, P.onef, P.box[0], P.box[1], P.box[2], thr_c,
+                        -P.box[2], inv_step, cut2, P.onef, P.box[0], P.box[1], P.box[2], P.clamp2, thr_c,
                         cnt_delta, one, dump, thr_s, cnt_s, dump_off};
 
   for (;;) {
@@ -752,12 +845,22 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
                 by[r] = __shfl_sync(0xffffffffu, shy, q * R + r);
                 bz[r] = __shfl_sync(0xffffffffu, shz, q * R + r);
               }
-              if (mu == FULL)
-                sub_tile_uni<false, R, 2>(mu, sx, sy, sz, q * SUB, nxi, nyi, nzi, bx, by, bz, geo);
-              else
-                sub_tile_uni<true, R, 2>(mu, sx, sy, sz, q * SUB, nxi, nyi, nzi, bx, by, bz, geo);
+              if (mu == FULL) {
+                sub_tile_uni<R>(sx, sy, sz, q * SUB, nxi, nyi, nzi, bx, by, bz, geo);
+              } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                  if ((mu >> r) & 1u)  // warp-uniform
+                    sub_tile_uni_row(sx, sy, sz, q * SUB, nxi[r], nyi[r], nzi[r], bx[r], by[r],
+                                     bz[r], geo);
+              }
             }
-            if (mm != 0u) sub_tile<true, R, AM, 2>(mm, sx, sy, sz, q * SUB, nxi, nyi, nzi, geo);
+            if (mm != 0u) {
+#pragma unroll
+              for (int r = 0; r < R; ++r)
+                if ((mm >> r) & 1u)  // warp-uniform
+                  sub_tile_gen_row(sx, sy, sz, q * SUB, nxi[r], nyi[r], nzi[r], geo);
+            }
           } else if (!CULL || m == FULL)
             sub_tile<false, R, AM, (CULL ? 2 : 4)>(m, sx, sy, sz, q * SUB, nxi, nyi, nzi, geo);
           else if (m != 0u)
@@ -1075,6 +1178,11 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
   P.cut2 = cut2;
   P.inv_step = static_cast<float>(static_cast<double>(nbins) / static_cast<double>(cutoff));
   P.nbins = nbins;
+  {
+    const double mid = (static_cast<double>(nbins) + 0.5) * static_cast<double>(cutoff) /
+                       static_cast<double>(nbins);
+    P.clamp2 = static_cast<float>(mid * mid);
+  }
   P.thr = thr;
   P.hist = hist;
   P.counter = reinterpret_cast<unsigned long long*>(work_counter);

@@ -597,6 +597,7 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tile + 2 * 3 * TJ); // full[2], empty[2]
   uint64_t* s_ebar = s_bar + 2;
   unsigned long long* s_item = reinterpret_cast<unsigned long long*>(s_bar + 4);
+  unsigned int* s_rel = reinterpret_cast<unsigned int*>(s_item + 1);  // warps done, per stage
   float* s_thr = reinterpret_cast<float*>(s_item + 2);
   const int thr_len = (P.nbins + 1 + 3) & ~3;
   unsigned int* s_cnt = reinterpret_cast<unsigned int*>(s_thr + thr_len);
@@ -614,13 +615,15 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
     mbar_init(&s_bar[1], 1);
     mbar_init(&s_ebar[0], NT / 32);  // one arrival per warp
     mbar_init(&s_ebar[1], NT / 32);
+    s_rel[0] = 0u;
+    s_rel[1] = 0u;
     fence_mbar_init();
   }
   __syncthreads();
 
-  uint32_t phase[2] = {0u, 0u};
-  // "stage is free" barriers: waiting on parity 1 of a fresh barrier returns at once
-  uint32_t ephase[2] = {1u, 1u};
+  uint32_t phase = 0u;   // bit s: parity to wait for on the full barrier of stage s
+  // "stage is free" barriers: one phase per tile and stage (NT / 32 arrivals)
+  uint32_t ephase = 0u;  // bit s: same for the empty barrier
   int cur_pair = -1;
   unsigned int tiles_since_flush = 0;
 
@@ -762,23 +765,19 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
     int jn = next_live(jt + 1);
     // Column tiles flow through a two-stage ring.  Warps are NOT block-synchronised per tile:
     // a warp signals "done with this stage" on the stage's empty barrier and moves on to the
-    // next tile as soon as its data has landed; only warp 0, which refills a stage, waits for
-    // all warps to have released it.  With block culling the work per (warp, tile) varies, and
-    // a per-tile __syncthreads made every warp wait for the slowest one.
-    if (tid < 32) {
-      mbar_wait(&s_ebar[0], ephase[0]);
-      if (tid == 0) issue(jt, 0);
-      if (jn < j_tile1) {
-        mbar_wait(&s_ebar[1], ephase[1]);
-        if (tid == 0) issue(jn, 1);
-      }
+    // next tile as soon as its data has landed.  The LAST warp to release a stage (elected by a
+    // shared-memory counter) refills it, so no warp ever blocks on the others: with block
+    // culling the work per (warp, tile) varies, a per-tile __syncthreads made every warp wait
+    // for the slowest one, and a fixed producer warp stalled itself on the empty barrier (6 % of
+    // the warp time in the round-1 profile).  Both stages are free here (block sync above).
+    if (tid == 0) {
+      issue(jt, 0);
+      if (jn < j_tile1) issue(jn, 1);
     }
-    ephase[0] ^= 1u;
-    if (jn < j_tile1) ephase[1] ^= 1u;
 
     for (int stage = 0; jt < j_tile1; stage ^= 1) {
-      mbar_wait(&s_bar[stage], phase[stage]);
-      phase[stage] ^= 1u;
+      mbar_wait(&s_bar[stage], (phase >> stage) & 1u);
+      phase ^= 1u << stage;
       const float* __restrict__ sx = s_tile + stage * 3 * TJ;
       const float* __restrict__ sy = sx + TJ;
       const float* __restrict__ sz = sy + TJ;
@@ -899,15 +898,18 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
         }
       }
       __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(&s_ebar[stage]);  // this warp is done reading the stage
       const int jnn = jn < j_tile1 ? next_live(jn + 1) : j_tile1;
-      if (jnn < j_tile1) {
-        if (tid < 32) {
-          mbar_wait(&s_ebar[stage], ephase[stage]);
-          if (tid == 0) issue(jnn, stage);
+      if ((tid & 31) == 0) {
+        mbar_arrive(&s_ebar[stage]);  // this warp is done reading the stage
+        if (atomicAdd(&s_rel[stage], 1u) == NT / 32 - 1) {  // last warp out: refill the stage
+          s_rel[stage] = 0u;
+          if (jnn < j_tile1) {
+            mbar_wait(&s_ebar[stage], (ephase >> stage) & 1u);  // completes at once (acquire)
+            issue(jnn, stage);
+          }
         }
-        ephase[stage] ^= 1u;
       }
+      ephase ^= 1u << stage;  // one phase of the empty barrier per tile and stage
       jt = jn;
       jn = jnn;
       if (!GLOBAL_HIST && ++tiles_since_flush >= P.flush_tiles) {

@@ -95,13 +95,18 @@ msd_windowed_kernel(const float* __restrict__ traj, long long T, long long a_lo,
 // reference's default data_range is 100) still fill the CTA: group g sweeps its own slice of the
 // window chunk.  The lane stride is R = 9 positions: odd, hence bank-conflict free (a skewed
 // index for R = 8 was measured slower).
-// Differences and squares run on FADD2/FFMA2 for {x,y} and FADD/FFMA for z; fp32 partial sums
-// over MD_FOLD * R origins are folded into fp64.
+// Two atoms are swept together: differences and squares run on FADD2/FFMA2 for {xA,yA},
+// {xB,yB} and {zA,zB} -- six packed instructions for two updates (a scalar FADD/FFMA on z costs
+// the same pipe slot as a packed one); fp32 partial sums over MD_FOLD * R origins of both atoms
+// are folded into fp64.
 constexpr int MD_NT = 64;
-constexpr int MD_FOLD = 3;  // outer iterations (of R origins) between fp64 folds
+constexpr int MD_FOLD = 3;   // outer iterations (of R origins) between fp64 folds
+constexpr int MD2_FOLD = 2;  // same for the two-atom kernel (twice the terms per iteration)
 
 constexpr int MD_R = 9;  // odd: the lane stride of MD_R positions is bank-conflict free
 
+// msd_dense_kernel: one atom per sweep ({x,y} packed, z scalar) -- kept for short lag ranges, where
+// window groups split the CTA and the two-atom variant below needs too many registers.
 template <bool GROUPS>
 __global__ void __launch_bounds__(MD_NT)
 msd_dense_kernel(const float* __restrict__ traj, long long T, long long a_lo, long long a_hi,
@@ -213,6 +218,144 @@ msd_dense_kernel(const float* __restrict__ traj, long long T, long long a_lo, lo
     }
 #pragma unroll
     for (int b = 0; b < R; ++b) acc64[b] += (double)((axy[b].x + axy[b].y) + az[b]);
+  }
+  if (active) {
+#pragma unroll
+    for (int b = 0; b < R; ++b) {
+      const int lag = lag_blk0 + kR + b;
+      if (kR + b < lags_here && lag < n_lags) atomicAdd(msd_sum + lag, acc64[b]);
+    }
+  }
+}
+
+// msd_dense2_kernel: two atoms per sweep, z components packed (lag ranges that fill the CTA).
+
+template <bool GROUPS>
+__global__ void __launch_bounds__(MD_NT)
+msd_dense2_kernel(const float* __restrict__ traj, long long T, long long a_lo, long long a_hi,
+                 int atoms_per_cta, long long t0, int W, int n_lags, int Wc, int len_alloc,
+                 double* __restrict__ msd_sum) {
+  constexpr int R = MD_R;
+  extern __shared__ __align__(16) float md_smem[];
+  // Two atoms (A, B) are swept together so that their z components share packed instructions:
+  // layout xyA (float2 x len_alloc) | xyB | zAB (float2 {zA, zB} x len_alloc) | origin copies
+  // for lag blocks > 0 (same three arrays, Wc entries each)
+  float2* s_xyA = reinterpret_cast<float2*>(md_smem);
+  float2* s_xyB = s_xyA + len_alloc;
+  float2* s_z2 = s_xyB + len_alloc;
+  float2* s_oA = s_z2 + len_alloc;
+  float2* s_oB = s_oA + Wc;
+  float2* s_oz = s_oB + Wc;
+  const int tid = threadIdx.x;
+  const int w0 = blockIdx.x * Wc;
+  const int w1 = min(W, w0 + Wc);
+  if (w0 >= w1) return;
+  const int nw = w1 - w0;
+  const int lag_blk0 = blockIdx.z * MD_NT * R;
+  const int lags_here = min(n_lags - lag_blk0, MD_NT * R);
+  // GROUPS: G lag-threads x NG window groups; otherwise every thread is a lag-thread and sweeps
+  // the whole window chunk (the lag range fills the CTA)
+  const int G = GROUPS ? (lags_here + R - 1) / R : MD_NT;
+  const int NG = GROUPS ? MD_NT / G : 1;
+  const int k = GROUPS ? tid % G : tid, wg = GROUPS ? tid / G : 0;
+  const bool active = wg < NG;
+  const int nwg = GROUPS ? (nw + NG - 1) / NG : nw;  // origins per group
+  const int ws_lo = GROUPS ? min(wg * nwg, nw) : 0;
+  const int ws_hi = GROUPS ? (active ? min(nw, ws_lo + nwg) : ws_lo) : nw;
+  const int len = nw + lags_here - 1;             // frames staged per atom
+  const long long t_begin = t0 + w0 + lag_blk0;   // slab index 0 <-> this frame
+  const long long a0 = a_lo + (long long)blockIdx.y * atoms_per_cta;
+  const long long a1 = min(a_hi, a0 + atoms_per_cta);
+  const int kR = k * R;
+
+  double acc64[R];
+#pragma unroll
+  for (int b = 0; b < R; ++b) acc64[b] = 0.0;
+
+  for (long long a = a0; a < a1; a += 2) {
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      // atom B of an odd tail is staged as zeros: every difference is 0 and adds nothing
+      const bool have = a + h < a1;
+      const float* __restrict__ row = traj + (size_t)(a + (have ? h : 0)) * T * 3;
+      float* __restrict__ dxy = reinterpret_cast<float*>(h ? s_xyB : s_xyA);
+      float* __restrict__ dz = reinterpret_cast<float*>(s_z2) + h;
+      const float* __restrict__ src = row + (size_t)t_begin * 3;
+      for (int e = tid; e < 3 * len; e += MD_NT) {
+        const float v = have ? __ldg(src + e) : 0.f;
+        const int t = e / 3, d = e - 3 * t;
+        if (d < 2) dxy[2 * t + d] = v; else dz[2 * t] = v;
+      }
+      if (lag_blk0 > 0) {
+        float* __restrict__ oxy = reinterpret_cast<float*>(h ? s_oB : s_oA);
+        float* __restrict__ oz = reinterpret_cast<float*>(s_oz) + h;
+        const float* __restrict__ so = row + (size_t)(t0 + w0) * 3;
+        for (int e = tid; e < 3 * nw; e += MD_NT) {
+          const float v = have ? __ldg(so + e) : 0.f;
+          const int t = e / 3, d = e - 3 * t;
+          if (d < 2) oxy[2 * t + d] = v; else oz[2 * t] = v;
+        }
+      }
+    }
+    __syncthreads();
+    const float2* __restrict__ o_A = lag_blk0 > 0 ? s_oA : s_xyA;
+    const float2* __restrict__ o_B = lag_blk0 > 0 ? s_oB : s_xyB;
+    const float2* __restrict__ o_z = lag_blk0 > 0 ? s_oz : s_z2;
+
+    float2 qA[R], qB[R], qz[R];
+#pragma unroll
+    for (int b = 0; b < R; ++b) {
+      const int p = min(ws_lo + kR + b, len_alloc - 1);
+      qA[b] = s_xyA[p];
+      qB[b] = s_xyB[p];
+      qz[b] = s_z2[p];
+    }
+    float2 axy[R], az[R];
+#pragma unroll
+    for (int b = 0; b < R; ++b) {
+      axy[b] = make_float2(0.f, 0.f);
+      az[b] = make_float2(0.f, 0.f);
+    }
+    int fold = 0;
+    for (int w = ws_lo; w < ws_lo + nwg; w += R) {
+#pragma unroll
+      for (int s = 0; s < R; ++s) {
+        const int ws = w + s;
+        if (ws < ws_hi) {
+          const float2 oA = o_A[ws], oB = o_B[ws], oz = o_z[ws];
+          const float2 noA = make_float2(-oA.x, -oA.y);
+          const float2 noB = make_float2(-oB.x, -oB.y);
+          const float2 noz = make_float2(-oz.x, -oz.y);
+#pragma unroll
+          for (int b = 0; b < R; ++b) {
+            const int slot = (s + b) % R;
+            const float2 dA = __fadd2_rn(qA[slot], noA);
+            const float2 dB = __fadd2_rn(qB[slot], noB);
+            const float2 dz = __fadd2_rn(qz[slot], noz);
+            axy[b] = __ffma2_rn(dA, dA, axy[b]);
+            az[b] = __ffma2_rn(dz, dz, az[b]);
+            axy[b] = __ffma2_rn(dB, dB, axy[b]);
+          }
+          // slot s held frame ws + lag: dead now; refill with frame ws + lag + R
+          const int nx = min(ws + kR + R, len_alloc - 1);
+          qA[s] = s_xyA[nx];
+          qB[s] = s_xyB[nx];
+          qz[s] = s_z2[nx];
+        }
+      }
+      if (++fold == MD2_FOLD) {
+        fold = 0;
+#pragma unroll
+        for (int b = 0; b < R; ++b) {
+          acc64[b] += (double)((axy[b].x + axy[b].y) + (az[b].x + az[b].y));
+          axy[b] = make_float2(0.f, 0.f);
+          az[b] = make_float2(0.f, 0.f);
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < R; ++b) acc64[b] += (double)((axy[b].x + axy[b].y) + (az[b].x + az[b].y));
   }
   if (active) {
 #pragma unroll
@@ -788,7 +931,9 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
   const int wc_max = grouped ? 4096 - lag_alloc : 512;
   const int Wc = W < wc_max ? W : wc_max;
   const int len_alloc = (Wc + lag_alloc + 3) & ~3;  // multiple of 4: float2 views stay aligned
-  const size_t smem = ((size_t)3 * len_alloc + (lag_blocks > 1 ? (size_t)3 * Wc : 0)) * sizeof(float);
+  // the two-atom kernel stages two atoms per sweep
+  const size_t smem = ((size_t)(grouped ? 3 : 6) * len_alloc +
+                       (lag_blocks > 1 ? (size_t)6 * Wc : 0)) * sizeof(float);
   const int chunks = (W + Wc - 1) / Wc;
   // 64-thread CTAs: aim for several waves of ~11 resident CTAs per SM
   const int apc = pick_atoms_per_cta(a_hi - a_lo, (long long)chunks * lag_blocks, 48);
@@ -801,9 +946,9 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
     msd_dense_kernel<true><<<grid, MD_NT, smem, as_stream(stream)>>>(
         traj, T, a_lo, a_hi, apc, t0, W, n_lags, Wc, len_alloc, msd_sum);
   } else {
-    MDK_CUDA(cudaFuncSetAttribute(msd_dense_kernel<false>,
+    MDK_CUDA(cudaFuncSetAttribute(msd_dense2_kernel<false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    msd_dense_kernel<false><<<grid, MD_NT, smem, as_stream(stream)>>>(
+    msd_dense2_kernel<false><<<grid, MD_NT, smem, as_stream(stream)>>>(
         traj, T, a_lo, a_hi, apc, t0, W, n_lags, Wc, len_alloc, msd_sum);
   }
   MDK_LAUNCH_CHECK();

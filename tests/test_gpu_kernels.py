@@ -177,6 +177,32 @@ def test_rdf_culling_is_exact_at_scale(cuda, cutoff_frac, tuning):
     assert a.sum() > 0 and np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("wrapped", [True, False])
+def test_rdf_uniform_image_two_species_orthorhombic(cuda, wrapped):
+    """Size-independent property at a scale where the uniform-image kernel (AM 7) is the
+    default: two species of unequal, ragged size in a non-cubic box -- the sorted, culled pass
+    returns exactly the histogram of the plain all-pairs pass (all three species pairs, diagonal
+    tiles included), for wrapped coordinates and for coordinates spread over two box images."""
+    import torch
+    from lammps_analysis_b200.engine import RdfEngine
+
+    gen = torch.Generator(device=cuda)
+    gen.manual_seed(77)
+    box = np.array([150.0, 131.0, 118.5])
+    counts = [70_001, 40_963]
+    lo, span = (0.0, 1.0) if wrapped else (-0.7, 2.1)
+    trajs = [((torch.rand(n, 1, 3, device=cuda, generator=gen) * span + lo)
+              * torch.tensor(box, dtype=torch.float32, device=cuda)).contiguous() for n in counts]
+    cutoff, nbins = 58.0, 5800
+    plain = RdfEngine(counts, box, cutoff, nbins, device=cuda, spatial_sort=False)
+    plain.add_frames(trajs, np.arange(1))
+    culled = RdfEngine(counts, box, cutoff, nbins, device=cuda, spatial_sort=True)
+    culled.add_frames(trajs, np.arange(1))
+    a, b = plain.counts(), culled.counts()
+    assert a.shape[0] == 3 and all(a[p].sum() > 0 for p in range(3))
+    assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("tuning", [0, 0x3000, 0x8400])
 def test_rdf_culling_with_unwrapped_coordinates(cuda, tuning):
     """Coordinates spread over several box images: the box test must stay conservative, and the

@@ -154,7 +154,7 @@ __device__ __forceinline__ void bin_two(float2 d2, float cut2, float2 inv_step2,
 #define MDK_BIN_HEAD                                   \
   "{\n"                                                \
   ".reg .pred p0, q0, p1, q1;\n"                       \
-  ".reg .f32 e0, e1, t0, t1, g0, g1;\n"                \
+  ".reg .f32 e0, e1, t0, t1;\n"                        \
   ".reg .b64 ee, tt;\n"                                \
   ".reg .u32 a0, a1, b0, b1;\n"                        \
   "setp.lt.f32 p0, %0, %2;\n"                          \
@@ -168,10 +168,10 @@ __device__ __forceinline__ void bin_two(float2 d2, float cut2, float2 inv_step2,
   "mov.b32 b1, t1;\n"                                  \
   "mad.lo.u32 a0, b0, 4, %5;\n"                        \
   "mad.lo.u32 a1, b1, 4, %5;\n"                        \
-  "@p0 ld.shared.f32 g0, [a0];\n"                      \
-  "@p1 ld.shared.f32 g1, [a1];\n"                      \
-  "setp.lt.f32 q0, %0, g0;\n"                          \
-  "setp.lt.f32 q1, %1, g1;\n"                          \
+  "@p0 ld.shared.f32 e0, [a0];\n"                      \
+  "@p1 ld.shared.f32 e1, [a1];\n"                      \
+  "setp.lt.f32 q0, %0, e0;\n"                          \
+  "setp.lt.f32 q1, %1, e1;\n"                          \
   "@q0 add.u32 a0, a0, -4;\n"                          \
   "@q1 add.u32 a1, a1, -4;\n"
 #define MDK_BIN_ARGS                                                                        \
@@ -269,7 +269,7 @@ __device__ __forceinline__ void bin_two_q(float2 d2, float cut2, float2 inv_step
   asm volatile(
       "{\n"
       ".reg .pred p0, p1, m0, m1, q0, q1;\n"
-      ".reg .f32 e0, e1, t0, t1, g0, g1;\n"
+      ".reg .f32 e0, e1, t0, t1;\n"
       ".reg .b64 ee, tt;\n"
       ".reg .u32 a0, a1, b0, b1, f0, f1, u0, u1;\n"
       "setp.lt.f32 p0, %0, %2;\n"
@@ -289,10 +289,10 @@ __device__ __forceinline__ void bin_two_q(float2 d2, float cut2, float2 inv_step
       "setp.eq.and.u32 m1, f1, 0, p1;\n"
       "add.u32 u0, a0, %5;\n"
       "add.u32 u1, a1, %5;\n"
-      "@m0 ld.shared.f32 g0, [u0];\n"
-      "@m1 ld.shared.f32 g1, [u1];\n"
-      "setp.lt.and.f32 q0, %0, g0, m0;\n"
-      "setp.lt.and.f32 q1, %1, g1, m1;\n"
+      "@m0 ld.shared.f32 e0, [u0];\n"
+      "@m1 ld.shared.f32 e1, [u1];\n"
+      "setp.lt.and.f32 q0, %0, e0, m0;\n"
+      "setp.lt.and.f32 q1, %1, e1, m1;\n"
       "@q0 add.u32 a0, a0, -4;\n"
       "@q1 add.u32 a1, a1, -4;\n"
       "selp.u32 a0, a0, %7, p0;\n"
@@ -326,7 +326,7 @@ __device__ __forceinline__ void bin_two_c(float2 d2, float clamp2, float2 inv_st
   asm volatile(
       "{\n"
       ".reg .pred m0, m1, q0, q1;\n"
-      ".reg .f32 c0, c1, e0, e1, t0, t1, g0, g1;\n"
+      ".reg .f32 c0, c1, e0, e1, t0, t1;\n"
       ".reg .b64 ee, tt;\n"
       ".reg .u32 a0, a1, b0, b1, f0, f1;\n"
       "min.f32 c0, %0, %2;\n"
@@ -344,10 +344,10 @@ __device__ __forceinline__ void bin_two_c(float2 d2, float clamp2, float2 inv_st
       "and.b32 f1, b1, 3;\n"
       "setp.eq.u32 m0, f0, 0;\n"
       "setp.eq.u32 m1, f1, 0;\n"
-      "@m0 ld.shared.f32 g0, [a0];\n"
-      "@m1 ld.shared.f32 g1, [a1];\n"
-      "setp.lt.and.f32 q0, c0, g0, m0;\n"
-      "setp.lt.and.f32 q1, c1, g1, m1;\n"
+      "@m0 ld.shared.f32 e0, [a0];\n"  // into the (dead) sqrt register: a fresh destination
+      "@m1 ld.shared.f32 e1, [a1];\n"  // of a predicated load would be loop-carried
+      "setp.lt.and.f32 q0, c0, e0, m0;\n"
+      "setp.lt.and.f32 q1, c1, e1, m1;\n"
       "@q0 add.u32 a0, a0, -4;\n"
       "@q1 add.u32 a1, a1, -4;\n"
       "add.u32 a0, a0, %5;\n"
@@ -463,7 +463,7 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
 // component and pair couple instead of FFMA2 + FADD2 + FFMA2 (or FADD2 + 2 FMNMX for wrapped
 // coordinates).  The block classification is done once per column tile by 16 lanes in parallel
 // (rdf_pair_hist_kernel); blocks that straddle a half-box boundary take the general path.
-template <int R>
+template <int R, bool SHIFT>
 __device__ __forceinline__ void sub_tile_uni(const float* __restrict__ sx,
                                              const float* __restrict__ sy,
                                              const float* __restrict__ sz, int jj0,
@@ -487,9 +487,15 @@ __device__ __forceinline__ void sub_tile_uni(const float* __restrict__ sx,
       const float2 zj = h ? make_float2(zj4.z, zj4.w) : make_float2(zj4.x, zj4.y);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const float2 rx = __fadd2_rn(__fadd2_rn(xj, nxi[r]), dup2(shx[r]));
-        const float2 ry = __fadd2_rn(__fadd2_rn(yj, nyi[r]), dup2(shy[r]));
-        const float2 rz = __fadd2_rn(__fadd2_rn(zj, nzi[r]), dup2(shz[r]));
+        // SHIFT == false: no pair of the block crosses a periodic boundary (all shifts are 0)
+        float2 rx = __fadd2_rn(xj, nxi[r]);
+        float2 ry = __fadd2_rn(yj, nyi[r]);
+        float2 rz = __fadd2_rn(zj, nzi[r]);
+        if (SHIFT) {
+          rx = __fadd2_rn(rx, dup2(shx[r]));
+          ry = __fadd2_rn(ry, dup2(shy[r]));
+          rz = __fadd2_rn(rz, dup2(shz[r]));
+        }
         const float2 xx = __fmul2_rn(rx, rx);
         const float2 yy = __fmul2_rn(ry, ry);
         const float2 zz = __fmul2_rn(rz, rz);
@@ -503,6 +509,7 @@ __device__ __forceinline__ void sub_tile_uni(const float* __restrict__ sx,
 // One row group of the warp against a 64-atom column sub-tile (partially live blocks): eight
 // columns per trip keep four independent pair couples in flight; no per-row-group branches in
 // the column loop.
+template <bool SHIFT>
 __device__ __forceinline__ void sub_tile_uni_row(const float* __restrict__ sx,
                                                  const float* __restrict__ sy,
                                                  const float* __restrict__ sz, int jj0,
@@ -527,9 +534,14 @@ __device__ __forceinline__ void sub_tile_uni_row(const float* __restrict__ sx,
         const float2 xj = h ? make_float2(xj4[v].z, xj4[v].w) : make_float2(xj4[v].x, xj4[v].y);
         const float2 yj = h ? make_float2(yj4[v].z, yj4[v].w) : make_float2(yj4[v].x, yj4[v].y);
         const float2 zj = h ? make_float2(zj4[v].z, zj4[v].w) : make_float2(zj4[v].x, zj4[v].y);
-        const float2 rx = __fadd2_rn(__fadd2_rn(xj, nx), dup2(shx));
-        const float2 ry = __fadd2_rn(__fadd2_rn(yj, ny), dup2(shy));
-        const float2 rz = __fadd2_rn(__fadd2_rn(zj, nz), dup2(shz));
+        float2 rx = __fadd2_rn(xj, nx);
+        float2 ry = __fadd2_rn(yj, ny);
+        float2 rz = __fadd2_rn(zj, nz);
+        if (SHIFT) {
+          rx = __fadd2_rn(rx, dup2(shx));
+          ry = __fadd2_rn(ry, dup2(shy));
+          rz = __fadd2_rn(rz, dup2(shz));
+        }
         const float2 xx = __fmul2_rn(rx, rx);
         const float2 yy = __fmul2_rn(ry, ry);
         const float2 zz = __fmul2_rn(rz, rz);
@@ -591,14 +603,15 @@ template <int NT, int R, bool EXACT, int AM, bool CULL>
 __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_kernel(const __grid_constant__ RdfParams P) {
   constexpr int TI = NT * R;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: [stage0 xyz | stage1 xyz | mbar x2 | item | thr (nbins+1) | cnt (nbins, padded
-  // to 32) | 32 dump slots]
+  // layout: [stage0 xyz | stage1 xyz | mbar x4 | item, release counters | row-tile box |
+  // thr (nbins+1) | cnt (nbins, padded to 32) | 32 dump slots]
   float* s_tile = reinterpret_cast<float*>(smem_raw);                 // 2 * 3 * TJ floats
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tile + 2 * 3 * TJ); // full[2], empty[2]
   uint64_t* s_ebar = s_bar + 2;
   unsigned long long* s_item = reinterpret_cast<unsigned long long*>(s_bar + 4);
   unsigned int* s_rel = reinterpret_cast<unsigned int*>(s_item + 1);  // warps done, per stage
-  float* s_thr = reinterpret_cast<float*>(s_item + 2);
+  float* s_rbox = reinterpret_cast<float*>(s_item + 2);               // row-tile box (8 floats)
+  float* s_thr = reinterpret_cast<float*>(s_item + 6);
   const int thr_len = (P.nbins + 1 + 3) & ~3;
   unsigned int* s_cnt = reinterpret_cast<unsigned int*>(s_thr + thr_len);
 
@@ -681,24 +694,20 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
     }
 
     const float* __restrict__ fx = P.pos + (size_t)f * 3 * P.n_pad;
-    const float* __restrict__ fy = fx + P.n_pad;
-    const float* __restrict__ fz = fy + P.n_pad;
 
     // ---- row atoms -> registers (negated, duplicated) -----------------------------------
     const int row_base = P.sp_lo[a] + I * TI;
     float2 nxi[R], nyi[R], nzi[R];
-    int irow[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       // the R row groups of a warp come from R different 256-row regions of the tile: their
       // culling masks differ, which balances the live work across the warps of the CTA
       const int i = row_base + r * NT + tid;
-      irow[r] = i;
       float x = __int_as_float(0x7fc00000), y = x, z = x;  // NaN rows never pass d2 < cut2
       if (i < P.sp_hi[a]) {
         x = __ldg(fx + i);
-        y = __ldg(fy + i);
-        z = __ldg(fz + i);
+        y = __ldg(fx + P.n_pad + i);
+        z = __ldg(fx + 2 * P.n_pad + i);
       }
       nxi[r] = make_float2(-x, -x);
       nyi[r] = make_float2(-y, -y);
@@ -713,6 +722,12 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
     if constexpr (CULL) {
       const int r_last = min(row_base + TI, P.sp_hi[a]);  // exclusive row bound
       for (int t = row_base / SUB; t * SUB < r_last; ++t) box_union(rbox, fbox + (size_t)t * 6);
+      // the row-tile box is the same for every thread: park it in shared memory (all threads
+      // store identical values; every warp reads what it, or another warp, wrote) so that it
+      // does not occupy six registers across the pair loops
+#pragma unroll
+      for (int d = 0; d < 6; ++d) s_rbox[d] = rbox[d];
+      __syncwarp();
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const float c[3] = {-nxi[r].x, -nyi[r].x, -nzi[r].x};
@@ -742,7 +757,10 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
       float cb6[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int q = 0; q < NSUB; ++q) box_union(cb6, fbox + (size_t)(col_box0 + jt * NSUB + q) * 6);
-      return boxes_far(rbox, cb6, P.box, P.cull_eps, P.cull2);
+      float rb[6];
+#pragma unroll
+      for (int d = 0; d < 6; ++d) rb[d] = s_rbox[d];
+      return boxes_far(rb, cb6, P.box, P.cull_eps, P.cull2);
     };
     auto next_live = [&](int jt) {
       if constexpr (CULL)
@@ -757,8 +775,8 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
       const size_t off = (size_t)col_base + (size_t)jt * TJ;
       mbar_expect_tx(&s_bar[stage], 3u * TJ * sizeof(float));
       bulk_g2s(dst, fx + off, TJ * sizeof(float), &s_bar[stage]);
-      bulk_g2s(dst + TJ, fy + off, TJ * sizeof(float), &s_bar[stage]);
-      bulk_g2s(dst + 2 * TJ, fz + off, TJ * sizeof(float), &s_bar[stage]);
+      bulk_g2s(dst + TJ, fx + P.n_pad + off, TJ * sizeof(float), &s_bar[stage]);
+      bulk_g2s(dst + 2 * TJ, fx + 2 * P.n_pad + off, TJ * sizeof(float), &s_bar[stage]);
     };
     int jt = next_live(j_tile0);
     if (jt >= j_tile1) continue;  // every column tile of this item is out of range
@@ -787,6 +805,7 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
       // which of this warp's row groups can reach which 64-atom sub-tile: bit (q * R + r)
       unsigned rmask = 0xffffffffu;
       unsigned umask = 0u;             // AM 7: blocks with a uniform periodic image
+      unsigned smask = 0u;             // AM 7: ... whose image shift is not zero
       float shx = 0.f, shy = 0.f, shz = 0.f;  // AM 7: image shift of block (lane & 15)
       if constexpr (AM == 7) {
         static_assert(AM != 7 || (R == 4 && NSUB == 4 && CULL), "AM 7 needs 4 x 4 blocks per tile");
@@ -816,6 +835,7 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
           shz = sh[2];
           rmask = __ballot_sync(0xffffffffu, live) & 0xffffu;
           umask = __ballot_sync(0xffffffffu, uni) & 0xffffu;
+          smask = __ballot_sync(0xffffffffu, shx != 0.f || shy != 0.f || shz != 0.f) & umask;
         }
       } else if (CULL && !diag) {
         rmask = 0u;
@@ -836,7 +856,13 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
           if constexpr (AM == 7) {
             const unsigned mu = (umask >> (q * R)) & FULL;
             const unsigned mm = m & ~mu;
-            if (mu != 0u) {
+            // adding a zero shift is exact, so skipping it changes nothing: fully live blocks
+            // that do not cross a periodic boundary (about half of them) save three FADD2 of the
+            // 28 instructions per pair couple
+            if (mu == FULL && ((smask >> (q * R)) & FULL) == 0u) {
+              const float zero[R] = {0.f, 0.f, 0.f, 0.f};
+              sub_tile_uni<R, false>(sx, sy, sz, q * SUB, nxi, nyi, nzi, zero, zero, zero, geo);
+            } else if (mu != 0u) {
               float bx[R], by[R], bz[R];
 #pragma unroll
               for (int r = 0; r < R; ++r) {
@@ -845,13 +871,13 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
                 bz[r] = __shfl_sync(0xffffffffu, shz, q * R + r);
               }
               if (mu == FULL) {
-                sub_tile_uni<R>(sx, sy, sz, q * SUB, nxi, nyi, nzi, bx, by, bz, geo);
+                sub_tile_uni<R, true>(sx, sy, sz, q * SUB, nxi, nyi, nzi, bx, by, bz, geo);
               } else {
 #pragma unroll
                 for (int r = 0; r < R; ++r)
                   if ((mu >> r) & 1u)  // warp-uniform
-                    sub_tile_uni_row(sx, sy, sz, q * SUB, nxi[r], nyi[r], nzi[r], bx[r], by[r],
-                                     bz[r], geo);
+                    sub_tile_uni_row<true>(sx, sy, sz, q * SUB, nxi[r], nyi[r], nzi[r], bx[r],
+                                           by[r], bz[r], geo);
               }
             }
             if (mm != 0u) {
@@ -889,7 +915,7 @@ __global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_ker
             }
             const float d2 =
                 __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
-            const bool ok = (d2 < cut2) && (!same || !diag || j > irow[r]);
+            const bool ok = (d2 < cut2) && (!same || !diag || j > row_base + r * NT + tid);
             if (GLOBAL_HIST)
               bin_one_global(d2, ok, P.thr, P.hist + (size_t)cur_pair * P.nbins, inv_step);
             else
@@ -1190,7 +1216,7 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
   P.counter = reinterpret_cast<unsigned long long*>(work_counter);
 
   const size_t smem = (size_t)2 * 3 * TJ * sizeof(float) + 4 * sizeof(uint64_t) +
-                      2 * sizeof(unsigned long long) +
+                      6 * sizeof(unsigned long long) +
                       (size_t)((nbins + 1 + 3) & ~3) * sizeof(float) +
                       (size_t)(((nbins + 31) & ~31) + 32) * sizeof(unsigned);
   const bool global_hist = smem > 227 * 1024 || ((flags >> 12) & 0xf) == 5;
@@ -1199,7 +1225,7 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
     // threshold table + private histogram do not fit: slow path with both in global memory
     am = 4;
     smem_used = (size_t)2 * 3 * TJ * sizeof(float) + 4 * sizeof(uint64_t) +
-                2 * sizeof(unsigned long long) + 64;
+                6 * sizeof(unsigned long long) + 64;
   }
   // resident CTAs per SM (shared-memory bound) -> persistent grid
   int per_sm = (int)((227 * 1024) / (smem_used + 1024));

@@ -321,43 +321,94 @@ __device__ __forceinline__ void bin_two_q(float2 d2, float cut2, float2 inv_step
 // (magic_thr = 1.5 * 2^23 + &thr[0], an integer below 2^24 and a multiple of 4), so the masked
 // mantissa IS the address of thr[floor-or-carry(t)]; cnt_delta = &cnt[0] - &thr[0] rides in the
 // ATOMS address as a uniform register.
+// BIN_FRAC fraction bits in the guess (2: M = round(4 t), one lane in four gathers its
+// threshold; 3: M = round(8 t), one in eight, at the cost of a shift per pair: measured +0.9 %
+// on the sorted 10^6-atom frame, -5 % on the unsorted 10^5-atom one, which is ALU bound).  The
+// magic constant carries the table address scaled by 2^(BIN_FRAC - 2) (bin_magic()).
+constexpr int BIN_FRAC = 2;
+__device__ __forceinline__ float bin_magic(uint32_t thr_s) {
+  return RINT_MAGIC + static_cast<float>(thr_s << (BIN_FRAC - 2));
+}
+__device__ __forceinline__ float bin_scale(float inv_step) {
+  return static_cast<float>(1 << BIN_FRAC) * inv_step;
+}
 __device__ __forceinline__ void bin_two_c(float2 d2, float clamp2, float2 inv_step4,
                                           float2 magic_thr, uint32_t cnt_delta) {
-  asm volatile(
-      "{\n"
-      ".reg .pred m0, m1, q0, q1;\n"
-      ".reg .f32 c0, c1, e0, e1, t0, t1;\n"
-      ".reg .b64 ee, tt;\n"
-      ".reg .u32 a0, a1, b0, b1, f0, f1;\n"
-      "min.f32 c0, %0, %2;\n"
-      "min.f32 c1, %1, %2;\n"
-      "sqrt.approx.ftz.f32 e0, c0;\n"
-      "sqrt.approx.ftz.f32 e1, c1;\n"
-      "mov.b64 ee, {e0, e1};\n"
-      "fma.rn.f32x2 tt, ee, %3, %4;\n"
-      "mov.b64 {t0, t1}, tt;\n"
-      "mov.b32 b0, t0;\n"
-      "mov.b32 b1, t1;\n"
-      "and.b32 a0, b0, 0x003ffffc;\n"
-      "and.b32 a1, b1, 0x003ffffc;\n"
-      "and.b32 f0, b0, 3;\n"
-      "and.b32 f1, b1, 3;\n"
-      "setp.eq.u32 m0, f0, 0;\n"
-      "setp.eq.u32 m1, f1, 0;\n"
-      "@m0 ld.shared.f32 e0, [a0];\n"  // into the (dead) sqrt register: a fresh destination
-      "@m1 ld.shared.f32 e1, [a1];\n"  // of a predicated load would be loop-carried
-      "setp.lt.and.f32 q0, c0, e0, m0;\n"
-      "setp.lt.and.f32 q1, c1, e1, m1;\n"
-      "@q0 add.u32 a0, a0, -4;\n"
-      "@q1 add.u32 a1, a1, -4;\n"
-      "add.u32 a0, a0, %5;\n"
-      "add.u32 a1, a1, %5;\n"
-      "red.shared.add.u32 [a0], 1;\n"
-      "red.shared.add.u32 [a1], 1;\n"
-      "}\n" ::"f"(d2.x),
-      "f"(d2.y), "f"(clamp2), "l"(*reinterpret_cast<unsigned long long*>(&inv_step4)),
-      "l"(*reinterpret_cast<unsigned long long*>(&magic_thr)), "r"(cnt_delta)
-      : "memory");
+  if (BIN_FRAC == 2) {
+    asm volatile(
+        "{\n"
+        ".reg .pred m0, m1, q0, q1;\n"
+        ".reg .f32 c0, c1, e0, e1, t0, t1;\n"
+        ".reg .b64 ee, tt;\n"
+        ".reg .u32 a0, a1, b0, b1, f0, f1;\n"
+        "min.f32 c0, %0, %2;\n"
+        "min.f32 c1, %1, %2;\n"
+        "sqrt.approx.ftz.f32 e0, c0;\n"
+        "sqrt.approx.ftz.f32 e1, c1;\n"
+        "mov.b64 ee, {e0, e1};\n"
+        "fma.rn.f32x2 tt, ee, %3, %4;\n"
+        "mov.b64 {t0, t1}, tt;\n"
+        "mov.b32 b0, t0;\n"
+        "mov.b32 b1, t1;\n"
+        "and.b32 a0, b0, 0x003ffffc;\n"
+        "and.b32 a1, b1, 0x003ffffc;\n"
+        "and.b32 f0, b0, 3;\n"
+        "and.b32 f1, b1, 3;\n"
+        "setp.eq.u32 m0, f0, 0;\n"
+        "setp.eq.u32 m1, f1, 0;\n"
+        "@m0 ld.shared.f32 e0, [a0];\n"  // into the (dead) sqrt register: a fresh destination
+        "@m1 ld.shared.f32 e1, [a1];\n"  // of a predicated load would be loop-carried
+        "setp.lt.and.f32 q0, c0, e0, m0;\n"
+        "setp.lt.and.f32 q1, c1, e1, m1;\n"
+        "@q0 add.u32 a0, a0, -4;\n"
+        "@q1 add.u32 a1, a1, -4;\n"
+        "add.u32 a0, a0, %5;\n"
+        "add.u32 a1, a1, %5;\n"
+        "red.shared.add.u32 [a0], 1;\n"
+        "red.shared.add.u32 [a1], 1;\n"
+        "}\n" ::"f"(d2.x),
+        "f"(d2.y), "f"(clamp2), "l"(*reinterpret_cast<unsigned long long*>(&inv_step4)),
+        "l"(*reinterpret_cast<unsigned long long*>(&magic_thr)), "r"(cnt_delta)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred m0, m1, q0, q1;\n"
+        ".reg .f32 c0, c1, e0, e1, t0, t1;\n"
+        ".reg .b64 ee, tt;\n"
+        ".reg .u32 a0, a1, b0, b1, f0, f1;\n"
+        "min.f32 c0, %0, %2;\n"
+        "min.f32 c1, %1, %2;\n"
+        "sqrt.approx.ftz.f32 e0, c0;\n"
+        "sqrt.approx.ftz.f32 e1, c1;\n"
+        "mov.b64 ee, {e0, e1};\n"
+        "fma.rn.f32x2 tt, ee, %3, %4;\n"
+        "mov.b64 {t0, t1}, tt;\n"
+        "mov.b32 b0, t0;\n"
+        "mov.b32 b1, t1;\n"
+        "shr.u32 a0, b0, 1;\n"
+        "shr.u32 a1, b1, 1;\n"
+        "and.b32 a0, a0, 0x001ffffc;\n"
+        "and.b32 a1, a1, 0x001ffffc;\n"
+        "and.b32 f0, b0, 7;\n"
+        "and.b32 f1, b1, 7;\n"
+        "setp.eq.u32 m0, f0, 0;\n"
+        "setp.eq.u32 m1, f1, 0;\n"
+        "@m0 ld.shared.f32 e0, [a0];\n"
+        "@m1 ld.shared.f32 e1, [a1];\n"
+        "setp.lt.and.f32 q0, c0, e0, m0;\n"
+        "setp.lt.and.f32 q1, c1, e1, m1;\n"
+        "@q0 add.u32 a0, a0, -4;\n"
+        "@q1 add.u32 a1, a1, -4;\n"
+        "add.u32 a0, a0, %5;\n"
+        "add.u32 a1, a1, %5;\n"
+        "red.shared.add.u32 [a0], 1;\n"
+        "red.shared.add.u32 [a1], 1;\n"
+        "}\n" ::"f"(d2.x),
+        "f"(d2.y), "f"(clamp2), "l"(*reinterpret_cast<unsigned long long*>(&inv_step4)),
+        "l"(*reinterpret_cast<unsigned long long*>(&magic_thr)), "r"(cnt_delta)
+        : "memory");
+  }
 }
 
 // Flush the CTA-private histogram to the global one and clear it.
@@ -394,7 +445,7 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
                                          const float2 (&nzi)[R], const GeoConst& c) {
   constexpr bool WRAP = (AM == 5 || AM == 6 || AM == 8);  // wrapped-coordinate minimum image
   const float2 inv_step4 = dup2(4.0f * c.inv_step);
-  const float2 magic_thr = dup2(RINT_MAGIC + static_cast<float>(c.thr_s));  // see bin_two_c
+  const float2 magic_thr = dup2(bin_magic(c.thr_s));  // see bin_two_c
   const float2 magic2 = dup2(RINT_MAGIC), nmagic2 = dup2(-RINT_MAGIC);
   const float2 inv_step2 = dup2(c.inv_step);
   const float2 one2 = dup2(c.onef);
@@ -447,7 +498,7 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
         else if (AM == 6)
           bin_two_q(d2, c.cut2, inv_step4, c.thr_s, c.cnt_s, c.dump_off);
         else if (AM == 7 || AM == 8)
-          bin_two_c(d2, c.clamp2, inv_step4, magic_thr, c.cnt_delta);
+          bin_two_c(d2, c.clamp2, dup2(bin_scale(c.inv_step)), magic_thr, c.cnt_delta);
         else
           bin_two<(AM >= 3 ? 2 : AM)>(d2, c.cut2, inv_step2, c.thr_c, c.cnt_delta, c.one, c.dump);
       }
@@ -471,8 +522,8 @@ __device__ __forceinline__ void sub_tile_uni(const float* __restrict__ sx,
                                              const float2 (&nzi)[R], const float (&shx)[R],
                                              const float (&shy)[R], const float (&shz)[R],
                                              const GeoConst& c) {
-  const float2 inv_step4 = dup2(4.0f * c.inv_step);
-  const float2 magic_thr = dup2(RINT_MAGIC + static_cast<float>(c.thr_s));  // see bin_two_c
+  const float2 inv_step4 = dup2(bin_scale(c.inv_step));
+  const float2 magic_thr = dup2(bin_magic(c.thr_s));  // see bin_two_c
   const float2 one2 = dup2(c.onef);
 #pragma unroll 1
   for (int jj = jj0; jj < jj0 + SUB; jj += 4) {
@@ -515,8 +566,8 @@ __device__ __forceinline__ void sub_tile_uni_row(const float* __restrict__ sx,
                                                  const float* __restrict__ sz, int jj0,
                                                  float2 nx, float2 ny, float2 nz, float shx,
                                                  float shy, float shz, const GeoConst& c) {
-  const float2 inv_step4 = dup2(4.0f * c.inv_step);
-  const float2 magic_thr = dup2(RINT_MAGIC + static_cast<float>(c.thr_s));
+  const float2 inv_step4 = dup2(bin_scale(c.inv_step));
+  const float2 magic_thr = dup2(bin_magic(c.thr_s));
   const float2 one2 = dup2(c.onef);
 #pragma unroll 1
   for (int jj = jj0; jj < jj0 + SUB; jj += 8) {
@@ -559,8 +610,8 @@ __device__ __forceinline__ void sub_tile_gen_row(const float* __restrict__ sx,
                                                  const float* __restrict__ sz, int jj0,
                                                  float2 nx, float2 ny, float2 nz,
                                                  const GeoConst& c) {
-  const float2 inv_step4 = dup2(4.0f * c.inv_step);
-  const float2 magic_thr = dup2(RINT_MAGIC + static_cast<float>(c.thr_s));
+  const float2 inv_step4 = dup2(bin_scale(c.inv_step));
+  const float2 magic_thr = dup2(bin_magic(c.thr_s));
   const float2 magic2 = dup2(RINT_MAGIC), nmagic2 = dup2(-RINT_MAGIC);
   const float2 one2 = dup2(c.onef);
 #pragma unroll 1
@@ -600,7 +651,7 @@ __device__ __forceinline__ void sub_tile_gen_row(const float* __restrict__ sx,
 
 // register budget: 768 resident threads per SM without culling (85 registers), 512 with it
 template <int NT, int R, bool EXACT, int AM, bool CULL>
-__global__ void __launch_bounds__(NT, (CULL ? 512 : 768) / NT) rdf_pair_hist_kernel(const __grid_constant__ RdfParams P) {
+__global__ void __launch_bounds__(NT, NT == 384 ? 2 : (CULL ? 512 : 768) / NT) rdf_pair_hist_kernel(const __grid_constant__ RdfParams P) {
   constexpr int TI = NT * R;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // layout: [stage0 xyz | stage1 xyz | mbar x4 | item, release counters | row-tile box |
@@ -1170,7 +1221,7 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
   int am = (flags >> 12) & 0xf;   // 0 = auto, else AM = am - 1
   if (cfg == 0) cfg = max_len <= 8192 ? 1 : 4;
   am = am == 0 ? 2 : am - 1;  // auto: unconditional ATOMS.POPC.INC (fastest measured)
-  MDK_CHECK_ARG(cfg >= 1 && cfg <= 4 && am >= 0 && am <= 8, "rdf_hist: bad tuning flags");
+  MDK_CHECK_ARG(cfg >= 1 && cfg <= 5 && am >= 0 && am <= 8, "rdf_hist: bad tuning flags");
   const bool auto_am = ((flags >> 12) & 0xf) == 0;
   if (am == 3 && nbins > FRAC_MAX_BINS) am = 2;  // fraction-bit binning needs nbins <= 15000
   // coordinates verified to span less than one box length: cheaper minimum image
@@ -1178,14 +1229,14 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
   if ((am == 2 || want_q) && !exact && (flags & MDK_RDF_WRAPPED)) am = want_q ? 6 : 5;
   else if (want_q) am = 2;
   // sorted frames with bounding boxes: uniform-image blocks + gated compare (any coordinates)
-  if ((auto_am || am == 7) && !exact && bbox && cfg == 4) am = 7;
+  if ((auto_am || am == 7) && !exact && bbox && cfg >= 4) am = 7;
   else if (am == 7) am = (flags & MDK_RDF_WRAPPED) ? 5 : 2;
   // wrapped minimum image + clamped gated compare (needs wrapped coordinates; instantiated for
   // the 256 x 4 tile): +4..6 % over AM 5 on unsorted frames
-  if (auto_am && am == 5 && cfg == 4) am = 8;
+  if (auto_am && am == 5 && cfg >= 4) am = 8;
   if (am == 8 && (exact || !(flags & MDK_RDF_WRAPPED))) am = 2;
-  if (am == 8 && cfg != 4) am = 5;
-  const int NT = (cfg <= 2) ? 128 : 256;
+  if (am == 8 && cfg < 4) am = 5;
+  const int NT = cfg == 5 ? 384 : (cfg <= 2) ? 128 : 256;
   const int R = (cfg == 1 || cfg == 3) ? 2 : 4;
   const int TI = NT * R;
 
@@ -1284,6 +1335,11 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
     case 1: return launch_rdf_cfg<128, 2>(P, smem_used, grid, s, exact, am);
     case 2: return launch_rdf_cfg<128, 4>(P, smem_used, grid, s, exact, am);
     case 3: return launch_rdf_cfg<256, 2>(P, smem_used, grid, s, exact, am);
+    case 5:  // tuning: 12 warps per CTA (AM 7 / 8 only)
+      if (am == 7 && P.bbox) return launch_rdf<384, 4, false, 7, true>(P, smem_used, grid, s);
+      if (am == 8 && !P.bbox) return launch_rdf<384, 4, false, 8, false>(P, smem_used, grid, s);
+      set_error("rdf_hist: tile configuration 5 needs atomic mode 7 (sorted) or 8 (unsorted)");
+      return MDK_EINVAL;
     default: return launch_rdf_cfg<256, 4>(P, smem_used, grid, s, exact, am);
   }
 }

@@ -524,10 +524,10 @@ def run_gpu_arm(args):
         "phases_ms_per_step": {k: 1e3 * v / steps for k, v in t.items()},
         "wall_s_timed_region": wall,
         # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch on this workload
-        # shape (10^6 atoms, 1 frame), ncu --set full capture profiles/r01i_ncu_rdf_uniform_image.md
+        # shape (10^6 atoms, 1 frame), ncu --set full capture profiles/r01k_ncu_rdf_final.md
         "roofline": dict(fp32_roof(FLOP_PER_PAIR * pairs_per_frame, t["rdf_kernel"],
-                                   traffic=None if small else 12.63e6),
-                         traffic_unit="bytes per launch (ncu capture r01i; the kernel is "
+                                   traffic=None if small else 12.64e6),
+                         traffic_unit="bytes per launch (ncu capture r01k; the kernel is "
                                       "compute bound: 12 MB of coordinates per 5e11 pairs)",
                          kernel="rdf_pair_hist_kernel",
                          algorithmic="20 FLOP per pair-distance x 4.999995e11 pairs per launch "

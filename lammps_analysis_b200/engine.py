@@ -48,7 +48,8 @@ class RdfEngine:
 
     # species at least this large are Morton-ordered per frame so that whole blocks of pairs
     # beyond the cutoff can be skipped; below it a tile spans too much of the box to gain
-    SORT_MIN_ATOMS = 150_000   # measured on B200: -7 % at 100k atoms, +5 % at 200k, +32 % at 10^6
+    SORT_MIN_ATOMS = 80_000    # measured on B200 (uniform-image kernel): -9 % at 50k atoms,
+                               # +5 % at 100k, +24 % at 200k, +50 % at 10^6
 
     def __init__(self, counts, box, cutoff: float, nbins: int, drop_first: bool = True,
                  device=None, max_batch_bytes: int = 2 << 30, spatial_sort=None):

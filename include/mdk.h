@@ -97,7 +97,11 @@ int mdk_coord_extent(const float* pos_soa, int n_frames, long long n_pad, float*
  *   hist    : device u64 [n_pairs][nbins], pair order = combinations_with_replacement
  *             (0,0),(0,1),...,(1,1),... ; accumulated (+=)
  *   work_counter : device scratch, 8 bytes, 8-byte aligned; zeroed by the call
- *   bbox    : NULL, or the tile boxes from mdk_rdf_bbox (enables block culling)
+ *   bbox    : NULL, or the tile boxes from mdk_rdf_bbox (enables block culling and, for species
+ *             blocks beyond 8192 atoms, the uniform-image fast path: blocks of pairs whose boxes
+ *             prove one common periodic image take d + (-n L) instead of the per-pair rint)
+ *   flags   : MDK_RDF_* bits; bits 8..11 (tile configuration) and 12..15 (binning / atomic
+ *             mode) are tuning overrides used by the tests and benchmarks, 0 = automatic
  * Pairs counted: i < j within a species block, all (i, j) across blocks, for each
  * frame: r = p_j - p_i; r -= rint(r / L) * L; d2 = (x*x + y*y) + z*z (fp32, each op
  * rounded); counted iff sqrt(d2) < cutoff.

@@ -196,6 +196,23 @@ int mdk_unwrap_indices(const float* pos, const float* img, long long n_atom_fram
 int mdk_ionic_current(const float* vel, long long A, long long T, const void* q, int q_mode,
                       double* J, mdk_stream_t stream);
 
+/* J[t][k] += sum over atoms of w(a, t) * x[a][t][comp0 + k], k < 3 (fp64 accumulation):
+ *   x  : device fp32 [A][T][ncomp];  w1, w2 : NULL (w = 1) or device fp32 [A][T] (w = w1 + w2,
+ *        w2 may be NULL);  J : device double [T][3], accumulated (+=)
+ * Replaces MomentumFlux.transform_batch (transformations/momentum_flux.py:45-55: ncomp 6,
+ * comp0 3, no weights) and IntegratedHeatCurrent.transform_batch
+ * (transformations/integrated_heat_current.py:49-60: unwrapped positions weighted by
+ * Kinetic_Energy + Potential_Energy). */
+int mdk_flux_sum(const float* x, long long A, long long T, int ncomp, int comp0, const float* w1,
+                 const float* w2, double* J, mdk_stream_t stream);
+
+/* J[t][k] += sum over atoms of (KE + PE) v_k - (S v)_k with the symmetric stress tensor S from
+ * the six components (xx, yy, zz, xy, xz, yz):  stress [A][T][6], vel [A][T][3], ke / pe [A][T],
+ * all device fp32; J device double [T][3], accumulated.
+ * Replaces ThermalFlux.transform_batch (transformations/thermal_flux.py:51-92). */
+int mdk_thermal_flux(const float* stress, const float* vel, const float* ke, const float* pe,
+                     long long A, long long T, double* J, mdk_stream_t stream);
+
 /* ------------------------------------------------------------------------- *
  * Ingest (HOST code, no GPU involved): LAMMPS text dump tokenizer
  * ------------------------------------------------------------------------- */

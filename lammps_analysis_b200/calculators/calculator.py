@@ -133,6 +133,12 @@ class TrajectoryCalculator(Calculator):
             run.IonicCurrent()
         elif dependency == "Translational_Dipole_Moment":
             run.TranslationalDipoleMoment()
+        elif dependency == "Integrated_Heat_Current":   # transformations_reference.py:27-34
+            run.IntegratedHeatCurrent()
+        elif dependency == "Thermal_Flux":
+            run.ThermalFlux()
+        elif dependency == "Momentum_Flux":
+            run.MomentumFlux()
         else:
             raise KeyError("Data not in database and cannot be generated.")  # :171-174
 

@@ -377,3 +377,43 @@ def ionic_current(vel: torch.Tensor, charge, J: torch.Tensor):
                                     _stream()),
               "mdk_ionic_current")
     _count()
+
+
+def flux_sum(x: torch.Tensor, J: torch.Tensor, comp0: int = 0, w1: torch.Tensor | None = None,
+             w2: torch.Tensor | None = None):
+    """J[t][k] += sum_a w(a, t) x[a][t][comp0 + k] (k < 3), w = 1 or w1 (+ w2), fp64 sums.
+
+    Replaces transformations/momentum_flux.py:45-55 and integrated_heat_current.py:49-60.
+    """
+    _need_cuda(x, torch.float32, "flux_sum x")
+    _need_cuda(J, torch.float64, "flux_sum J")
+    A, T, ncomp = x.shape
+    if J.numel() != T * 3:
+        raise MdkError("flux_sum: J must hold T * 3 values")
+    for w in (w1, w2):
+        if w is not None:
+            _need_cuda(w, torch.float32, "flux_sum weight")
+            if w.numel() != A * T:
+                raise MdkError("flux_sum: weights must have A * T elements")
+    check(_lib.load().mdk_flux_sum(_ptr(x), A, T, int(ncomp), int(comp0),
+                                   _ptr(w1) if w1 is not None else None,
+                                   _ptr(w2) if w2 is not None else None, _ptr(J), _stream()),
+          "mdk_flux_sum")
+    _count()
+
+
+def thermal_flux(stress: torch.Tensor, vel: torch.Tensor, ke: torch.Tensor, pe: torch.Tensor,
+                 J: torch.Tensor):
+    """J[t][k] += sum_a (KE + PE) v_k - (S v)_k.  Replaces transformations/thermal_flux.py:51-92."""
+    _need_cuda(stress, torch.float32, "thermal_flux stress")
+    _need_cuda(vel, torch.float32, "thermal_flux vel")
+    _need_cuda(ke, torch.float32, "thermal_flux ke")
+    _need_cuda(pe, torch.float32, "thermal_flux pe")
+    _need_cuda(J, torch.float64, "thermal_flux J")
+    A, T, D = vel.shape
+    if D != 3 or tuple(stress.shape) != (A, T, 6) or ke.numel() != A * T or pe.numel() != A * T \
+            or J.numel() != T * 3:
+        raise MdkError("thermal_flux: bad shapes")
+    check(_lib.load().mdk_thermal_flux(_ptr(stress), _ptr(vel), _ptr(ke), _ptr(pe), A, T, _ptr(J),
+                                       _stream()), "mdk_thermal_flux")
+    _count()

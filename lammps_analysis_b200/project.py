@@ -378,7 +378,37 @@ class RunComputation:
         from .transformations import TranslationalDipoleMoment
         return self._transformation(TranslationalDipoleMoment)
 
+    @property
+    def IntegratedHeatCurrent(self):
+        from .transformations import IntegratedHeatCurrent
+        return self._transformation(IntegratedHeatCurrent)
+
+    @property
+    def ThermalFlux(self):
+        from .transformations import ThermalFlux
+        return self._transformation(ThermalFlux)
+
+    @property
+    def MomentumFlux(self):
+        from .transformations import MomentumFlux
+        return self._transformation(MomentumFlux)
+
     # calculators
+    @property
+    def EinsteinHelfandThermalConductivity(self):
+        from .calculators import EinsteinHelfandThermalConductivity
+        return EinsteinHelfandThermalConductivity(**self.kwargs)
+
+    @property
+    def GreenKuboThermalConductivity(self):
+        from .calculators import GreenKuboThermalConductivity
+        return GreenKuboThermalConductivity(**self.kwargs)
+
+    @property
+    def GreenKuboViscosity(self):
+        from .calculators import GreenKuboViscosity
+        return GreenKuboViscosity(**self.kwargs)
+
     @property
     def EinsteinHelfandIonicConductivity(self):
         from .calculators import EinsteinHelfandIonicConductivity

@@ -185,3 +185,81 @@ class TranslationalDipoleMoment(IonicCurrent):
                 exp.run.UnwrapViaIndices(species=missing)
             else:
                 exp.run.CoordinateUnwrapper(species=missing)
+
+
+class _AtomSumObservable(Transformations):
+    """MultiSpeciesTrafo pattern (transformations.py:522-619) for observables that are plain
+    sums over atoms and species: ``Observables/{output_property}`` of shape (1, n_frames, 3).
+    Atoms shard across ranks; the partial sums meet in one all-reduce (as IonicCurrent)."""
+
+    def _ensure_inputs(self, species):
+        pass
+
+    def _accumulate(self, sp, lo, hi, J):
+        raise NotImplementedError
+
+    def run_transformation(self, species: list = None):
+        import torch
+
+        exp = self.experiment
+        out_path = join_path("Observables", self.output_property)
+        if exp.store.check_existence(out_path):
+            log.info("%s already exists, skipping", self.output_property)
+            return  # transformations.py:572-579
+        species = list(exp.species) if species is None else species
+        self._ensure_inputs(species)
+        n_frames = exp.number_of_configurations
+        J = torch.zeros(n_frames, 3, dtype=torch.float64, device="cuda")
+        for sp in species:
+            paths = [self._require(sp, p) for p in self.input_properties]
+            n_atoms = exp.store.shape(paths[0])[0]
+            lo, hi = D.shard_atoms(0, n_atoms)
+            if hi > lo:
+                self._accumulate(sp, lo, hi, J)
+        D.all_reduce_sum_([J])
+        out = exp.store.add_dataset(out_path, (1, n_frames, 3))
+        out[0] = J.cpu().numpy()  # float64 -> float32 store rounding
+        exp.store.invalidate(out_path)
+
+    def _dev(self, sp, prop, lo, hi):
+        return self.experiment.store.device(join_path(sp, prop), rows=(lo, hi))
+
+
+class MomentumFlux(_AtomSumObservable):
+    """Sum over atoms of the off-diagonal stress components xy, xz, yz
+    (momentum_flux.py:45-55)."""
+
+    input_properties = ["Stress"]
+    output_property = "Momentum_Flux"
+
+    def _accumulate(self, sp, lo, hi, J):
+        K.flux_sum(self._dev(sp, "Stress", lo, hi), J, comp0=3)
+
+
+class IntegratedHeatCurrent(_AtomSumObservable):
+    """sum_a r_a (KE_a + PE_a) on unwrapped positions (integrated_heat_current.py:49-60)."""
+
+    input_properties = ["Unwrapped_Positions", "Kinetic_Energy", "Potential_Energy"]
+    output_property = "Integrated_Heat_Current"
+
+    def _ensure_inputs(self, species):
+        TranslationalDipoleMoment._ensure_inputs(self, species)
+
+    def _accumulate(self, sp, lo, hi, J):
+        ke = self._dev(sp, "Kinetic_Energy", lo, hi)
+        pe = self._dev(sp, "Potential_Energy", lo, hi)
+        K.flux_sum(self._dev(sp, "Unwrapped_Positions", lo, hi), J, comp0=0,
+                   w1=ke.reshape(hi - lo, -1).contiguous(), w2=pe.reshape(hi - lo, -1).contiguous())
+
+
+class ThermalFlux(_AtomSumObservable):
+    """sum_a (KE_a + PE_a) v_a - S_a v_a (thermal_flux.py:51-92)."""
+
+    input_properties = ["Stress", "Velocities", "Kinetic_Energy", "Potential_Energy"]
+    output_property = "Thermal_Flux"
+
+    def _accumulate(self, sp, lo, hi, J):
+        ke = self._dev(sp, "Kinetic_Energy", lo, hi).reshape(hi - lo, -1).contiguous()
+        pe = self._dev(sp, "Potential_Energy", lo, hi).reshape(hi - lo, -1).contiguous()
+        K.thermal_flux(self._dev(sp, "Stress", lo, hi), self._dev(sp, "Velocities", lo, hi), ke,
+                       pe, J)

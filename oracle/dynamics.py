@@ -235,3 +235,46 @@ def eh_ionic_msd(dipole: np.ndarray, plan: dict, data_range: int, correlation_ti
             msd = (ensemble[:, tau_values] - ensemble[:, None, 0]) ** 2
             msd_array += (prefactor * msd.sum(axis=2))[0, :]
     return msd_array / (int(plan["n_batches"]) * ensemble_loop)
+
+
+# --- green_kubo_thermal_conductivity.py:152-248, green_kubo_viscosity.py:146-227 ------------
+_trapz = getattr(np, "trapezoid", None) or np.trapz   # np.trapz was renamed in NumPy 2
+
+
+def gk_thermal_prefactor(units, temperature, volume, data_range):
+    denominator = 3 * (data_range - 1) * temperature**2 * units.boltzmann * volume
+    return (1 / denominator) * (units.energy / units.length / units.time)
+
+
+def gk_viscosity_prefactor(units, temperature, volume, data_range):
+    denominator = 3 * (data_range - 1) * temperature * units.boltzmann * volume
+    return (1 / denominator) * (units.pressure**2 * units.length**3 * units.time / units.energy)
+
+
+def gk_flux(flux: np.ndarray, plan: dict, data_range: int, correlation_time: int,
+            time: np.ndarray, integration_range: int, prefactor: float, value_key: str):
+    """flux: (1, T, 3) system observable.  Per window: jacf = data_range * sum_dims
+    tfp.auto_correlation(window, axis=0); self.jacf += jacf; sigma.append(trapz(...)).  The
+    result is prefactor * sigma[0] with "uncertainty" prefactor * sigma[1] (the first two
+    windows), and the stored acf is the un-averaged sum (reference behaviour, restated as is)."""
+    jacf_sum = np.zeros(data_range)
+    sigma = []
+    for _atom_sel, start, stop, data_size in iter_batches(plan, system=True):
+        batch = np.asarray(flux[start:stop], dtype=np.float64)
+        if batch.shape[0] == 0:
+            raise ValueError("system observable requested with more than one batch (Q7)")
+        for s, e in iter_ensembles(data_size, data_range, correlation_time):
+            ensemble = batch[0, s:e]                       # (N, 3)
+            acf = tfp_auto_correlation(ensemble[None])[0]  # (N, 3), axis 0 correlated
+            jacf = data_range * acf.sum(axis=-1)
+            jacf_sum += jacf
+            sigma.append(_trapz(jacf[:integration_range], x=time[:integration_range]))
+    result = prefactor * np.array(sigma)
+    return {value_key: result[0], "uncertainty": result[1], "time": np.asarray(time).tolist(),
+            "acf": jacf_sum.tolist()}
+
+
+# --- einstein_helfand_thermal_conductivity.py:152-229 ----------------------------------------
+def eh_thermal_prefactor(units, temperature, volume):
+    denominator = volume * temperature * units.boltzmann
+    return (1 / denominator) * (units.energy / units.length / units.time / units.temperature)

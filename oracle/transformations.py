@@ -108,3 +108,55 @@ def dipole_moment_transform_batch(batch: dict):
     for d in dipms[1:]:
         out = out + d
     return out
+
+
+def momentum_flux_transform_batch(batch: dict):
+    """momentum_flux.py:45-55: sum over atoms (and species) of stress components 3, 4, 5."""
+    fluxes = []
+    for properties in batch.values():
+        stress = np.asarray(properties["Stress"], dtype=np.float64)
+        phi = np.stack([stress[:, :, 3], stress[:, :, 4], stress[:, :, 5]], axis=2)
+        fluxes.append(np.sum(phi, axis=0))
+    out = fluxes[0]
+    for f in fluxes[1:]:
+        out = out + f
+    return out
+
+
+def integrated_heat_current_transform_batch(batch: dict):
+    """integrated_heat_current.py:49-60: sum_a pos * (KE + PE)."""
+    currents = []
+    for properties in batch.values():
+        pos = np.asarray(properties["Unwrapped_Positions"], dtype=np.float64)
+        ke = np.asarray(properties["Kinetic_Energy"], dtype=np.float64)
+        pe = np.asarray(properties["Potential_Energy"], dtype=np.float64)
+        currents.append(np.sum(pos * (ke + pe), axis=0))
+    out = currents[0]
+    for c in currents[1:]:
+        out = out + c
+    return out
+
+
+def thermal_flux_transform_batch(batch: dict):
+    """thermal_flux.py:51-92: sum_a (KE + PE) v - S v with the 6-component stress."""
+    fluxes = []
+    for properties in batch.values():
+        stress = np.asarray(properties["Stress"], dtype=np.float64)
+        vel = np.asarray(properties["Velocities"], dtype=np.float64)
+        ke = np.asarray(properties["Kinetic_Energy"], dtype=np.float64)
+        pe = np.asarray(properties["Potential_Energy"], dtype=np.float64)
+        phi_x = (stress[:, :, 0] * vel[:, :, 0] + stress[:, :, 3] * vel[:, :, 1]
+                 + stress[:, :, 4] * vel[:, :, 2])
+        phi_y = (stress[:, :, 3] * vel[:, :, 0] + stress[:, :, 1] * vel[:, :, 1]
+                 + stress[:, :, 5] * vel[:, :, 2])
+        phi_z = (stress[:, :, 4] * vel[:, :, 0] + stress[:, :, 5] * vel[:, :, 1]
+                 + stress[:, :, 2] * vel[:, :, 2])
+        phi = np.dstack([phi_x, phi_y, phi_z])
+        phi_sum_atoms = phi.sum(axis=0)
+        energy = ke + pe
+        energy_velocity_atoms = np.sum(energy * vel, axis=0)
+        fluxes.append(energy_velocity_atoms - phi_sum_atoms)
+    out = fluxes[0]
+    for f in fluxes[1:]:
+        out = out + f
+    return out

@@ -464,6 +464,114 @@ def test_einstein_helfand_ionic_conductivity(tmp_path, cuda):
     assert res["System"]["ionic_conductivity"] == pytest.approx(popt[0] / 6, rel=1e-4)
 
 
+def _flux_experiment(tmp_path, n_atoms=216, n_frames=700, seed=21):
+    """Two species with per-atom Stress (6), Velocities, Kinetic / Potential energy and wrapped
+    positions: the inputs of the MomentumFlux / ThermalFlux / IntegratedHeatCurrent chain."""
+    from lammps_analysis_b200.config import config
+    from lammps_analysis_b200.file_io import ScriptInput
+    from lammps_analysis_b200.project import Project
+    from lammps_analysis_b200.synthetic import nacl_trajectory
+
+    config.planner_memory_bytes = MEM
+    data, box = nacl_trajectory(n_atoms, n_frames, 18.0, seed=seed, sigma_step=0.2)
+    rng = np.random.default_rng(seed)
+    for sp in data:
+        A = data[sp]["Positions"].shape[0]
+        # slowly varying per-atom fields so that the flux autocorrelations are not pure noise
+        walk = np.cumsum(rng.normal(0, 0.05, size=(A, n_frames, 6)), axis=1)
+        data[sp]["Stress"] = (rng.normal(0, 1.0, size=(A, 1, 6)) + walk).astype(np.float32)
+        data[sp]["Kinetic_Energy"] = rng.uniform(0.5, 1.5, size=(A, n_frames, 1)).astype(np.float32)
+        data[sp]["Potential_Energy"] = rng.normal(-3.0, 0.3, size=(A, n_frames, 1)).astype(np.float32)
+    project = Project("flux", storage_path=str(tmp_path))
+    exp = project.add_experiment("NaCl", timestep=0.002, temperature=1400.0, units="metal")
+    exp.add_data(ScriptInput(data, box, sample_rate=10, atom_major=True))
+    return exp, data, box
+
+
+def _system_plan(n_frames, N):
+    from oracle.planner import ArrayDatabase, plan_trajectory_calculator
+
+    class _S:
+        shape = (1, n_frames, 3)
+
+    return plan_trajectory_calculator(ArrayDatabase({"x": _S()}), ["x"], N, 1,
+                                      {"linear": {"scale_factor": 5}}, MEM)
+
+
+def test_flux_transformations_match_oracle(tmp_path, cuda):
+    """MomentumFlux, ThermalFlux, IntegratedHeatCurrent against the restated
+    transform_batch bodies; the observables are stored as float32 (1, T, 3)."""
+    from oracle import transformations as ot
+
+    exp, data, box = _flux_experiment(tmp_path)
+    exp.run.MomentumFlux()
+    exp.run.ThermalFlux()
+    exp.run.IntegratedHeatCurrent()      # runs the unwrap first
+    ref_m = ot.momentum_flux_transform_batch({s: {"Stress": data[s]["Stress"]} for s in data})
+    ref_t = ot.thermal_flux_transform_batch({s: {k: data[s][k] for k in
+                                                 ("Stress", "Velocities", "Kinetic_Energy",
+                                                  "Potential_Energy")} for s in data})
+    unw = {s: ot.run_unwrap(data[s]["Positions"], box, batch_size=data[s]["Positions"].shape[1])
+           for s in data}
+    ref_h = ot.integrated_heat_current_transform_batch(
+        {s: {"Unwrapped_Positions": unw[s], "Kinetic_Energy": data[s]["Kinetic_Energy"],
+             "Potential_Energy": data[s]["Potential_Energy"]} for s in data})
+    for name, ref in (("Momentum_Flux", ref_m), ("Thermal_Flux", ref_t),
+                      ("Integrated_Heat_Current", ref_h)):
+        got = exp.store.host(f"Observables/{name}")
+        assert got.shape == (1, ref.shape[0], 3) and got.dtype == np.float32
+        np.testing.assert_allclose(got[0], ref, rtol=2e-7, atol=1e-6 * np.abs(ref).max())
+    # a second call finds the datasets and skips (transformations.py:572-579)
+    exp.run.MomentumFlux()
+
+
+@pytest.mark.parametrize("which", ["thermal", "viscosity"])
+def test_green_kubo_flux_calculators(tmp_path, cuda, which):
+    """GreenKuboThermalConductivity / GreenKuboViscosity: dependency resolution runs the flux
+    transformation, the windowed ACF kernels reproduce the restated reference (value = first
+    window's integral, "uncertainty" = second window's, acf = sum over windows)."""
+    from lammps_analysis_b200.units import METAL
+    from oracle import dynamics as od
+
+    exp, data, box = _flux_experiment(tmp_path, seed=22)
+    N, ir = 100, 80
+    if which == "thermal":
+        res = exp.run.GreenKuboThermalConductivity(data_range=N, integration_range=ir)
+        prop, key = "Thermal_Flux", "computation_results"
+        pref = od.gk_thermal_prefactor(METAL, 1400.0, float(np.prod(box)), N)
+    else:
+        res = exp.run.GreenKuboViscosity(data_range=N, integration_range=ir)
+        prop, key = "Momentum_Flux", "viscosity"
+        pref = od.gk_viscosity_prefactor(METAL, 1400.0, float(np.prod(box)), N)
+    J = exp.store.host(f"Observables/{prop}").astype(np.float64)
+    T = J.shape[1]
+    _, _, _, times = od.handle_tau_values(np.s_[:], N, 0.002, 10)
+    ref = od.gk_flux(J, _system_plan(T, N), N, 1, times, ir, pref, key)
+    got = res["System"]
+    assert set(got) == {key, "uncertainty", "time", "acf"}
+    scale = np.abs(ref["acf"]).max()
+    np.testing.assert_allclose(got["acf"], ref["acf"], rtol=RTOL, atol=1e-7 * scale)
+    np.testing.assert_allclose(got["time"], ref["time"], rtol=1e-12)
+    assert got[key] == pytest.approx(ref[key], rel=1e-4)
+    assert got["uncertainty"] == pytest.approx(ref["uncertainty"], rel=1e-4)
+
+
+def test_einstein_helfand_thermal_conductivity(tmp_path, cuda):
+    from lammps_analysis_b200.units import METAL
+    from oracle import dynamics as od
+
+    exp, data, box = _flux_experiment(tmp_path, seed=23)
+    N = 90
+    res = exp.run.EinsteinHelfandThermalConductivity(data_range=N, plot=False)
+    Q = exp.store.host("Observables/Integrated_Heat_Current").astype(np.float64)
+    tau, _, _, times = od.handle_tau_values(np.s_[:], N, 0.002, 10)
+    pref = od.eh_thermal_prefactor(METAL, 1400.0, float(np.prod(box)))
+    msd = od.eh_ionic_msd(Q, _system_plan(Q.shape[1], N), N, 1, tau, pref)
+    np.testing.assert_allclose(res["System"]["msd"], msd, rtol=RTOL, atol=1e-9 * np.abs(msd).max())
+    popt, _, _, _ = od.fit_einstein_curve(times, msd, N - 1)
+    assert res["System"]["thermal_conductivity"] == pytest.approx(popt[0] / 6, rel=1e-4)
+
+
 def test_in_memory_pinned_store_matches_persistent_store(tmp_path, cuda):
     """persist=False keeps datasets in page-locked host memory: the RDF pack kernels gather the
     sampled frames from it in place (zero copy), uploads are single DMA transfers.  Same numbers

@@ -230,12 +230,13 @@ msd_dense_kernel(const float* __restrict__ traj, long long T, long long a_lo, lo
 
 // msd_dense2_kernel: two atoms per sweep, z components packed (lag ranges that fill the CTA).
 
-template <bool GROUPS>
+// R (lags per thread, odd) is picked by the launcher so that the lag range fills the 64 threads:
+// 5 for up to 320 lags, 7 for up to 448, 9 beyond (several lag blocks above 576).
+template <bool GROUPS, int R>
 __global__ void __launch_bounds__(MD_NT)
 msd_dense2_kernel(const float* __restrict__ traj, long long T, long long a_lo, long long a_hi,
                  int atoms_per_cta, long long t0, int W, int n_lags, int Wc, int len_alloc,
                  double* __restrict__ msd_sum) {
-  constexpr int R = MD_R;
   extern __shared__ __align__(16) float md_smem[];
   // Two atoms (A, B) are swept together so that their z components share packed instructions:
   // layout xyA (float2 x len_alloc) | xyB | zAB (float2 {zA, zB} x len_alloc) | origin copies
@@ -918,11 +919,12 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
     MDK_LAUNCH_CHECK();
     return MDK_OK;
   }
-  constexpr int R = MD_R;
+  // window groups (one-atom kernel, R = 9) only pay off when the lag range leaves at least half
+  // of the CTA idle; otherwise the two-atom kernel with the smallest odd R that covers the range
+  const bool grouped = (n_lags + MD_R - 1) / MD_R <= MD_NT / 2;
+  const int R = grouped ? MD_R : (n_lags <= MD_NT * 5 ? 5 : (n_lags <= MD_NT * 7 ? 7 : 9));
   const int lag_span = MD_NT * R;
   const int lag_blocks = (n_lags + lag_span - 1) / lag_span;
-  // window groups only pay off when the lag range leaves at least half of the CTA idle
-  const bool grouped = lag_blocks == 1 && (n_lags + R - 1) / R <= MD_NT / 2;
   // every thread may read up to one ring refill past its last lag: the slab covers the window
   // chunk plus the lag span of the block (plus R), so those (discarded) reads stay inside it.
   // Short lag ranges take long window chunks (up to ~4096 frames, 48 KB): with few lags per
@@ -946,10 +948,17 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
     msd_dense_kernel<true><<<grid, MD_NT, smem, as_stream(stream)>>>(
         traj, T, a_lo, a_hi, apc, t0, W, n_lags, Wc, len_alloc, msd_sum);
   } else {
-    MDK_CUDA(cudaFuncSetAttribute(msd_dense2_kernel<false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    msd_dense2_kernel<false><<<grid, MD_NT, smem, as_stream(stream)>>>(
-        traj, T, a_lo, a_hi, apc, t0, W, n_lags, Wc, len_alloc, msd_sum);
+#define MDK_MD2_LAUNCH(RR)                                                                    \
+  do {                                                                                        \
+    MDK_CUDA(cudaFuncSetAttribute(msd_dense2_kernel<false, RR>,                               \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    msd_dense2_kernel<false, RR><<<grid, MD_NT, smem, as_stream(stream)>>>(                   \
+        traj, T, a_lo, a_hi, apc, t0, W, n_lags, Wc, len_alloc, msd_sum);                     \
+  } while (0)
+    if (R == 5) MDK_MD2_LAUNCH(5);
+    else if (R == 7) MDK_MD2_LAUNCH(7);
+    else MDK_MD2_LAUNCH(9);
+#undef MDK_MD2_LAUNCH
   }
   MDK_LAUNCH_CHECK();
   return MDK_OK;

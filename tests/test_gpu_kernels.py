@@ -238,6 +238,8 @@ def _plan(A, T, data_range, ct, memory=60e9, scale=150):
     (60, 1000, 100, 1, 2.0e5 * 60 / 64),  # several batches + remainder
     (9, 1500, 700, 1, 60e9),      # more lags than one lag block of the dense kernel (576)
     (5, 700, 577, 1, 60e9),       # one lag into the second lag block; few windows
+    (11, 900, 300, 1, 60e9),      # two-atom kernel with 5 lags per thread (odd atom count)
+    (7, 1000, 400, 1, 60e9),      # ... with 7 lags per thread
 ])
 def test_msd_matches_oracle(cuda, A, T, N, ct, memory):
     from lammps_analysis_b200.engine import msd_series, plan_windows, to_device_f32

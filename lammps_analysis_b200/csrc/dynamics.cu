@@ -107,12 +107,11 @@ constexpr int MD_R = 9;  // odd: the lane stride of MD_R positions is bank-confl
 
 // msd_dense_kernel: one atom per sweep ({x,y} packed, z scalar) -- kept for short lag ranges, where
 // window groups split the CTA and the two-atom variant below needs too many registers.
-template <bool GROUPS>
+template <bool GROUPS, int R>
 __global__ void __launch_bounds__(MD_NT)
 msd_dense_kernel(const float* __restrict__ traj, long long T, long long a_lo, long long a_hi,
                  int atoms_per_cta, long long t0, int W, int n_lags, int Wc, int len_alloc,
                  double* __restrict__ msd_sum) {
-  constexpr int R = MD_R;
   extern __shared__ __align__(16) float md_smem[];
   // layout: xy (float2 x len_alloc) | z (len_alloc floats) | origin copies for lag blocks > 0
   float2* s_xy = reinterpret_cast<float2*>(md_smem);
@@ -922,7 +921,22 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
   // window groups (one-atom kernel, R = 9) only pay off when the lag range leaves at least half
   // of the CTA idle; otherwise the two-atom kernel with the smallest odd R that covers the range
   const bool grouped = (n_lags + MD_R - 1) / MD_R <= MD_NT / 2;
-  const int R = grouped ? MD_R : (n_lags <= MD_NT * 5 ? 5 : (n_lags <= MD_NT * 7 ? 7 : 9));
+  // grouped: the odd R in {5, 7, 9} that keeps most threads busy (G lag-threads x NG groups;
+  // ties go to the larger R, which reuses a loaded position more often).  The two-atom kernel
+  // was measured slower there (register pressure of the group bookkeeping).
+  int R = n_lags <= MD_NT * 5 ? 5 : (n_lags <= MD_NT * 7 ? 7 : 9);
+  if (grouped) {
+    int best = -1;
+    for (int r : {9, 7, 5}) {
+      const int G = (n_lags + r - 1) / r;
+      if (G > MD_NT) continue;
+      const int busy = G * (MD_NT / G);
+      if (busy > best) {
+        best = busy;
+        R = r;
+      }
+    }
+  }
   const int lag_span = MD_NT * R;
   const int lag_blocks = (n_lags + lag_span - 1) / lag_span;
   // every thread may read up to one ring refill past its last lag: the slab covers the window
@@ -943,10 +957,17 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
   MDK_CHECK_ARG(groups <= 65535 && lag_blocks <= 65535, "msd_dense: grid too large");
   dim3 grid(chunks, (unsigned)groups, lag_blocks);
   if (grouped) {
-    MDK_CUDA(cudaFuncSetAttribute(msd_dense_kernel<true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    msd_dense_kernel<true><<<grid, MD_NT, smem, as_stream(stream)>>>(
-        traj, T, a_lo, a_hi, apc, t0, W, n_lags, Wc, len_alloc, msd_sum);
+#define MDK_MD1_LAUNCH(RR)                                                                    \
+  do {                                                                                        \
+    MDK_CUDA(cudaFuncSetAttribute(msd_dense_kernel<true, RR>,                                 \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    msd_dense_kernel<true, RR><<<grid, MD_NT, smem, as_stream(stream)>>>(                     \
+        traj, T, a_lo, a_hi, apc, t0, W, n_lags, Wc, len_alloc, msd_sum);                     \
+  } while (0)
+    if (R == 5) MDK_MD1_LAUNCH(5);
+    else if (R == 7) MDK_MD1_LAUNCH(7);
+    else MDK_MD1_LAUNCH(9);
+#undef MDK_MD1_LAUNCH
   } else {
 #define MDK_MD2_LAUNCH(RR)                                                                    \
   do {                                                                                        \

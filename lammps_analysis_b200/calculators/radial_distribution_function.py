@@ -14,6 +14,7 @@ from dataclasses import dataclass
 from typing import Union
 
 import numpy as np
+import torch
 
 from .. import distributed as D
 from ..engine import RdfEngine
@@ -109,6 +110,16 @@ class RadialDistributionFunction(TrajectoryCalculator):
         # the sampled frames over PCIe / NVLink-C2C): no host-side gather, no staging copy
         zero_copy = (not resident and not isinstance(sel, dict)
                      and all(store.pinned_tensor(p) is not None for p in paths))
+        if zero_copy and len(frames):
+            # a strided 12-byte gather over the host link moves at least one 64-byte segment per
+            # atom and frame: beyond ~1/6 of the frames one bulk DMA of the whole array is less
+            # traffic (C4: 1000 frames of 100k atoms, 0.6 s of gathers against a 25 ms upload)
+            total_frames = max(store.shape(paths[0])[1], 1)
+            nbytes = sum(int(np.prod(store.shape(p))) * 4 for p in paths)
+            free_bytes = torch.cuda.mem_get_info()[0]
+            if len(frames) * 6 >= total_frames and nbytes < 0.4 * free_bytes:
+                zero_copy = False
+                resident = True
         for s, path in zip(self.args.species, paths):
             if resident:
                 trajs.append(store.device(path))

@@ -48,6 +48,7 @@ class RdfEngine:
 
     # species at least this large are Morton-ordered per frame so that whole blocks of pairs
     # beyond the cutoff can be skipped; below it a tile spans too much of the box to gain
+    SORT_BATCH_FRAMES = 16
     SORT_MIN_ATOMS = 80_000    # measured on B200 (uniform-image kernel): -9 % at 50k atoms,
                                # +5 % at 100k, +24 % at 200k, +50 % at 10^6
 
@@ -96,8 +97,12 @@ class RdfEngine:
     def add_frames(self, species_traj, frames, check_extent: bool = True, tuning: int = 0):
         """species_traj: list of CUDA float32 [A_s][T][3]; frames: int array of frame ids."""
         frames = np.asarray(frames, dtype=np.int64)
-        for k0 in range(0, len(frames), self.max_frames):
-            sel = frames[k0:k0 + self.max_frames]
+        # the sorted pack is one host call per frame and species: short launch batches let the
+        # host enqueue the packs of the next batch while the pair kernel of this one runs
+        step = min(self.max_frames, self.SORT_BATCH_FRAMES) if self.spatial_sort \
+            else self.max_frames
+        for k0 in range(0, len(frames), step):
+            sel = frames[k0:k0 + step]
             buf = self._buffer(len(sel))
             for s, traj in enumerate(species_traj):
                 if traj.shape[0] != self.full_counts[s]:

@@ -18,7 +18,19 @@
 //   * binning is exact: a fast fp32 guess g = rint(sqrt.approx(d2)/step) is corrected
 //     against a table of fp32 thresholds on d2 (mdk_rdf_thresholds) held in shared memory;
 //   * counts go to a CTA-private u32 histogram in shared memory and are flushed to the
-//     global u64 histogram when the species pair changes / the CTA retires.
+//     global u64 histogram when the species pair changes / the CTA retires;
+//   * on Hilbert-sorted frames with bounding boxes (mdk_rdf_pack_sorted, mdk_rdf_bbox) whole
+//     blocks of pairs beyond the cutoff are skipped, and blocks whose boxes prove one common
+//     periodic image replace the per-pair rint by a warp-uniform shift (AM 7, sub_tile_uni).
+//
+// Variants (template parameter AM, selected in mdk_rdf_hist; all produce the same integers):
+//   0 / 1 / 2  table compare for every in-cutoff lane; predicated / per-lane dump / POPC.INC
+//   3          bin from 7 fraction bits of the guess, table compare under a warp vote
+//   4          tables and histogram in global memory (bin counts beyond shared memory)
+//   5          as 2 with the wrapped-coordinate minimum image min(|d|, L - |d|)
+//   6          as 5 with a quarter-bit gated table compare
+//   7          DEFAULT on sorted frames: uniform-image blocks + clamped gated compare
+//   8          DEFAULT on unsorted wrapped frames: wrapped minimum image + clamped gated compare
 #include "mdk_common.cuh"
 
 #include <cmath>
@@ -650,6 +662,7 @@ __device__ __forceinline__ void sub_tile_gen_row(const float* __restrict__ sx,
 }
 
 // register budget: 768 resident threads per SM without culling (85 registers), 512 with it
+// (AM 7 needs 94; the 112 KB of tables per CTA at 13.5k bins allow two CTAs per SM anyway)
 template <int NT, int R, bool EXACT, int AM, bool CULL>
 __global__ void __launch_bounds__(NT, NT == 384 ? 2 : (CULL ? 512 : 768) / NT) rdf_pair_hist_kernel(const __grid_constant__ RdfParams P) {
   constexpr int TI = NT * R;

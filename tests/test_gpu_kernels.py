@@ -499,6 +499,35 @@ def test_reference_run_rdf_counts_on_gpu(cuda):
         assert np.array_equal(got[p], np.asarray(g["counts"][key])), key
 
 
+def test_reference_run_flux_kernels_on_gpu(cuda):
+    """mdk_flux_sum / mdk_thermal_flux against vectors from the reference's own source."""
+    import json
+    import os
+
+    import torch
+    from lammps_analysis_b200 import kernels as K
+    from lammps_analysis_b200.engine import to_device_f32
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_flux.json")) as fh:
+        g = json.load(fh)
+    T = len(g["momentum_flux"])
+    Jm = torch.zeros(T, 3, dtype=torch.float64, device=cuda)
+    Jt = torch.zeros_like(Jm)
+    Jh = torch.zeros_like(Jm)
+    for sp, d in g["inputs"].items():
+        dev = {k: to_device_f32(np.asarray(v, dtype=np.float32), cuda) for k, v in d.items()}
+        A = dev["Stress"].shape[0]
+        ke = dev["Kinetic_Energy"].reshape(A, T).contiguous()
+        pe = dev["Potential_Energy"].reshape(A, T).contiguous()
+        K.flux_sum(dev["Stress"], Jm, comp0=3)
+        K.thermal_flux(dev["Stress"], dev["Velocities"], ke, pe, Jt)
+        K.flux_sum(dev["Unwrapped_Positions"], Jh, comp0=0, w1=ke, w2=pe)
+    for got, key in ((Jm, "momentum_flux"), (Jt, "thermal_flux"), (Jh, "integrated_heat_current")):
+        want = np.asarray(g[key])
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-13,
+                                   atol=1e-14 * np.abs(want).max())
+
+
 def test_reference_run_transformations_on_gpu(cuda):
     import torch
     from lammps_analysis_b200 import kernels as K

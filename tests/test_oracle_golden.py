@@ -202,6 +202,26 @@ def test_reference_run_transformations(ref_run):
                           np.asarray(ref_run["dipole_moment"]["moment"]))
 
 
+def test_reference_run_flux_transformations():
+    """Flux transformations and the Einstein-Helfand thermal window operation against vectors
+    from the reference's own source (tests/golden/make_reference_flux_goldens.py)."""
+    from oracle import dynamics as od
+
+    g = _load("reference_flux.json")
+    batch = {sp: {k: np.asarray(v, dtype=np.float32) for k, v in d.items()}
+             for sp, d in g["inputs"].items()}
+    assert np.array_equal(ot.momentum_flux_transform_batch(batch), np.asarray(g["momentum_flux"]))
+    assert np.array_equal(ot.thermal_flux_transform_batch(batch), np.asarray(g["thermal_flux"]))
+    assert np.array_equal(ot.integrated_heat_current_transform_batch(batch),
+                          np.asarray(g["integrated_heat_current"]))
+    e = g["eh_thermal_ensemble_operation"]
+    window = np.asarray(e["window"])
+    N = window.shape[0]
+    plan = {"batch_size": N, "n_batches": 1, "remainder": 0, "minibatch": False}
+    msd = od.eh_ionic_msd(window[None], plan, N, 1, np.arange(N), e["prefactor"])
+    np.testing.assert_allclose(msd, np.asarray(e["msd"]), rtol=1e-14)
+
+
 def test_reference_run_planner(ref_run):
     from lammps_analysis_b200.planner import plan_batches
 

@@ -438,6 +438,7 @@ def run_gpu_arm(args):
         type(gk).__call__.__wrapped__(gk, data_range=N, plot=False)
         acf_sum, count2, win, a_sel = gk.compute_acf("A")
         exp_dyn.run.IonicCurrent()
+        exp_dyn.store.flush()   # the unwrapped positions' write-back (side stream) has landed
         return msd_sum, acf_sum
 
     e2e_step(0, [])

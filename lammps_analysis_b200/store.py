@@ -48,6 +48,10 @@ class TrajectoryStore:
         self._device_cache: "OrderedDict[Tuple, object]" = OrderedDict()
         self._device_bytes = 0
         self.h2d_bytes = 0  # bytes uploaded so far (bench.py reads this)
+        # device -> host write-backs in flight on the copy stream, per dataset: whoever reads a
+        # dataset's host copy (or replaces it) drains them first (_drain)
+        self._copy_stream = None
+        self._pending: Dict[str, list] = {}
         if directory is not None:
             os.makedirs(directory, exist_ok=True)
             self._load_index()
@@ -97,8 +101,20 @@ class TrajectoryStore:
         self._save_index()
         return arr
 
+    def _drain(self, path: Optional[str] = None):
+        """Wait for the asynchronous write-backs of one dataset (or of all of them)."""
+        keys = [path] if path is not None else list(self._pending)
+        for k in keys:
+            for ev in self._pending.pop(k, []):
+                ev.synchronize()
+
+    def flush(self):
+        """Block until every asynchronous device -> host write-back has landed."""
+        self._drain(None)
+
     def resize_dataset(self, path: str, n_frames: int):
         """simulation_database.py:380-420 (extend along the frame axis)."""
+        self._drain(path)
         old = self._arrays[path]
         if old.shape[1] >= n_frames:
             return old
@@ -113,6 +129,7 @@ class TrajectoryStore:
     def add_data(self, path: str, data, start: int = 0):
         """Write ``data`` (n_rows, k, n_dims) at frame offset ``start``; values are rounded to
         float32 exactly as the HDF5 store does (simulation_database.py:333-378)."""
+        self._drain(path)
         arr = self._arrays[path]
         data = np.asarray(data)
         arr[:, start : start + data.shape[1]] = data.astype(np.float32, copy=False)
@@ -124,6 +141,7 @@ class TrajectoryStore:
         if array.ndim != 3:
             raise ValueError("datasets are (n_rows, n_frames, n_dims)")
         if path in self._arrays:
+            self._drain(path)
             del self._arrays[path]
             self._pinned.pop(path, None)
             self.invalidate(path)
@@ -141,9 +159,11 @@ class TrajectoryStore:
 
     def load_data(self, path: str, select_slice=np.s_[:]) -> np.ndarray:
         """Host read as float64 (simulation_database.py:594-639 casts to tf.float64)."""
+        self._drain(path)
         return np.asarray(self._arrays[path][select_slice], dtype=np.float64)
 
     def host(self, path: str) -> np.ndarray:
+        self._drain(path)
         return self._arrays[path]
 
     def paths(self):
@@ -190,6 +210,7 @@ class TrajectoryStore:
             whole = self._device_cache.get((path, 0, arr.shape[0], str(dev)))
             if whole is not None:
                 return whole[lo:hi]          # rows are the leading axis: a contiguous view
+        self._drain(path)                    # the host copy is read from here on
         src = arr[row_index] if row_index is not None else arr[lo:hi]
         nbytes = int(np.prod(src.shape)) * 4
         budget = self._budget()
@@ -210,6 +231,7 @@ class TrajectoryStore:
 
     def pinned_tensor(self, path: str):
         """The page-locked host tensor behind a dataset of an in-memory store (or None)."""
+        self._drain(path)
         return self._pinned.get(path)
 
     def is_resident(self, path: str) -> bool:
@@ -230,6 +252,7 @@ class TrajectoryStore:
         cached): the RDF samples a few frames of a long trajectory."""
         import torch
 
+        self._drain(path)
         arr = self._arrays[path]
         frames = np.asarray(frames, dtype=np.int64)
         src = arr[:, frames] if row_index is None else arr[np.asarray(row_index)][:, frames]
@@ -246,13 +269,25 @@ class TrajectoryStore:
         k = tensor.shape[1]
         pin = self._pinned.get(path)
         if pin is not None:
-            pin[:, t0:t0 + k].copy_(tensor, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            # asynchronous write-back on a side stream: PCIe is full duplex, so the copy overlaps
+            # the uploads and kernels of whatever runs next; readers of the host copy drain it
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=tensor.device)
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(ready)
+                pin[:, t0:t0 + k].copy_(tensor, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record()
+            tensor.record_stream(self._copy_stream)
+            self._pending.setdefault(path, []).append(done)
         else:
             arr[:, t0:t0 + k] = tensor.cpu().numpy()
 
     def remove(self, path: str):
         """Delete a dataset (host, disk and device copies)."""
+        self._drain(path)
         self.invalidate(path)
         arr = self._arrays.pop(path, None)
         self._pinned.pop(path, None)

@@ -13,7 +13,7 @@ mdsuite/calculators/trajectory_calculator.py:243-297.
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional, Tuple
 
 from .config import config, machine_memory

@@ -5,7 +5,6 @@ C1: 1,000-atom NaCl LAMMPS text dump, 100 frames -> RadialDistributionFunction (
 C2: same system, 1,500 frames, data_range 200    -> Einstein + Green-Kubo diffusion
 C3: 1,728-atom NaCl, 1,200 frames, data_range 150 -> unwrap, ionic current, GK ionic conductivity
 """
-import itertools
 
 import numpy as np
 import pytest

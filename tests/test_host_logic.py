@@ -171,6 +171,54 @@ def test_lammps_dump_roundtrip_with_unsorted_ids(tmp_path):
         assert np.array_equal(got, results[(not native, sp, prop)])   # bit-identical float64
 
 
+def test_native_lammps_reader_number_formats(tmp_path):
+    """The native tokenizer (exact fast path + strtod fallback, frame-parallel) returns the same
+    float64 as Python's float() for every spelling: exponents, long mantissas, subnormals,
+    signed zero, nan / inf, bare dots; CRLF line ends; no trailing newline; several threads."""
+    import os
+
+    from lammps_analysis_b200.file_io import LAMMPSTrajectoryFile
+
+    toks = ["1e-5", "-0.0", "123456789012345678901", "1.7976931348623157e308", "4.9e-324",
+            "0.1", "+3.", ".5", "1E+3", "2.5e-23", "9007199254740993", "0.30000000000000004",
+            "1e22", "1e23", "123456.789e-30", "-7.25", "nan", "inf", "-inf", "1e-400",
+            "3.14159265358979323846264338327950288", "00012.50", "6.02214076e23", "1e", "-"]
+    n_atoms = 5
+    rng = np.random.default_rng(4)
+    frames = []
+    for f in range(7):
+        rows = []
+        for a in rng.permutation(n_atoms):
+            vals = [toks[int(k)] for k in rng.integers(0, len(toks), 6)]
+            rows.append(f"{a + 1} {1 + a % 2} {'Na' if a % 2 == 0 else 'Cl'} " + " ".join(vals))
+        hdr = ["ITEM: TIMESTEP", str(10 * f), "ITEM: NUMBER OF ATOMS", str(n_atoms),
+               "ITEM: BOX BOUNDS pp pp pp", "0 9.5", "0 9.5", "0 9.5",
+               "ITEM: ATOMS id type element x y z vx vy vz"]
+        frames.append("\r\n".join(hdr + rows) if f % 2 else "\n".join(hdr + rows))
+    path = str(tmp_path / "odd.lammpstraj")
+    with open(path, "w", newline="") as fh:
+        fh.write("\n".join(frames))          # no trailing newline
+    results = {}
+    for native, threads in ((True, "1"), (True, "3"), (False, "1")):
+        os.environ["MDK_INGEST_THREADS"] = threads
+        try:
+            reader = LAMMPSTrajectoryFile(path, native=native)
+            assert reader.metadata.n_configurations == 7
+            chunks = list(reader.get_configurations_generator(3))
+        finally:
+            os.environ.pop("MDK_INGEST_THREADS", None)
+        results[(native, threads)] = {
+            (sp, prop): np.concatenate([c.data[sp][prop] for c in chunks], axis=1)
+            for sp in ("Na", "Cl") for prop in ("Positions", "Velocities")}
+    ref = results[(False, "1")]
+    for key, got in results.items():
+        for k in ref:
+            a, b = got[k], ref[k]
+            assert a.shape == b.shape and np.array_equal(np.isnan(a), np.isnan(b)), (key, k)
+            assert np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)]), (key, k)
+            assert np.array_equal(np.signbit(a), np.signbit(b)), (key, k)
+
+
 def test_native_lammps_reader_rejects_truncated_file(tmp_path):
     from lammps_analysis_b200._lib import MdkError
     from lammps_analysis_b200.file_io import LAMMPSTrajectoryFile, write_lammps_dump

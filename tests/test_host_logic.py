@@ -29,6 +29,32 @@ def test_libmdk_exports_every_declared_symbol():
     assert _lib.MDK_RDF_EXACT_DIV == int(re.search(r"#define MDK_RDF_EXACT_DIV (\d+)", hdr).group(1))
 
 
+def test_c_abi_rejects_bad_arguments_without_a_gpu():
+    """Argument checks run before any CUDA call: error code < 0 and a message, no launch."""
+    from lammps_analysis_b200 import _lib
+
+    lib = _lib.load()
+    one = ctypes.c_double(1.0)
+    buf = (ctypes.c_float * 16)()
+    ptr = ctypes.cast(buf, ctypes.c_void_p)
+    cases = [
+        lib.mdk_flux_sum(None, 1, 1, 3, 0, None, None, None, None),            # null pointers
+        lib.mdk_flux_sum(ptr, 1, 1, 2, 0, None, None, ptr, None),              # ncomp < 3
+        lib.mdk_flux_sum(ptr, 1, 1, 6, 4, None, None, ptr, None),              # comp0 + 3 > ncomp
+        lib.mdk_flux_sum(ptr, 1, 1, 3, 0, None, ptr, ptr, None),               # w2 without w1
+        lib.mdk_thermal_flux(ptr, ptr, ptr, None, 1, 1, ptr, None),            # null pe
+        lib.mdk_ionic_current(ptr, 1, 1, ctypes.cast(ctypes.byref(one), ctypes.c_void_p), 7, ptr,
+                              None),                                           # bad q_mode
+        lib.mdk_msd_dense(ptr, 1, 4, 0, 1, 0, 3, 4, ptr, None),                # windows exceed T
+        lib.mdk_rdf_thresholds(ctypes.c_float(-1.0), 10, ptr, ptr),            # cutoff <= 0
+    ]
+    assert all(rc < 0 for rc in cases), cases
+    assert lib.mdk_last_error().decode() != ""
+    # empty work is not an error and launches nothing
+    assert lib.mdk_flux_sum(ptr, 0, 1, 3, 0, None, None, ptr, None) == 0
+    assert lib.mdk_thermal_flux(ptr, ptr, ptr, ptr, 0, 1, ptr, None) == 0
+
+
 def test_rdf_thresholds_reproduce_double_step_binning():
     """mdk_rdf_thresholds (host helper, no GPU): bin(d2) via the table equals
     int(min(double(d)/step, nbins-1)) for every sampled fp32 distance."""

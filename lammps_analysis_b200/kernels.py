@@ -9,6 +9,7 @@ Each function names the reference code it replaces (paths relative to the MDSuit
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import itertools
 from dataclasses import dataclass, field
 
@@ -70,6 +71,14 @@ def peak_fp32(packed: bool = True, iters: int = 20000) -> float:
 # RDF
 # --------------------------------------------------------------------------------------
 def rdf_thresholds(cutoff: float, nbins: int):
+    """Cached front end of :func:`_rdf_thresholds` (the table depends on (cutoff, nbins) only;
+    repeated calculator runs reuse it)."""
+    thr, cut2 = _rdf_thresholds(float(np.float32(cutoff)), int(nbins))
+    return thr.copy(), cut2
+
+
+@functools.lru_cache(maxsize=32)
+def _rdf_thresholds(cutoff: float, nbins: int):
     """Host table of fp32 thresholds on d^2 reproducing tf.histogram_fixed_width exactly.
 
     Returns (thr float32[nbins + 1], cut2 float).  Replaces bin_minibatch

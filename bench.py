@@ -248,7 +248,12 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
+        # NCCL's INFO log is the evidence of which ranks joined the communicator: keep whatever the
+        # launcher configured, otherwise send it to stderr (stdout stays the one JSON line)
+        if "NCCL_DEBUG" not in os.environ:
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     steps, warm = max(1, args.steps), max(3, args.warmup)

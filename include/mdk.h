@@ -82,6 +82,15 @@ int mdk_rdf_pack(const float* traj, long long A_total, long long T, long long at
                  long long atom_count, const int* frames, int n_frames, float* out,
                  long long n_pad, long long dst_first, long long dst_span, mdk_stream_t stream);
 
+/* Sampled frames of an atom block, kept atom-major:  out[a][k][:] = traj[a][frames[k]][:].
+ *   traj   : [A][T][3] fp32, device memory OR page-locked host memory (read in place)
+ *   frames : device int32 [n_frames], values in [0, T)
+ *   out    : [A][n_frames][3] fp32
+ * The send buffer of the multi-rank frame exchange (each rank holds an atom block of the
+ * store and the RDF shards frames).  Replaces data_manager.py:195-201 (frame fancy index). */
+int mdk_gather_frames(const float* traj, long long A, long long T, const int* frames,
+                      int n_frames, float* out, mdk_stream_t stream);
+
 /* Per-dimension min / max of a packed frame array (NaN padding ignored).
  * minmax: device float[6] = {minx,miny,minz,maxx,maxy,maxz}, caller-initialised to
  * {+inf x3, -inf x3}.  Used by the host to decide whether the fast minimum-image

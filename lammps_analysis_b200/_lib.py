@@ -36,6 +36,7 @@ PROTOTYPES = {
     "mdk_rdf_tile": [],
     "mdk_rdf_thresholds": [_F, _I, _P, _P],
     "mdk_rdf_pack": [_P, _LL, _LL, _LL, _LL, _P, _I, _P, _LL, _LL, _LL, _P],
+    "mdk_gather_frames": [_P, _LL, _LL, _P, _I, _P, _P],
     "mdk_coord_extent": [_P, _I, _LL, _P, _P],
     "mdk_rdf_hist": [_P, _I, _LL, _P, _P, _I, _P, _F, _F, _I, _P, _P, _P, _P, _I, _P],
     "mdk_rdf_sort_workspace": [_I],

@@ -61,6 +61,7 @@ class Calculator:
         self.args = None
         self.plot = False
         self._queued_data: List = []
+        self._queued_metadata: dict = {}
         self._saved_parameters = None
 
     # -- cache protocol (database/calculator_database.py:91-248) ---------------------------------
@@ -73,6 +74,7 @@ class Calculator:
 
     def prepare_db_entry(self):
         self._queued_data = []
+        self._queued_metadata = {}
 
     def save_computation_args(self):
         # stored *before* the run, i.e. with the user's -1 / None defaults unresolved
@@ -81,10 +83,16 @@ class Calculator:
     def queue_data(self, data: dict, subjects: list):
         self._queued_data.append((subjects_key(list(subjects)), data))
 
+    def queue_metadata(self, **items):
+        """Run diagnostics stored next to the result (``Computation.metadata``), outside the
+        reference's ``data_dict``."""
+        self._queued_metadata.update(items)
+
     def save_db_data(self):
         results = OrderedDict(self._queued_data)
         self.experiment.project.store_computation(self.analysis_name, self.experiment.name,
-                                                  self._saved_parameters, results)
+                                                  self._saved_parameters, results,
+                                                  metadata=self._queued_metadata)
 
     def run_analysis(self):
         """calculator.py:310-317."""
@@ -157,6 +165,28 @@ class TrajectoryCalculator(Calculator):
             self.data_resolution = len(self.args.tau_values)
         return (np.asarray(self.args.tau_values) * self.experiment.time_step
                 * self.experiment.sample_rate)
+
+    # -- device residency of one species' rows -------------------------------------------------------------
+    def _device_rows(self, path: str, species: str):
+        """The atom rows of ``path`` this rank processes, on the device.
+
+        Returns (traj, n_atoms, a_shard, row_offset): ``traj`` holds the selected atoms
+        [a_shard[0], a_shard[1]) of the species (indices into the atom selection, or global atom
+        indices when everything is selected), ``n_atoms`` is the size of the whole selection
+        (what the reference's plan and normalisation see), ``row_offset`` the selection index of
+        traj's first row.  Atoms shard across ranks along the store's row blocks."""
+        store = self.experiment.store
+        sel = self.args.atom_selection
+        lo, hi = store.owned_rows(path)
+        if isinstance(sel, dict):
+            idx = np.asarray(sel[species])
+            i0, i1 = 0, len(idx)
+            if store.is_sharded(path):
+                if np.any(np.diff(idx) < 0):
+                    raise ValueError("atom_selection must be sorted when atoms shard across ranks")
+                i0, i1 = (int(v) for v in np.searchsorted(idx, [lo, hi]))
+            return store.device(path, row_index=idx[i0:i1]), len(idx), (i0, i1), i0
+        return store.device(path, rows=(lo, hi)), store.shape(path)[0], (lo, hi), lo
 
     # -- batch plan (:243-297) ------------------------------------------------------------------------------
     def _prepare_managers(self, data_path: list, correct: bool = False) -> BatchPlan:

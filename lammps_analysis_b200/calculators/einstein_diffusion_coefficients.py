@@ -114,24 +114,15 @@ class EinsteinDiffusionCoefficients(TrajectoryCalculator):
     # -- hot path ----------------------------------------------------------------------------------
     def compute_msd(self, species: str):
         """Returns (msd_sum float64 [n_tau] on the host, count) for one species."""
-        store = self.experiment.store
         path = join_path(species, self.loaded_property)
         self._prepare_managers([path])
-        n_atoms = store.shape(path)[0]
-        sel = self.args.atom_selection
-        if isinstance(sel, dict):
-            traj = store.device(path, row_index=np.asarray(sel[species]))
-            n_atoms = traj.shape[0]
-            shard = D.shard_atoms(0, n_atoms)
-        else:
-            # only this rank's atom block is uploaded
-            shard = D.shard_atoms(0, n_atoms)
-            traj = store.device(path, rows=shard)
+        # only this rank's atom block is uploaded (it is already resident when the unwrap
+        # transformation has just produced it)
+        traj, n_atoms, shard, offset = self._device_rows(path, species)
         launches = plan_windows(self.plan.as_dict(), self.args.data_range,
                                 self.args.correlation_time, n_atoms)
         msd, count = msd_series(traj, launches, self.args.data_range, self.args.correlation_time,
-                                self.args.tau_values, a_shard=shard, row_offset=shard[0]
-                                if not isinstance(sel, dict) else 0)
+                                self.args.tau_values, a_shard=shard, row_offset=offset)
         D.all_reduce_sum_([msd])
         return msd.cpu().numpy(), count
 

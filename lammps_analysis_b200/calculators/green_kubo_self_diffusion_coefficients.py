@@ -67,18 +67,9 @@ class GreenKuboDiffusionCoefficients(TrajectoryCalculator):
     def compute_acf(self, species: str):
         """Returns (acf_sum [N], count, per-window atom-summed ACFs [W_total][N], A_sel per
         window [W_total]) on the host, in simulation units (no length^2/time^2 factor)."""
-        store = self.experiment.store
         path = join_path(species, self.loaded_property)
         self._prepare_managers([path])
-        n_atoms = store.shape(path)[0]
-        sel = self.args.atom_selection
-        if isinstance(sel, dict):
-            traj = store.device(path, row_index=np.asarray(sel[species]))
-            n_atoms = traj.shape[0]
-            shard, offset = D.shard_atoms(0, n_atoms), 0
-        else:
-            shard = D.shard_atoms(0, n_atoms)
-            traj, offset = store.device(path, rows=shard), shard[0]
+        traj, n_atoms, shard, offset = self._device_rows(path, species)
         launches = plan_windows(self.plan.as_dict(), self.args.data_range,
                                 self.args.correlation_time, n_atoms)
         acf, count, wins, sizes = acf_series(traj, launches, self.args.data_range,

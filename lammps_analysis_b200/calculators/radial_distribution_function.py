@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from .. import distributed as D
+from .. import kernels as K
 from ..engine import RdfEngine
 from ..store import join_path
 from .calculator import TrajectoryCalculator, call
@@ -101,25 +102,44 @@ class RadialDistributionFunction(TrajectoryCalculator):
         reduced result)."""
         exp = self.experiment
         store = exp.store
+        paths = [join_path(s, self.loaded_property) for s in self.args.species]
+        if any(store.is_sharded(p) for p in paths):
+            trajs, frame_ids = self._exchange_sampled_frames(paths)
+        else:
+            trajs, frame_ids = self._local_sampled_frames(paths)
+        self.engine = RdfEngine(self.particles_list, exp.box_array, self.args.cutoff,
+                                self.args.number_of_bins, drop_first=self.parity_mode)
+        if len(frame_ids):
+            self.engine.add_frames(trajs, frame_ids)
+        D.all_reduce_sum_([self.engine.hist])
+        return self.engine.counts()
+
+    def _bulk_upload_pays(self, paths, n_sampled: int) -> bool:
+        """A strided 12-byte gather over the host link moves at least one 64-byte segment per
+        atom and frame: beyond ~1/6 of the frames one bulk DMA of the whole array is less
+        traffic (C4: 1000 frames of 100k atoms, 0.6 s of gathers against a 25 ms upload)."""
+        store = self.experiment.store
+        total_frames = max(store.shape(paths[0])[1], 1)
+        nbytes = 0
+        for p in paths:
+            lo, hi = store.owned_rows(p)
+            nbytes += (hi - lo) * int(np.prod(store.shape(p)[1:])) * 4
+        return n_sampled * 6 >= total_frames and nbytes < 0.4 * torch.cuda.mem_get_info()[0]
+
+    def _local_sampled_frames(self, paths):
+        """One rank holds every atom: the sampled frames (this rank's share of them when a
+        process group runs on unsharded per-rank stores) are packed straight from the store."""
+        store = self.experiment.store
         sel = self.args.atom_selection
         frames = D.shard_frames(self.sample_configurations)
         trajs, frame_ids = [], frames
-        paths = [join_path(s, self.loaded_property) for s in self.args.species]
         resident = all(store.is_resident(p) for p in paths) and not isinstance(sel, dict)
         # page-locked host datasets are read in place by the pack kernels (zero-copy gather of
         # the sampled frames over PCIe / NVLink-C2C): no host-side gather, no staging copy
         zero_copy = (not resident and not isinstance(sel, dict)
                      and all(store.pinned_tensor(p) is not None for p in paths))
-        if zero_copy and len(frames):
-            # a strided 12-byte gather over the host link moves at least one 64-byte segment per
-            # atom and frame: beyond ~1/6 of the frames one bulk DMA of the whole array is less
-            # traffic (C4: 1000 frames of 100k atoms, 0.6 s of gathers against a 25 ms upload)
-            total_frames = max(store.shape(paths[0])[1], 1)
-            nbytes = sum(int(np.prod(store.shape(p))) * 4 for p in paths)
-            free_bytes = torch.cuda.mem_get_info()[0]
-            if len(frames) * 6 >= total_frames and nbytes < 0.4 * free_bytes:
-                zero_copy = False
-                resident = True
+        if zero_copy and len(frames) and self._bulk_upload_pays(paths, len(frames)):
+            zero_copy, resident = False, True
         for s, path in zip(self.args.species, paths):
             if resident:
                 trajs.append(store.device(path))
@@ -131,12 +151,40 @@ class RadialDistributionFunction(TrajectoryCalculator):
                 trajs.append(store.device_frames(path, frames, row_index=rows))
         if not resident and not zero_copy:
             frame_ids = np.arange(len(frames))
-        self.engine = RdfEngine(self.particles_list, exp.box_array, self.args.cutoff,
-                                self.args.number_of_bins, drop_first=self.parity_mode)
-        if len(frames):
-            self.engine.add_frames(trajs, frame_ids)
-        D.all_reduce_sum_([self.engine.hist])
-        return self.engine.counts()
+        return trajs, frame_ids
+
+    def _exchange_sampled_frames(self, paths):
+        """Atom-sharded store: every rank gathers the sampled frames of ITS atom block (from
+        HBM when resident, else in place from page-locked host memory) and the ranks swap the
+        (atom block x frame) slabs with one all-to-all per species over NVLink, so that each
+        ends up with all atoms of the frames it owns.  Every byte crosses the host link once."""
+        store = self.experiment.store
+        sel = self.args.atom_selection
+        frames = np.asarray(self.sample_configurations)
+        n_f = len(frames)
+        fdev = torch.from_numpy(frames.astype(np.int32)).cuda()
+        bulk = not isinstance(sel, dict) and self._bulk_upload_pays(paths, n_f)
+        trajs = []
+        for s, path in zip(self.args.species, paths):
+            if isinstance(sel, dict):
+                idx = np.asarray(sel[s])
+                if np.any(np.diff(idx) < 0):
+                    raise ValueError("atom_selection must be sorted when atoms shard across ranks")
+                cuts = [np.searchsorted(idx, [lo, hi]) for lo, hi in store.rows_per_rank(path)]
+                i0, i1 = cuts[store.rank]
+                local = store.device_frames(path, frames, row_index=idx[i0:i1])
+                rows_per_rank = [int(b - a) for a, b in cuts]
+            else:
+                rows_per_rank = [hi - lo for lo, hi in store.rows_per_rank(path)]
+                pin = store.pinned_tensor(path)
+                if store.is_resident(path) or (bulk and pin is not None):
+                    local = store.device(path).index_select(1, fdev.long())
+                elif pin is not None:
+                    local = K.gather_frames(pin, fdev)
+                else:
+                    local = store.device_frames(path, frames)
+            trajs.append(D.exchange_frames(local, rows_per_rank, n_f))
+        return trajs, np.arange(len(D.shard_frames(frames)))
 
     # -- :299-382, 719-826 -------------------------------------------------------------------------------
     @property

@@ -1038,6 +1038,25 @@ __global__ void rdf_pack_kernel(const float* __restrict__ traj, long long T, lon
   }
 }
 
+// Sampled frames of an atom block, kept atom-major: out[a][k][:] = traj[a][frames[k]][:].
+// traj may be page-locked host memory (read in place over the host link): this is the send
+// buffer of the multi-rank frame exchange.
+__global__ void gather_frames_kernel(const float* __restrict__ traj, long long T, long long A,
+                                     const int* __restrict__ frames, int F,
+                                     float* __restrict__ out) {
+  const long long total = A * F;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long a = e / F;
+    const int k = static_cast<int>(e - a * F);
+    const float* src = traj + ((size_t)a * T + frames[k]) * 3;
+    const float x = __ldg(src), y = __ldg(src + 1), z = __ldg(src + 2);
+    out[3 * e] = x;
+    out[3 * e + 1] = y;
+    out[3 * e + 2] = z;
+  }
+}
+
 __device__ __forceinline__ void atomic_min_f(float* addr, float v) {
   // valid for any sign: compare as ordered ints
   if (v >= 0.f)
@@ -1184,6 +1203,20 @@ extern "C" int mdk_rdf_pack(const float* traj, long long A_total, long long T, l
   dim3 grid((unsigned)blocks, (unsigned)n_frames);
   rdf_pack_kernel<<<grid, threads, 0, as_stream(stream)>>>(traj, T, atom_first, atom_count, frames,
                                                            out, n_pad, dst_first, dst_span);
+  MDK_LAUNCH_CHECK();
+  return MDK_OK;
+}
+
+extern "C" int mdk_gather_frames(const float* traj, long long A, long long T, const int* frames,
+                                 int n_frames, float* out, mdk_stream_t stream) {
+  MDK_CHECK_ARG(A >= 0 && T >= 0 && n_frames >= 0, "gather_frames: negative size");
+  if (A == 0 || n_frames == 0) return MDK_OK;
+  MDK_CHECK_ARG(traj && frames && out, "gather_frames: null pointer");
+  long long blocks = (A * n_frames + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  gather_frames_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(traj, T, A, frames,
+                                                                         n_frames, out);
   MDK_LAUNCH_CHECK();
   return MDK_OK;
 }

@@ -1,11 +1,18 @@
 """Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink on the
-GPU box, gloo in CPU tests).  The hot path has exactly two exchange steps:
+GPU box, gloo in CPU tests).  The trajectory store is ATOM-SHARDED across ranks (store.py): a
+rank keeps, uploads and writes back only its own atom block of every per-species dataset.  The
+hot path has three exchange steps:
 
-* RDF shards the sampled frames across ranks -> one all-reduce(sum, int64) of the
-  ``[n_pairs][nbins]`` histograms;
-* MSD / ACF / ionic current shard atoms across ranks -> all-reduce(sum, float64) of the series.
+* RDF shards the sampled frames across ranks: the ranks swap (atom block x sampled frame)
+  slabs with one all-to-all over NVLink so that each holds all atoms of its frames
+  (``exchange_frames``), then one all-reduce(sum, int64) of the ``[n_pairs][nbins]`` histograms;
+* MSD / ACF / ionic current run on the rank's own atom block -> all-reduce(sum, float64) of
+  the series;
+* unwrap needs no communication (per-atom scan over the rank's block).
 
-Everything else (unwrap, fits, coordination numbers) needs no communication.
+Fits and coordination numbers run replicated on every rank.  Persistent state (dataset files,
+index, result database) is created and written by rank 0 only (``is_root``), the other ranks
+wait on a barrier; the cache-hit decision is broadcast so that all ranks take the same branch.
 """
 from __future__ import annotations
 
@@ -76,3 +83,60 @@ def all_reduce_sum_(tensors: List):
         if t is not None:
             d.all_reduce(t, op=d.ReduceOp.SUM)
     return tensors
+
+
+def is_root() -> bool:
+    return rank() == 0
+
+
+def barrier():
+    d = _dist()
+    if d is not None and d.get_world_size() > 1:
+        d.barrier()
+
+
+def broadcast_object(obj, src: int = 0):
+    """Rank ``src``'s picklable object on every rank (cache decisions, small results)."""
+    d = _dist()
+    if d is None or d.get_world_size() == 1:
+        return obj
+    box = [obj if d.get_rank() == src else None]
+    d.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def gather_rows(local, n_rows_total: int):
+    """All ranks' contiguous row blocks (shard_atoms order) of a host array -> the whole array
+    on every rank.  Collective; used by host reads of a sharded in-memory dataset."""
+    d = _dist()
+    if d is None or d.get_world_size() == 1:
+        return local
+    parts = [None] * d.get_world_size()
+    d.all_gather_object(parts, local)
+    out = np.concatenate(parts, axis=0)
+    assert out.shape[0] == n_rows_total
+    return out
+
+
+def exchange_frames(local, rows_per_rank, n_frames: int):
+    """All-to-all of sampled frames: ``local`` is this rank's atom block of ALL sampled frames,
+    a tensor [A_local][n_frames][3]; ``rows_per_rank[q]`` is the block size of rank q.  The
+    result is [sum(rows_per_rank)][F_mine][3] holding every atom of the frames
+    ``shard_frames(arange(n_frames))`` this rank owns.  Blocks are contiguous and in rank
+    order, so the received pieces are already in atom order."""
+    import torch
+
+    d = _dist()
+    if d is None or d.get_world_size() == 1:
+        return local
+    w, r = d.get_world_size(), d.get_rank()
+    a_loc = local.shape[0]
+    if a_loc != rows_per_rank[r]:
+        raise ValueError("exchange_frames: local block does not match rows_per_rank")
+    f_of = [len(range(q, n_frames, w)) for q in range(w)]
+    send = torch.cat([local[:, q::w].reshape(-1) for q in range(w)])
+    in_splits = [a_loc * f * 3 for f in f_of]
+    out_splits = [int(n) * f_of[r] * 3 for n in rows_per_rank]
+    recv = local.new_empty(sum(out_splits))
+    d.all_to_all_single(recv, send.contiguous(), out_splits, in_splits)
+    return recv.view(int(sum(rows_per_rank)), f_of[r], 3)

@@ -165,6 +165,26 @@ def rdf_pack(traj: torch.Tensor, frames: torch.Tensor, out: torch.Tensor, layout
         _count()
 
 
+def gather_frames(traj: torch.Tensor, frames: torch.Tensor, out: torch.Tensor = None):
+    """out[a][k] = traj[a][frames[k]] for an atom block [A][T][3] (CUDA or pinned host memory);
+    returns the CUDA tensor [A][len(frames)][3].  Replaces data_manager.py:195-201."""
+    _need_device_readable(traj, torch.float32, "gather_frames traj")
+    _need_cuda(frames, torch.int32, "gather_frames frames")
+    A, T, D = traj.shape
+    if D != 3:
+        raise MdkError("gather_frames: trajectory must be [A][T][3]")
+    nf = frames.numel()
+    if out is None:
+        out = torch.empty(A, nf, 3, dtype=torch.float32, device=frames.device)
+    _need_cuda(out, torch.float32, "gather_frames out")
+    if out.numel() != A * nf * 3:
+        raise MdkError("gather_frames: output must hold A * n_frames * 3 values")
+    check(_lib.load().mdk_gather_frames(_ptr(traj), A, T, _ptr(frames), nf, _ptr(out), _stream()),
+          "mdk_gather_frames")
+    _count()
+    return out
+
+
 def coord_extent(pos_soa: torch.Tensor, n_frames: int, n_pad: int) -> np.ndarray:
     """Per-dimension [min xyz, max xyz] of a packed frame array (synchronises)."""
     _need_cuda(pos_soa, torch.float32, "coord_extent")

@@ -15,7 +15,6 @@ from __future__ import annotations
 import json
 import logging
 import os
-import pickle
 import sqlite3
 from collections import OrderedDict
 from dataclasses import dataclass, fields, is_dataclass
@@ -24,6 +23,7 @@ from typing import Dict, List, Optional, Union
 
 import numpy as np
 
+from . import distributed as D
 from .file_io import LAMMPSTrajectoryFile, ScriptInput, TrajectoryMetadata
 from .store import TrajectoryStore, join_path
 from .units import Units, resolve_units
@@ -56,12 +56,16 @@ class Computation:
     """Result of one calculator run (database/scheme.py:193-342)."""
 
     def __init__(self, name: str, experiment_name: str, parameters: dict,
-                 results: "OrderedDict[str, dict]", comp_id: Optional[int] = None):
+                 results: "OrderedDict[str, dict]", comp_id: Optional[int] = None,
+                 metadata: Optional[dict] = None):
         self.name = name
         self.experiment_name = experiment_name
         self._parameters = parameters
         self._results = results
         self.id = comp_id
+        # run diagnostics that are not part of the reference's data_dict (e.g. the RDF's
+        # bin-edge tie report); data_dict keeps exactly the reference's keys
+        self.metadata = dict(metadata or {})
 
     def __repr__(self):
         return f"Exp{self.experiment_name}_{self.name}_{self.id}"
@@ -117,13 +121,19 @@ class Experiment:
         self.name = name
         self.time_step = time_step
         self.temperature = temperature
+        # experiment.py:188-191: units given here win, stored units come next, REAL is the
+        # default only when nothing is stored (_load_metadata)
+        self._units_given = units is not None
         self.units = resolve_units(units if units is not None else "real")
         self.cluster_mode = cluster_mode
         self.active = True
         self.experiment_path = os.path.join(project.storage_path, project.name, name)
         self.database_path = os.path.join(self.experiment_path, "database")
-        os.makedirs(self.database_path, exist_ok=True)
-        self.store = TrajectoryStore(self.database_path if project.persist else None)
+        if project.is_writer:
+            os.makedirs(self.database_path, exist_ok=True)
+        project.barrier()
+        self.store = TrajectoryStore(self.database_path if project.persist else None,
+                                     sharded=project.sharded)
         self.species: "OrderedDict[str, Species]" = OrderedDict()
         self.molecules: dict = {}
         self.box_array: Optional[list] = None
@@ -152,14 +162,17 @@ class Experiment:
             self.version = m["version"]
             self.read_files = m["read_files"]
             self.species = OrderedDict((k, Species(**v)) for k, v in m["species"])
+            if not self._units_given and m.get("units") is not None:
+                self.units = Units(**m["units"])
 
     def _save_metadata(self):
-        if not self.project.persist:
+        if not self.project.persist or not self.project.is_writer:
             return
         m = dict(time_step=self.time_step, temperature=self.temperature,
                  box_array=self.box_array, number_of_configurations=self.number_of_configurations,
                  number_of_atoms=self.number_of_atoms, sample_rate=self.sample_rate,
                  version=self.version, read_files=self.read_files,
+                 units={f.name: getattr(self.units, f.name) for f in fields(self.units)},
                  species=[(k, v.__dict__) for k, v in self.species.items()])
         with open(self._meta_path(), "w") as fh:
             json.dump(m, fh)
@@ -185,6 +198,7 @@ class Experiment:
             self._add_from_processor(proc)
             self.read_files.append(str(tag))
         self._save_metadata()
+        self.project.barrier()     # shared files: every rank's rows have landed
 
     def _add_from_processor(self, proc):
         meta: TrajectoryMetadata = proc.metadata
@@ -249,21 +263,51 @@ def _get_processor(item):
 # Project
 # ------------------------------------------------------------------------------------------
 class Project:
-    def __init__(self, name: str = None, storage_path: str = "./", persist: bool = True):
+    def __init__(self, name: str = None, storage_path: str = "./", persist: bool = True,
+                 sharded: bool = None):
+        """``sharded`` (default: True when a torch.distributed group with more than one rank is
+        active): all ranks open the SAME project; the trajectory store is atom-sharded
+        (store.py), a persistent project directory is shared and written by rank 0 only, and
+        cache decisions are broadcast.  ``sharded=False`` gives every rank a private, complete
+        project (bench.py's weak-scaling replicas)."""
         self.name = f"MDSuite_Project_{name}" if name is not None else "MDSuite_Project"
         self.storage_path = str(storage_path)
         self.persist = persist
-        os.makedirs(os.path.join(self.storage_path, self.name), exist_ok=True)
+        self.sharded = (D.world_size() > 1) if sharded is None else bool(sharded)
+        self._shared_files = self.sharded and persist   # one directory for all ranks
+        if self.is_writer:
+            os.makedirs(os.path.join(self.storage_path, self.name), exist_ok=True)
+        self.barrier()
         self._experiments: "OrderedDict[str, Experiment]" = OrderedDict()
-        db_path = os.path.join(self.storage_path, self.name, "project.db") if persist else ":memory:"
-        self._db = sqlite3.connect(db_path)
-        self._db.execute(
-            "CREATE TABLE IF NOT EXISTS computations (id INTEGER PRIMARY KEY, name TEXT, "
-            "experiment TEXT, parameters TEXT, results BLOB)")
-        self._db.execute("CREATE TABLE IF NOT EXISTS experiments (name TEXT PRIMARY KEY)")
-        self._db.commit()
-        for (exp_name,) in self._db.execute("SELECT name FROM experiments").fetchall():
+        self._db = None
+        names = []
+        if self.is_writer:
+            db_path = os.path.join(self.storage_path, self.name, "project.db") if persist \
+                else ":memory:"
+            self._db = sqlite3.connect(db_path)
+            self._db.execute(
+                "CREATE TABLE IF NOT EXISTS computations (id INTEGER PRIMARY KEY, name TEXT, "
+                "experiment TEXT, parameters TEXT, results BLOB, metadata TEXT)")
+            self._db.execute("CREATE TABLE IF NOT EXISTS experiments (name TEXT PRIMARY KEY)")
+            cols = [r[1] for r in self._db.execute("PRAGMA table_info(computations)")]
+            if "metadata" not in cols:      # database written before the metadata column
+                self._db.execute("ALTER TABLE computations ADD COLUMN metadata TEXT")
+            self._db.commit()
+            names = [n for (n,) in self._db.execute("SELECT name FROM experiments").fetchall()]
+        if self._shared_files:
+            names = D.broadcast_object(names)
+        for exp_name in names:
             self._experiments[exp_name] = Experiment(self, exp_name)
+
+    @property
+    def is_writer(self) -> bool:
+        """False only on the non-zero ranks of a shared persistent project: they neither create
+        files nor touch the database."""
+        return not self._shared_files or D.is_root()
+
+    def barrier(self):
+        if self._shared_files:
+            D.barrier()
 
     @property
     def experiments(self) -> Dict[str, Experiment]:
@@ -293,8 +337,9 @@ class Project:
                          cluster_mode=cluster_mode)
         exp.active = active
         self._experiments[name] = exp
-        self._db.execute("INSERT OR IGNORE INTO experiments VALUES (?)", (name,))
-        self._db.commit()
+        if self.is_writer:
+            self._db.execute("INSERT OR IGNORE INTO experiments VALUES (?)", (name,))
+            self._db.commit()
         if simulation_data is not None:
             exp.add_data(simulation_data, update_with_pubchempy=update_with_pubchempy)
         exp._save_metadata()
@@ -302,32 +347,96 @@ class Project:
 
     # -- computation cache ------------------------------------------------------------------------------
     def find_computation(self, name: str, experiment: str, parameters: dict) -> Optional[Computation]:
-        want = json.dumps(parameters, sort_keys=True)
-        row = self._db.execute(
-            "SELECT id, results FROM computations WHERE name=? AND experiment=? AND parameters=?",
-            (name, experiment, want)).fetchone()
+        """Cached result with identical arguments and experiment version, or None.  In a
+        sharded project rank 0 decides (and, for a shared database, provides the record), so
+        every rank takes the same hit / miss branch."""
+        row = None
+        if self.is_writer:
+            want = json.dumps(parameters, sort_keys=True)
+            row = self._db.execute(
+                "SELECT id, results, metadata FROM computations WHERE name=? AND experiment=? "
+                "AND parameters=?", (name, experiment, want)).fetchone()
+            if row is not None:
+                row = (row[0], bytes(row[1]), row[2])
+        if self._shared_files:
+            row = D.broadcast_object(row)
+        elif self.sharded:
+            hit = D.broadcast_object(row is not None)
+            if hit != (row is not None):
+                raise RuntimeError("ranks disagree about a cached computation: the per-rank "
+                                   "projects of a sharded run have diverged")
         if row is None:
             return None
-        results = OrderedDict(pickle.loads(row[1]))
-        return Computation(name, experiment, parameters, results, comp_id=row[0])
+        return Computation(name, experiment, parameters, decode_results(row[1]), comp_id=row[0],
+                           metadata=json.loads(row[2]) if row[2] else {})
 
     def store_computation(self, name: str, experiment: str, parameters: dict,
-                          results: "OrderedDict[str, dict]"):
-        self._db.execute(
-            "INSERT INTO computations (name, experiment, parameters, results) VALUES (?,?,?,?)",
-            (name, experiment, json.dumps(parameters, sort_keys=True),
-             # series are long lists of floats: a binary blob is ~50x cheaper than JSON text
-             # (the reference stores JSON; the returned data_dict has the same structure)
-             sqlite3.Binary(pickle.dumps(list(results.items()), protocol=pickle.HIGHEST_PROTOCOL))))
-        self._db.commit()
+                          results: "OrderedDict[str, dict]", metadata: dict = None):
+        if self.is_writer:
+            self._db.execute(
+                "INSERT INTO computations (name, experiment, parameters, results, metadata) "
+                "VALUES (?,?,?,?,?)",
+                (name, experiment, json.dumps(parameters, sort_keys=True),
+                 sqlite3.Binary(encode_results(results)),
+                 json.dumps(metadata) if metadata else None))
+            self._db.commit()
+        self.barrier()
 
 
-def _json_default(o):
-    if isinstance(o, np.ndarray):
-        return o.tolist()
-    if isinstance(o, (np.floating, np.integer)):
-        return o.item()
-    raise TypeError(f"not JSON serialisable: {type(o)}")
+# Result blobs: a JSON index in which every long numeric series is replaced by a reference into
+# a packed float64 payload (the reference stores plain JSON text, database/scheme.py:270-333;
+# series are ~50x cheaper packed).  Nothing read back from the database is ever executed.
+_RESULT_MAGIC = b"MDKR0001"
+_SERIES_MIN = 16
+
+
+def _pack_value(val, payload: list, cursor: list):
+    if isinstance(val, dict):
+        return {str(k): _pack_value(v, payload, cursor) for k, v in val.items()}
+    if isinstance(val, np.ndarray):
+        val = val.tolist()
+    if isinstance(val, (np.floating, np.integer)):
+        return val.item()
+    if isinstance(val, (list, tuple)):
+        if len(val) >= _SERIES_MIN and all(type(v) is float for v in val):
+            arr = np.asarray(val, dtype=np.float64)
+            ref = {"__f64__": [cursor[0], len(arr)]}
+            payload.append(arr)
+            cursor[0] += len(arr)
+            return ref
+        return [_pack_value(v, payload, cursor) for v in val]
+    if isinstance(val, (str, int, float, bool)) or val is None:
+        return val
+    raise TypeError(f"result value of type {type(val)} cannot be stored")
+
+
+def _unpack_value(val, payload: np.ndarray):
+    if isinstance(val, dict):
+        if set(val) == {"__f64__"}:
+            off, n = val["__f64__"]
+            return payload[off:off + n].tolist()
+        return {k: _unpack_value(v, payload) for k, v in val.items()}
+    if isinstance(val, list):
+        return [_unpack_value(v, payload) for v in val]
+    return val
+
+
+def encode_results(results: "OrderedDict[str, dict]") -> bytes:
+    payload, cursor = [], [0]
+    index = [[k, _pack_value(v, payload, cursor)] for k, v in results.items()]
+    text = json.dumps(index).encode()
+    text += b" " * (-len(text) % 8)
+    body = np.concatenate(payload).tobytes() if payload else b""
+    return _RESULT_MAGIC + len(text).to_bytes(8, "little") + text + body
+
+
+def decode_results(blob: bytes) -> "OrderedDict[str, dict]":
+    if blob[:8] != _RESULT_MAGIC:
+        raise ValueError("project.db: unknown result record format (not written by this version)")
+    n = int.from_bytes(blob[8:16], "little")
+    index = json.loads(blob[16:16 + n].decode())
+    payload = np.frombuffer(blob, dtype=np.float64, offset=16 + n)
+    return OrderedDict((k, _unpack_value(v, payload)) for k, v in index)
 
 
 def args_to_parameters(args, version: int) -> dict:

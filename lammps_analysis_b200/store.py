@@ -8,6 +8,13 @@ kept: ``add_dataset / add_data / check_existence / get_data_size / load_data``.
 HBM residency: ``device(path, ...)`` returns a CUDA tensor of (a row range of) a dataset and
 keeps it cached, so that consecutive calculators do not re-upload; uploads go through pinned
 host staging in bounded chunks.
+
+Multi-rank (one process per GPU): the store is ATOM-SHARDED.  Every per-species dataset keeps
+its global shape, but a rank owns the contiguous row block ``distributed.shard_atoms`` assigns
+to it: an in-memory store holds (page-locks, uploads, writes back) only that block; a directory
+store maps the whole file -- created by rank 0, the others wait on a barrier -- and every rank
+reads and writes only its own rows of it.  ``Observables/*`` datasets are replicated.  Row
+arguments and results of the public methods are always GLOBAL row indices.
 """
 from __future__ import annotations
 
@@ -18,6 +25,7 @@ from typing import Dict, Optional, Tuple
 
 import numpy as np
 
+from . import distributed as D
 from .config import config
 
 
@@ -36,9 +44,18 @@ def join_path(*args) -> str:
 
 
 class TrajectoryStore:
-    def __init__(self, directory: Optional[str] = None, pinned: Optional[bool] = None):
+    def __init__(self, directory: Optional[str] = None, pinned: Optional[bool] = None,
+                 sharded: Optional[bool] = None):
         self.directory = directory
+        # the shard geometry is fixed at construction: (rank, world) of the process group, or
+        # (0, 1) for an unsharded store (single process, or sharded=False: the caller keeps a
+        # full private copy per rank, as bench.py's weak-scaling replicas do)
+        if sharded is None:
+            sharded = D.world_size() > 1
+        self.rank, self.world = (D.rank(), D.world_size()) if sharded else (0, 1)
         self._arrays: Dict[str, np.ndarray] = {}
+        self._rows: Dict[str, int] = {}     # global row count of a dataset
+        self._row0: Dict[str, int] = {}     # global index of the first row of the host array
         # in-memory stores live in page-locked host memory when a GPU is present: uploads and
         # downloads are then single DMA transfers without a staging copy
         if pinned is None:
@@ -68,12 +85,63 @@ class TrajectoryStore:
             with open(self._index_path()) as fh:
                 for path in json.load(fh):
                     if os.path.exists(self._file_of(path)):
-                        self._arrays[path] = np.load(self._file_of(path), mmap_mode="r+")
+                        self._map_file(path)
+
+    def _map_file(self, path: str):
+        arr = np.load(self._file_of(path), mmap_mode="r+")
+        self._arrays[path] = arr
+        self._rows[path] = arr.shape[0]
+        self._row0[path] = 0
 
     def _save_index(self):
-        if self.directory is not None:
+        if self.directory is not None and self._is_writer():
             with open(self._index_path(), "w") as fh:
                 json.dump(sorted(self._arrays), fh)
+
+    # ---- sharding ---------------------------------------------------------------------
+    def _is_writer(self) -> bool:
+        """Rank that creates files and writes the index of a shared directory store."""
+        return self.rank == 0
+
+    def _barrier(self):
+        if self.world > 1:
+            self._check_group()
+            D.barrier()
+
+    def _check_group(self):
+        if self.world != D.world_size():
+            from ._lib import MdkError
+
+            raise MdkError(f"store sharded over {self.world} rank(s) used in a process group of "
+                           f"{D.world_size()} (inside distributed.local_only()?)")
+
+    def is_sharded(self, path: str) -> bool:
+        return self.world > 1 and not path.startswith("Observables/")
+
+    def owned_rows(self, path: str) -> Tuple[int, int]:
+        """Global row range [lo, hi) of ``path`` this rank reads, uploads and writes."""
+        n = self._rows[path]
+        if not self.is_sharded(path):
+            return 0, n
+        self._check_group()
+        return D.shard_atoms(0, n, self.rank, self.world)
+
+    def rows_per_rank(self, path: str):
+        """[(lo, hi)] of every rank, in rank order."""
+        n = self._rows[path]
+        if not self.is_sharded(path):
+            return [(0, n)]
+        return [D.shard_atoms(0, n, r, self.world) for r in range(self.world)]
+
+    def _local(self, path: str, lo: int, hi: int) -> np.ndarray:
+        """Host view of the global rows [lo, hi); they must be held by this rank."""
+        arr, r0 = self._arrays[path], self._row0[path]
+        if hi > lo and (lo < r0 or hi > r0 + arr.shape[0]):
+            from ._lib import MdkError
+
+            raise MdkError(f"rows [{lo}, {hi}) of {path} are not held by rank {self.rank} "
+                           f"(it holds [{r0}, {r0 + arr.shape[0]}))")
+        return arr[lo - r0:hi - r0]
 
     # ---- simulation_database.Database interface ------------------------------------------
     def check_existence(self, path: str) -> bool:
@@ -84,19 +152,33 @@ class TrajectoryStore:
         """simulation_database.py:452-497: float32 dataset of (n_rows, n_frames, n_dims)."""
         if path in self._arrays:
             raise ValueError(f"dataset {path} already exists")
+        shape = tuple(int(s) for s in shape)
+        self._rows[path] = shape[0]
         if self.directory is not None:
-            arr = np.lib.format.open_memmap(self._file_of(path), mode="w+", dtype=np.float32,
-                                            shape=tuple(int(s) for s in shape))
-        elif self.pinned:
-            import torch
-
-            # not zero-filled: every writer (ingest, transformations) covers the whole dataset,
-            # and a memset of gigabytes of page-locked memory costs as much as the transfer
-            t = torch.empty(tuple(int(s) for s in shape), dtype=torch.float32, pin_memory=True)
-            self._pinned[path] = t
-            arr = t.numpy()
+            # one file for the whole dataset: rank 0 creates it, the others map it afterwards
+            if self._is_writer():
+                arr = np.lib.format.open_memmap(self._file_of(path), mode="w+", dtype=np.float32,
+                                                shape=shape)
+                arr.flush()
+            self._barrier()
+            if not self._is_writer():
+                arr = np.load(self._file_of(path), mmap_mode="r+")
+            self._row0[path] = 0
         else:
-            arr = np.zeros(shape, dtype=np.float32)
+            lo, hi = self.owned_rows(path)
+            local = (hi - lo,) + shape[1:]
+            self._row0[path] = lo
+            if self.pinned:
+                import torch
+
+                # not zero-filled: every writer (ingest, transformations) covers the whole
+                # dataset, and a memset of gigabytes of page-locked memory costs as much as the
+                # transfer
+                t = torch.empty(local, dtype=torch.float32, pin_memory=True)
+                self._pinned[path] = t
+                arr = t.numpy()
+            else:
+                arr = np.zeros(local, dtype=np.float32)
         self._arrays[path] = arr
         self._save_index()
         return arr
@@ -118,21 +200,42 @@ class TrajectoryStore:
         old = self._arrays[path]
         if old.shape[1] >= n_frames:
             return old
-        data = np.array(old)
-        del self._arrays[path]
+        lo, hi = self.owned_rows(path)
+        data = np.array(self._local(path, lo, hi))      # this rank's rows survive the resize
+        n_rows = self._rows[path]
+        self._barrier()                                  # everyone has read the old file
+        del self._arrays[path], old
         self._pinned.pop(path, None)
         self.invalidate(path)
-        new = self.add_dataset(path, (old.shape[0], n_frames, old.shape[2]))
-        new[:, : data.shape[1]] = data
-        return new
+        self.add_dataset(path, (n_rows, n_frames, data.shape[2]))
+        self._local(path, lo, hi)[:, : data.shape[1]] = data
+        return self._arrays[path]
 
-    def add_data(self, path: str, data, start: int = 0):
+    def add_data(self, path: str, data, start: int = 0, rows: Optional[Tuple[int, int]] = None):
         """Write ``data`` (n_rows, k, n_dims) at frame offset ``start``; values are rounded to
-        float32 exactly as the HDF5 store does (simulation_database.py:333-378)."""
+        float32 exactly as the HDF5 store does (simulation_database.py:333-378).  ``data``
+        covers the whole dataset (every rank keeps its own block of it), this rank's block, or
+        the global row range ``rows``."""
         self._drain(path)
-        arr = self._arrays[path]
         data = np.asarray(data)
-        arr[:, start : start + data.shape[1]] = data.astype(np.float32, copy=False)
+        lo, hi = self.owned_rows(path)
+        if rows is not None:
+            # data holds the global rows [rows[0], rows[1]): keep what this rank owns of them
+            g0, g1 = int(rows[0]), int(rows[1])
+            lo, hi = max(lo, g0), min(hi, g1)
+            data = data[max(lo - g0, 0):max(hi - g0, 0)]
+        elif data.shape[0] == self._rows[path]:
+            data = data[lo:hi]                           # global array: every rank reads the source
+        elif data.shape[0] != hi - lo:
+            raise ValueError(f"add_data({path}): {data.shape[0]} rows given, expected the whole "
+                             f"dataset ({self._rows[path]}) or this rank's block ({hi - lo})")
+        shared_replica = self.directory is not None and self.world > 1 and \
+            not self.is_sharded(path)
+        if hi > lo and (not shared_replica or self._is_writer()):
+            self._local(path, lo, hi)[:, start:start + data.shape[1]] = \
+                data.astype(np.float32, copy=False)
+        if shared_replica:
+            self._barrier()        # one file for all ranks: rank 0 wrote it
         self.invalidate(path)
 
     def put(self, path: str, array):
@@ -142,29 +245,42 @@ class TrajectoryStore:
             raise ValueError("datasets are (n_rows, n_frames, n_dims)")
         if path in self._arrays:
             self._drain(path)
+            self._barrier()
             del self._arrays[path]
             self._pinned.pop(path, None)
             self.invalidate(path)
-        arr = self.add_dataset(path, array.shape)
-        arr[...] = array.astype(np.float32, copy=False)
-        return arr
+        self.add_dataset(path, array.shape)
+        self.add_data(path, array)
+        return self._arrays[path]
 
     def get_data_size(self, path: str):
         """(n_rows, n_configurations, n_bytes) -- simulation_database.py:683-690."""
-        a = self._arrays[path]
-        return a.shape[0], a.shape[1], int(a.size * 4)
+        n, t, d = self.shape(path)
+        return n, t, int(n * t * d * 4)
 
     def shape(self, path: str):
-        return self._arrays[path].shape
+        """Global shape (n_rows, n_frames, n_dims)."""
+        a = self._arrays[path]
+        return (self._rows[path],) + tuple(a.shape[1:])
 
     def load_data(self, path: str, select_slice=np.s_[:]) -> np.ndarray:
         """Host read as float64 (simulation_database.py:594-639 casts to tf.float64)."""
         self._drain(path)
+        if self.is_sharded(path):
+            # collective: every rank contributes its block (in-memory store) or waits for the
+            # other ranks' writes to the shared file (directory store)
+            if self.directory is None:
+                lo, hi = self.owned_rows(path)
+                whole = D.gather_rows(np.array(self._local(path, lo, hi)), self._rows[path])
+                return np.asarray(whole[select_slice], dtype=np.float64)
+            self._barrier()
         return np.asarray(self._arrays[path][select_slice], dtype=np.float64)
 
     def host(self, path: str) -> np.ndarray:
+        """Host array of the rows this rank owns (the whole dataset for one rank)."""
         self._drain(path)
-        return self._arrays[path]
+        lo, hi = self.owned_rows(path)
+        return self._local(path, lo, hi)
 
     def paths(self):
         return sorted(self._arrays)
@@ -187,7 +303,8 @@ class TrajectoryStore:
 
     def device(self, path: str, rows: Optional[Tuple[int, int]] = None,
                row_index: Optional[np.ndarray] = None, device=None):
-        """CUDA float32 tensor of dataset rows [lo, hi) (or a fancy row selection)."""
+        """CUDA float32 tensor of the global dataset rows [lo, hi) (default: the rows this rank
+        owns) or of a fancy row selection (global indices); the rows must be held by this rank."""
         import torch
 
         from ._lib import MdkError
@@ -195,23 +312,31 @@ class TrajectoryStore:
         if not torch.cuda.is_available():
             raise MdkError("CUDA device required: the trajectory store has no CPU compute path")
         dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-        arr = self._arrays[path]
+        own = self.owned_rows(path)
         if row_index is not None:
             row_index = np.asarray(row_index)
             key = (path, "idx", hash(row_index.tobytes()), str(dev))
         else:
-            lo, hi = (0, arr.shape[0]) if rows is None else (int(rows[0]), int(rows[1]))
+            lo, hi = own if rows is None else (int(rows[0]), int(rows[1]))
             key = (path, lo, hi, str(dev))
         hit = self._device_cache.get(key)
         if hit is not None:
             self._device_cache.move_to_end(key)
             return hit
         if row_index is None:
-            whole = self._device_cache.get((path, 0, arr.shape[0], str(dev)))
-            if whole is not None:
-                return whole[lo:hi]          # rows are the leading axis: a contiguous view
+            whole = self._device_cache.get((path, own[0], own[1], str(dev)))
+            if whole is not None and own[0] <= lo and hi <= own[1]:
+                return whole[lo - own[0]:hi - own[0]]   # rows are the leading axis: a view
         self._drain(path)                    # the host copy is read from here on
-        src = arr[row_index] if row_index is not None else arr[lo:hi]
+        r0 = self._row0[path]
+        if row_index is not None:
+            if len(row_index) and (row_index.min() < r0
+                                   or row_index.max() >= r0 + self._arrays[path].shape[0]):
+                raise MdkError(f"row selection of {path} reaches outside the rows held by rank "
+                               f"{self.rank}")
+            src = self._arrays[path][row_index - r0]
+        else:
+            src = self._local(path, lo, hi)
         nbytes = int(np.prod(src.shape)) * 4
         budget = self._budget()
         while self._device_cache and self._device_bytes + nbytes > budget:
@@ -220,7 +345,7 @@ class TrajectoryStore:
         out = torch.empty(src.shape, dtype=torch.float32, device=dev)
         pin = self._pinned.get(path)
         if pin is not None and row_index is None:
-            out.copy_(pin[lo:hi], non_blocking=True)     # one DMA from page-locked memory
+            out.copy_(pin[lo - r0:hi - r0], non_blocking=True)   # one DMA from page-locked memory
             torch.cuda.current_stream().synchronize()
             self.h2d_bytes += nbytes
         else:
@@ -230,44 +355,57 @@ class TrajectoryStore:
         return out
 
     def pinned_tensor(self, path: str):
-        """The page-locked host tensor behind a dataset of an in-memory store (or None)."""
+        """The page-locked host tensor behind this rank's rows of a dataset of an in-memory
+        store (or None).  Row 0 of the tensor is global row ``owned_rows(path)[0]``."""
         self._drain(path)
         return self._pinned.get(path)
 
     def is_resident(self, path: str) -> bool:
-        return any(k[0] == path and k[1] == 0 and k[2] == self._arrays[path].shape[0]
+        lo, hi = self.owned_rows(path)
+        return any(k[0] == path and k[1] == lo and k[2] == hi
                    for k in self._device_cache if k[1] != "idx")
 
     def adopt_device(self, path: str, tensor):
-        """Register a device tensor that already holds the whole dataset ``path`` (e.g. the
-        output a transformation just produced), so that the next calculator does not re-upload
-        it."""
+        """Register a device tensor that already holds this rank's rows of the dataset ``path``
+        (e.g. the output a transformation just produced), so that the next calculator does not
+        re-upload it."""
         self.invalidate(path)
-        key = (path, 0, int(tensor.shape[0]), str(tensor.device))
+        lo, hi = self.owned_rows(path)
+        if tensor.shape[0] != hi - lo:
+            raise ValueError("adopt_device: tensor does not hold the rows this rank owns")
+        key = (path, lo, hi, str(tensor.device))
         self._device_cache[key] = tensor
         self._device_bytes += tensor.numel() * tensor.element_size()
 
     def device_frames(self, path: str, frames, row_index=None, device=None):
-        """CUDA float32 [rows][len(frames)][dims] holding only the selected frames (not
-        cached): the RDF samples a few frames of a long trajectory."""
+        """CUDA float32 [rows][len(frames)][dims] holding only the selected frames of the rows
+        this rank owns (or of the global row selection ``row_index`` within them); not cached:
+        the RDF samples a few frames of a long trajectory."""
         import torch
 
         self._drain(path)
-        arr = self._arrays[path]
+        lo, hi = self.owned_rows(path)
+        arr = self._local(path, lo, hi)
         frames = np.asarray(frames, dtype=np.int64)
-        src = arr[:, frames] if row_index is None else arr[np.asarray(row_index)][:, frames]
+        src = arr[:, frames] if row_index is None else \
+            arr[np.asarray(row_index) - lo][:, frames]
         dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         out = torch.empty(src.shape, dtype=torch.float32, device=dev)
         self._upload(np.ascontiguousarray(src), out)
         return out
 
-    def write_from_device(self, path: str, tensor, t0: int = 0):
-        """Device tensor (n_rows, k, n_dims) -> frames [t0, t0 + k) of the host dataset."""
+    def write_from_device(self, path: str, tensor, t0: int = 0, row0: Optional[int] = None):
+        """Device tensor (n_rows, k, n_dims) -> frames [t0, t0 + k) of the global rows
+        [row0, row0 + n_rows) of the host dataset (default: the rows this rank owns)."""
         import torch
 
-        arr = self._arrays[path]
+        lo, hi = self.owned_rows(path)
+        row0 = lo if row0 is None else int(row0)
+        arr = self._local(path, row0, row0 + tensor.shape[0])
         k = tensor.shape[1]
         pin = self._pinned.get(path)
+        if pin is not None:
+            pin = pin[row0 - self._row0[path]:row0 - self._row0[path] + tensor.shape[0]]
         if pin is not None:
             # asynchronous write-back on a side stream: PCIe is full duplex, so the copy overlaps
             # the uploads and kernels of whatever runs next; readers of the host copy drain it
@@ -289,10 +427,15 @@ class TrajectoryStore:
         """Delete a dataset (host, disk and device copies)."""
         self._drain(path)
         self.invalidate(path)
+        if self.directory is not None:
+            self._barrier()
         arr = self._arrays.pop(path, None)
         self._pinned.pop(path, None)
+        self._rows.pop(path, None)
+        self._row0.pop(path, None)
         del arr
-        if self.directory is not None and os.path.exists(self._file_of(path)):
+        if self.directory is not None and self._is_writer() and \
+                os.path.exists(self._file_of(path)):
             os.remove(self._file_of(path))
         self._save_index()
 

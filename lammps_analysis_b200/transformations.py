@@ -63,7 +63,12 @@ class _SingleSpeciesTrafo(Transformations):
             paths = [self._require(sp, p) for p in self.input_properties]
             n_atoms, n_frames, _ = exp.store.shape(paths[0])
             exp.store.add_dataset(out_path, (n_atoms, n_frames, self.output_dims))
-            per_frame = n_atoms * 12 * (len(paths) + 1)
+            # every atom is an independent series: a rank transforms the atom block it owns
+            # (store.py) and writes back only those rows -- no communication
+            lo, hi = exp.store.owned_rows(out_path)
+            if hi <= lo:
+                continue
+            per_frame = (hi - lo) * 12 * (len(paths) + 1)
             frames_per_chunk = max(1, min(n_frames, self.chunk_bytes // max(per_frame, 1)))
             carry = None
             whole = None
@@ -142,13 +147,10 @@ class IonicCurrent(Transformations):
         species = list(exp.species) if species is None else species
         self._ensure_inputs(species)
         n_frames = exp.number_of_configurations
-        J = None
+        J = torch.zeros(n_frames, 3, dtype=torch.float64, device="cuda")
         for sp in species:
             vpath = self._require(sp, self.vector_property)
-            n_atoms = exp.store.shape(vpath)[0]
-            lo, hi = D.shard_atoms(0, n_atoms)
-            if J is None:
-                J = torch.zeros(n_frames, 3, dtype=torch.float64, device="cuda")
+            lo, hi = exp.store.owned_rows(vpath)
             if hi <= lo:
                 continue
             vel = exp.store.device(vpath, rows=(lo, hi))
@@ -161,9 +163,7 @@ class IonicCurrent(Transformations):
                 q = float(exp.species[sp].charge)
             K.ionic_current(vel, q, J)
         D.all_reduce_sum_([J])
-        out = exp.store.add_dataset(out_path, (1, n_frames, 3))
-        out[0] = J.cpu().numpy()  # float64 -> float32 store rounding
-        exp.store.invalidate(out_path)
+        exp.store.put(out_path, J.cpu().numpy()[None])  # float64 -> float32 store rounding
 
 
 class TranslationalDipoleMoment(IonicCurrent):
@@ -212,14 +212,11 @@ class _AtomSumObservable(Transformations):
         J = torch.zeros(n_frames, 3, dtype=torch.float64, device="cuda")
         for sp in species:
             paths = [self._require(sp, p) for p in self.input_properties]
-            n_atoms = exp.store.shape(paths[0])[0]
-            lo, hi = D.shard_atoms(0, n_atoms)
+            lo, hi = exp.store.owned_rows(paths[0])
             if hi > lo:
                 self._accumulate(sp, lo, hi, J)
         D.all_reduce_sum_([J])
-        out = exp.store.add_dataset(out_path, (1, n_frames, 3))
-        out[0] = J.cpu().numpy()  # float64 -> float32 store rounding
-        exp.store.invalidate(out_path)
+        exp.store.put(out_path, J.cpu().numpy()[None])  # float64 -> float32 store rounding
 
     def _dev(self, sp, prop, lo, hi):
         return self.experiment.store.device(join_path(sp, prop), rows=(lo, hi))

@@ -80,3 +80,86 @@ def test_two_rank_reduction_equals_single_process(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+# ---------------------------------------------------------------------------------------------
+# atom-sharded store, frame exchange, rank-0 gating of persistent state
+# ---------------------------------------------------------------------------------------------
+def _sharded_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    from lammps_analysis_b200 import distributed as D
+    from lammps_analysis_b200.file_io import ScriptInput
+    from lammps_analysis_b200.project import Project
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(7)            # the same source data on every rank
+        T = 9
+        data = {"Na": {"Positions": rng.random((11, T, 3)).astype(np.float32)},
+                "Cl": {"Positions": rng.random((1, T, 3)).astype(np.float32)}}
+        for persist in (False, True):
+            project = Project("shard", storage_path=os.path.join(out_dir, "proj"),
+                              persist=persist)
+            assert project.sharded
+            exp = project.add_experiment("X", timestep=1.0, temperature=1.0, units="metal")
+            exp.add_data(ScriptInput(data, [4.0, 4.0, 4.0], atom_major=True))
+            st = exp.store
+            for sp, n in (("Na", 11), ("Cl", 1)):
+                path = f"{sp}/Positions"
+                assert st.shape(path) == (n, T, 3)
+                lo, hi = st.owned_rows(path)
+                assert (lo, hi) == D.shard_atoms(0, n, rank, world)
+                assert np.array_equal(st.host(path), data[sp]["Positions"][lo:hi])
+                # host reads of a sharded dataset are collective and return the whole array
+                assert np.array_equal(st.load_data(path), data[sp]["Positions"].astype(float))
+                # the frame exchange hands every rank all atoms of its frames
+                frames = np.array([0, 3, 4, 8, 2])
+                local = torch.from_numpy(np.ascontiguousarray(st.host(path)[:, frames]))
+                full = D.exchange_frames(local, [b - a for a, b in st.rows_per_rank(path)],
+                                         len(frames))
+                mine = D.shard_frames(frames)
+                assert np.array_equal(full.numpy(), data[sp]["Positions"][:, mine])
+            # rows of another rank are refused, not silently read
+            other = D.shard_atoms(0, 11, 1 - rank, world)
+            if not persist:
+                with pytest.raises(Exception):
+                    st._local("Na/Positions", *other)
+            # replicated observable; written once for a shared directory
+            st.put("Observables/J", np.full((1, T, 3), 2.5))
+            assert st.owned_rows("Observables/J") == (0, 1)
+            assert np.array_equal(st.host("Observables/J"), np.full((1, T, 3), 2.5, np.float32))
+            # appended data extends every rank's block (resize keeps the rows it owns)
+            more = {s: {"Positions": rng.random((n, 4, 3)).astype(np.float32)}
+                    for s, n in (("Na", 11), ("Cl", 1))}
+            exp.add_data(ScriptInput(more, [4.0, 4.0, 4.0], atom_major=True, name="more"))
+            lo, hi = st.owned_rows("Na/Positions")
+            want = np.concatenate([data["Na"]["Positions"], more["Na"]["Positions"]], axis=1)
+            assert st.shape("Na/Positions") == (11, T + 4, 3)
+            assert np.array_equal(st.host("Na/Positions"), want[lo:hi])
+            # result cache: rank 0 writes a shared database, every rank gets the same hit
+            params = {"a": 1, "version": exp.version}
+            assert project.find_computation("calc", "X", params) is None
+            project.store_computation("calc", "X", params,
+                                      {"Na": {"x": [float(i) for i in range(40)], "v": 1.5}},
+                                      metadata={"ties": 0})
+            hit = project.find_computation("calc", "X", params)
+            assert hit is not None and hit["Na"]["x"][39] == 39.0 and hit.metadata == {"ties": 0}
+            if persist:
+                assert (project._db is not None) == (rank == 0)
+                dist.barrier()
+                files = os.listdir(os.path.join(out_dir, "proj", "MDSuite_Project_shard", "X",
+                                                "database"))
+                assert "Na__Positions.npy" in files and "index.json" in files
+        open(os.path.join(out_dir, f"sharded_ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_sharded_store_exchange_and_gating(tmp_path):
+    port = _free_port()
+    mp.spawn(_sharded_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "sharded_ok0") and os.path.exists(tmp_path / "sharded_ok1")

@@ -389,7 +389,7 @@ def run_gpu_arm(args):
 
     mdk_config.planner_memory_bytes = 60e9      # the SURVEY.md A.5 plan (C5: 2 atom batches)
     project = Project(f"bench{rank}", storage_path=tempfile.mkdtemp(prefix="mdk_bench_"),
-                      persist=False)
+                      persist=False, sharded=False)   # weak scaling: a private replica per rank
     exp_rdf = project.add_experiment("rdf", timestep=0.002, temperature=300.0, units="real")
     exp_rdf.add_data(ScriptInput({"A": {"Positions": sp_traj[0].cpu().numpy()},
                                   "B": {"Positions": sp_traj[1].cpu().numpy()}},
@@ -434,17 +434,13 @@ def run_gpu_arm(args):
         return rdf, msd_sum, acf_sum
 
     def e2e_dynamics():
-        exp_dyn.run.CoordinateUnwrapper()
-        ein = exp_dyn.run.EinsteinDiffusionCoefficients
-        type(ein).__call__.__wrapped__(ein, data_range=N, plot=False)
-        ein._handle_tau_values()
-        msd_sum, count = ein.compute_msd("A")
-        gk = exp_dyn.run.GreenKuboDiffusionCoefficients
-        type(gk).__call__.__wrapped__(gk, data_range=N, plot=False)
-        acf_sum, count2, win, a_sel = gk.compute_acf("A")
+        # the public calls: Einstein resolves its Unwrapped_Positions dependency by running the
+        # CoordinateUnwrapper transformation; line fit and trapezoid post-processing included
+        ein = exp_dyn.run.EinsteinDiffusionCoefficients(data_range=N, plot=False)
+        gk = exp_dyn.run.GreenKuboDiffusionCoefficients(data_range=N, plot=False)
         exp_dyn.run.IonicCurrent()
         exp_dyn.store.flush()   # the unwrapped positions' write-back (side stream) has landed
-        return msd_sum, acf_sum
+        return np.array(ein["A"]["msd"]), np.array(gk["A"]["acf"])
 
     e2e_step(0, [])
     barrier()
@@ -483,6 +479,13 @@ def run_gpu_arm(args):
         t_msd = probe(lambda: msd_series(unw, l_short, n_short, 1, np.arange(n_short)))
         t_acf = probe(lambda: acf_series(vel, l_short, n_short, 1, per_window=False))
         probes.append((n_short, t_msd, t_acf))
+
+    # ---- strong scaling: the fixed C5 problem through the calculators' own sharding -------------
+    del sp_traj, pos, vel, unw, eng, project, exp_rdf, exp_dyn
+    torch.cuda.empty_cache()
+    strong = None
+    if not args.no_strong:
+        strong = run_strong_leg(args, world, rank, dev, barrier)
 
     if rank != 0:
         if world > 1:
@@ -555,9 +558,10 @@ def run_gpu_arm(args):
                               hbm=hbm_roof(12.0 * shard * n_frames, t["msd_kernel"])),
              "e2e": {"value": 2 * total_upd / e_dyn, "unit": "atom-lag updates/s (MSD+ACF)",
                      "h2d_bytes_per_step": h2d_dyn, "d2h_bytes_per_step": d2h_dyn,
-                     "api": "run.CoordinateUnwrapper() + Einstein.compute_msd + "
-                            "GreenKubo.compute_acf + run.IonicCurrent() on a host-resident "
-                            "store (fits excluded)"}},
+                     "api": "run.EinsteinDiffusionCoefficients(data_range=500) (runs "
+                            "CoordinateUnwrapper, fit included) + "
+                            "run.GreenKuboDiffusionCoefficients(data_range=500) + "
+                            "run.IonicCurrent() on a host-resident store"}},
             {"metric": "acf_atom_lag_updates_per_s", "unit": "atom-lag updates/s",
              "value": total_upd / t["acf_kernels"],
              "roofline": dict(fp32_roof(FLOP_PER_ACF * upd_per_step, t["acf_kernels"]),
@@ -580,6 +584,8 @@ def run_gpu_arm(args):
         for n, t_msd, t_acf in probes
         for k, t in (("msd_stream_kernel", t_msd),
                      ("acf_stream_kernel (+prefix, windows)", t_acf))]
+    if strong is not None:
+        line["strong"] = strong
     if cpu is not None:
         line["cpu_baseline"] = {"value": cpu["rdf"][0], "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": cpu["rdf"][1], "host_cores_available": cores}
@@ -592,6 +598,117 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+def run_strong_leg(args, world, rank, dev, barrier):
+    """Time-to-solution of the FIXED C5 problem at `world` ranks, through the public calculator
+    API and the product's own sharding (no local_only): every rank opens the same project; the
+    store keeps this rank's atom block in page-locked host memory; the RDF shards frames (one
+    all-to-all of the sampled frames + one all-reduce of the histograms), unwrap / MSD / ACF
+    run on the rank's atom block (all-reduce of the series).  Inputs are host resident, results
+    land on the host; fits and post-processing are inside the timed region."""
+    import torch
+
+    from lammps_analysis_b200.config import config as mdk_config
+    from lammps_analysis_b200.file_io import ScriptInput
+    from lammps_analysis_b200.project import Project
+    from lammps_analysis_b200.synthetic import device_fluid
+    import tempfile
+
+    small = args.small
+    n_sp = N_SPECIES_ATOMS if not small else 16_000
+    n_frames = args.strong_frames or (N_FRAMES if not small else 600)
+    N = DATA_RANGE if not small else 100
+    n_cfg = args.strong_rdf_configs if not small else 8
+    box_l = BOX if not small else (2 * n_sp / DENSITY) ** (1 / 3)
+    box = np.array([box_l] * 3)
+    mdk_config.planner_memory_bytes = 60e9
+    project = Project("strong", storage_path=tempfile.mkdtemp(prefix="mdk_strong_"),
+                      persist=False)          # sharded whenever world > 1
+    exp = project.add_experiment("melt", timestep=0.002, temperature=300.0, units="real")
+    # the same global trajectory for every N: atoms are generated in fixed chunks of 1/8 species
+    # (seeded by species and chunk), each rank makes the chunks of the atom block it owns
+    chunk = n_sp // 8
+    t_setup = time.perf_counter()
+    from lammps_analysis_b200.distributed import shard_atoms
+    data, rows = {}, {}
+    for si, sp in enumerate(("A", "B")):
+        lo, hi = shard_atoms(0, n_sp, rank, world) if world > 1 else (0, n_sp)
+        rows[sp] = (lo, hi)
+        pos_h = torch.empty(hi - lo, n_frames, 3, dtype=torch.float32, pin_memory=True)
+        vel_h = torch.empty(hi - lo, n_frames, 3, dtype=torch.float32, pin_memory=True)
+        for c0 in range(lo, hi, chunk):
+            c1 = min(hi, c0 + chunk)
+            seed = 4000 + 100 * si + c0 // chunk
+            p = device_fluid(c1 - c0, n_frames, box_l, seed, dev, sigma_step=0.4)
+            pos_h[c0 - lo:c1 - lo].copy_(p)
+            del p
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(seed + 50)
+            v = torch.randn(c1 - c0, n_frames, 3, device=dev, generator=gen)
+            vel_h[c0 - lo:c1 - lo].copy_(v)
+            del v
+        data[sp] = {"Positions": pos_h.numpy(), "Velocities": vel_h.numpy()}
+    exp.add_data(ScriptInput(data, box, atom_major=True, rows=rows,
+                             n_particles={"A": n_sp, "B": n_sp}))
+    del data, pos_h, vel_h
+    torch.cuda.empty_cache()
+    t_setup = time.perf_counter() - t_setup
+
+    def reset():
+        exp.store.invalidate()
+        for sp in ("A", "B"):
+            if exp.store.check_existence(f"{sp}/Unwrapped_Positions"):
+                exp.store.remove(f"{sp}/Unwrapped_Positions")
+        exp.version += 1            # defeat the result cache
+        barrier()
+
+    def timed_pass(n_configs):
+        reset()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        h2d0 = exp.store.h2d_bytes
+        w0 = time.perf_counter()
+        marks[0].record()
+        rdf = exp.run.RadialDistributionFunction(number_of_configurations=n_configs, plot=False)
+        marks[1].record()
+        ein = exp.run.EinsteinDiffusionCoefficients(data_range=N, plot=False)
+        marks[2].record()
+        gk = exp.run.GreenKuboDiffusionCoefficients(data_range=N, plot=False)
+        exp.store.flush()           # write-back of the unwrapped positions has landed
+        marks[3].record()
+        barrier()
+        wall = time.perf_counter() - w0
+        t = [marks[i].elapsed_time(marks[i + 1]) * 1e-3 for i in range(3)]
+        tt = torch.tensor(t + [wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return tt.cpu().tolist(), rdf, ein, gk, exp.store.h2d_bytes - h2d0
+
+    timed_pass(2)                   # warm-up: kernels, pinned pools, NCCL channels
+    (t_rdf, t_ein, t_gk, wall), rdf, ein, gk, h2d = timed_pass(n_cfg)
+    n_tot = 2 * n_sp
+    W = n_frames - N                # one frame batch, correlation_time 1 (SURVEY A.5)
+    pairs = n_cfg * n_tot * (n_tot - 1) // 2
+    updates = 2 * W * n_sp * N      # per calculator, both species
+    if rank != 0:
+        return None
+    return {
+        "problem": f"C5 fixed: 2 x {n_sp} atoms x {n_frames} frames host-resident; "
+                   f"RadialDistributionFunction(number_of_configurations={n_cfg}) + "
+                   f"EinsteinDiffusionCoefficients(data_range={N}) (runs CoordinateUnwrapper) + "
+                   f"GreenKuboDiffusionCoefficients(data_range={N}), public calls, fits included",
+        "n_gpus": world, "sharded_store": bool(project.sharded),
+        "t_s": t_rdf + t_ein + t_gk, "t_rdf_s": t_rdf, "t_einstein_s": t_ein,
+        "t_green_kubo_s": t_gk, "wall_s": wall,
+        "rdf_pair_distances_per_s": pairs / t_rdf,
+        "dynamics_atom_lag_updates_per_s": 2 * updates / (t_ein + t_gk),
+        "h2d_bytes_this_rank": h2d, "setup_s": t_setup,
+        "D_A": ein["A"]["diffusion_coefficient"], "gk_D_A": gk["A"]["diffusion_coefficient"][0],
+        "rdf_checksum": float(np.nansum(np.array(rdf["A_B"]["y"])[1:])),
+        "note": "time-to-solution is the max over ranks (CUDA events around the public calls); "
+                "speed-up at N GPUs = t_s(1) / t_s(N) of the driver's per-N runs",
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -600,6 +717,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--small", action="store_true", help="reduced sizes (debug only; not a bench)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true",
+                    help="skip the fixed-problem (strong scaling) leg")
+    ap.add_argument("--strong-frames", type=int, default=None,
+                    help="frames of the strong-scaling trajectory (default: the full 2,000)")
+    ap.add_argument("--strong-rdf-configs", type=int, default=64)
     args = ap.parse_args()
 
     if args.gpus > 1 and "RANK" not in os.environ:

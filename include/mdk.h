@@ -121,6 +121,19 @@ int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad, const int*
                  int nbins, const float* thr, unsigned long long* hist,
                  unsigned int* work_counter, const float* bbox, int flags, mdk_stream_t stream);
 
+/* Bin-edge tie census of one packed frame ([3][n_pad], as mdk_rdf_hist takes it): for the pairs
+ * (i, j > i) of its first n_rows atoms against all atoms,
+ *   out[0] += pairs inside the cutoff,
+ *   out[1] += pairs whose reference bin (threshold table = tf.histogram_fixed_width's
+ *             double-step rule on the correctly rounded fp32 distance) differs from the bin of
+ *             a plain fp32 histogram, floor(sqrt_rn(d2) * float(nbins / cutoff)).
+ * out: device u64[2], accumulated.  flags: MDK_RDF_EXACT_DIV as for mdk_rdf_hist.  The pair
+ * kernel itself always takes the reference bin; this is the "tie count reported" of the parity
+ * criterion (radial_distribution_function.py:616-645). */
+int mdk_rdf_tie_count(const float* pos_frame, long long n_pad, long long n_rows, const float* box,
+                      float cut2, float cutoff, int nbins, const float* thr, int flags,
+                      unsigned long long* out, mdk_stream_t stream);
+
 /* Spatially ordered variant of mdk_rdf_pack for ONE frame of one species: the atoms are written
  * in Hilbert-curve order of a 128^3 cell grid (the histogram does not depend on the order of the atoms
  * inside a species block), NaN padded as above.  `workspace` is device scratch of at least

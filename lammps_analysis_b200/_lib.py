@@ -39,6 +39,7 @@ PROTOTYPES = {
     "mdk_gather_frames": [_P, _LL, _LL, _P, _I, _P, _P],
     "mdk_coord_extent": [_P, _I, _LL, _P, _P],
     "mdk_rdf_hist": [_P, _I, _LL, _P, _P, _I, _P, _F, _F, _I, _P, _P, _P, _P, _I, _P],
+    "mdk_rdf_tie_count": [_P, _LL, _LL, _P, _F, _F, _I, _P, _I, _P, _P],
     "mdk_rdf_sort_workspace": [_I],
     "mdk_rdf_pack_sorted": [_P, _LL, _LL, _LL, _I, _LL, _P, _LL, _LL, _I, _P, _P, _LL, _P],
     "mdk_rdf_bbox": [_P, _I, _LL, _P, _P],

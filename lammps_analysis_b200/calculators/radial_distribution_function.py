@@ -111,7 +111,8 @@ class RadialDistributionFunction(TrajectoryCalculator):
                                 self.args.number_of_bins, drop_first=self.parity_mode)
         if len(frame_ids):
             self.engine.add_frames(trajs, frame_ids)
-        D.all_reduce_sum_([self.engine.hist])
+        D.all_reduce_sum_([self.engine.hist, self.engine.tie_counts])
+        self.tie_report = self.engine.tie_report()
         return self.engine.counts()
 
     def _bulk_upload_pays(self, paths, n_sampled: int) -> bool:
@@ -223,6 +224,9 @@ class RadialDistributionFunction(TrajectoryCalculator):
     def run_calculator(self):
         self.check_input()
         counts = self.compute_counts()
+        # bin counts are bit-exact with the reference rule; this is how many of the sampled
+        # pairs sit on an fp32 bin edge (Computation.metadata["tie_report"])
+        self.queue_metadata(tie_report=self.tie_report)
         x = (self.experiment.units.length / 1e-9) * np.linspace(0.0, self.args.cutoff,
                                                                 self.args.number_of_bins)
         self.counts = {}

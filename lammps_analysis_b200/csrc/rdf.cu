@@ -1102,6 +1102,54 @@ __global__ void coord_extent_kernel(const float* __restrict__ pos, long long n_p
   }
 }
 
+// Bin-edge tie census (north_star: "bit-exact away from fp32 bin-edge ties, tie count
+// reported").  For the pairs (i, j > i) of the first `n_rows` atoms of a packed frame against
+// all atoms, the reference's bin -- double-step rule on the correctly rounded fp32 distance,
+// i.e. the threshold table the pair kernel uses -- is compared with the bin a plain fp32
+// histogram would take, floor(sqrt_rn(d2) * float(nbins / cutoff)).  out[0] += pairs inside the
+// cutoff, out[1] += pairs whose two bins differ: those sit on a bin edge to within fp32
+// rounding, and they are the only pairs an fp32-binning implementation could count differently.
+__global__ void rdf_tie_count_kernel(const float* __restrict__ pos, long long n_pad,
+                                     long long n_rows, const float* __restrict__ thr, int nbins,
+                                     float cut2, float inv_step, float box0, float box1,
+                                     float box2, int exact, unsigned long long* __restrict__ out) {
+  unsigned long long in_cut = 0, ties = 0;
+  const float L[3] = {box0, box1, box2};
+  const long long total = n_rows * n_pad;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / n_pad, j = e - i * n_pad;
+    if (j <= i) continue;
+    float d2 = 0.f, sq[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      float r = __fsub_rn(__ldg(pos + d * n_pad + j), __ldg(pos + d * n_pad + i));
+      if (exact)
+        r = __fsub_rn(r, __fmul_rn(rintf(__fdiv_rn(r, L[d])), L[d]));
+      else
+        r = fmaf(__fadd_rn(fmaf(r, 1.0f / L[d], RINT_MAGIC), -RINT_MAGIC), -L[d], r);
+      sq[d] = __fmul_rn(r, r);
+    }
+    d2 = __fadd_rn(__fadd_rn(sq[0], sq[1]), sq[2]);
+    if (!(d2 < cut2)) continue;  // also drops NaN padding
+    ++in_cut;
+    const float t = fmaf(sqrt_approx(d2), inv_step, RINT_MAGIC);
+    const unsigned g = min(__float_as_uint(t) - RINT_MAGIC_BITS, (unsigned)nbins);
+    const int k_ref = (int)g - (d2 >= __ldg(thr + g) ? 0 : 1);
+    const int k_f32 = min((int)floorf(__fmul_rn(__fsqrt_rn(d2), inv_step)), nbins - 1);
+    ties += (k_ref != k_f32);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    in_cut += __shfl_xor_sync(0xffffffffu, in_cut, o);
+    ties += __shfl_xor_sync(0xffffffffu, ties, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (in_cut) atomicAdd(out, in_cut);
+    if (ties) atomicAdd(out + 1, ties);
+  }
+}
+
 template <int NT, int R, bool EXACT, int AM, bool CULL>
 int launch_rdf(const RdfParams& P, size_t smem, int grid, cudaStream_t s) {
   auto kern = rdf_pair_hist_kernel<NT, R, EXACT, AM, CULL>;
@@ -1230,6 +1278,25 @@ extern "C" int mdk_coord_extent(const float* pos_soa, int n_frames, long long n_
   const long long cap = (long long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   coord_extent_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(pos_soa, n_pad, total, minmax);
+  MDK_LAUNCH_CHECK();
+  return MDK_OK;
+}
+
+extern "C" int mdk_rdf_tie_count(const float* pos_frame, long long n_pad, long long n_rows,
+                                 const float* box, float cut2, float cutoff, int nbins,
+                                 const float* thr, int flags, unsigned long long* out,
+                                 mdk_stream_t stream) {
+  MDK_CHECK_ARG(pos_frame && box && thr && out, "rdf_tie_count: null pointer");
+  MDK_CHECK_ARG(nbins >= 1 && cutoff > 0.f && cut2 > 0.f && n_pad >= 0 && n_rows >= 0 &&
+                    n_rows <= n_pad, "rdf_tie_count: bad sizes");
+  if (n_rows == 0 || n_pad == 0) return MDK_OK;
+  const float inv_step = static_cast<float>(static_cast<double>(nbins) / static_cast<double>(cutoff));
+  long long blocks = (n_rows * n_pad + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  rdf_tie_count_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      pos_frame, n_pad, n_rows, thr, nbins, cut2, inv_step, box[0], box[1], box[2],
+      (flags & MDK_RDF_EXACT_DIV) ? 1 : 0, out);
   MDK_LAUNCH_CHECK();
   return MDK_OK;
 }

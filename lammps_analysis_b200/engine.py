@@ -48,6 +48,7 @@ class RdfEngine:
 
     # species at least this large are Morton-ordered per frame so that whole blocks of pairs
     # beyond the cutoff can be skipped; below it a tile spans too much of the box to gain
+    TIE_ROWS = 1024
     SORT_BATCH_FRAMES = 16
     SORT_MIN_ATOMS = 80_000    # measured on B200 (uniform-image kernel): -9 % at 50k atoms,
                                # +5 % at 100k, +24 % at 200k, +50 % at 10^6
@@ -82,6 +83,11 @@ class RdfEngine:
         self._bbox = None
         self.record_events = False      # bench.py: CUDA events around every mdk_rdf_hist launch
         self.kernel_events = []
+        # bin-edge tie census on the first packed frame (rows sampled: the first TIE_ROWS atoms
+        # against all atoms); 0 disables it
+        self.tie_rows = self.TIE_ROWS
+        self.tie_counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self._tie_done = False
 
     # pair-distance evaluations per frame (all i<j pairs of the full system)
     def pairs_per_frame(self) -> int:
@@ -148,6 +154,10 @@ class RdfEngine:
                 exact = True
             # coordinates inside one box length: min(|d|, L - |d|) is the minimum image
             wrapped = bool(np.all(span < self.box))
+        if self.tie_rows and not self._tie_done and n_frames:
+            K.rdf_tie_count(pos_soa, self.layout, self.tie_rows, self.box, self.cutoff,
+                            self.nbins, self.thr, self.cut2, self.tie_counts, exact_div=exact)
+            self._tie_done = True
         if self.record_events:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -158,6 +168,17 @@ class RdfEngine:
             e1.record()
             self.kernel_events.append((e0, e1))
         self.frames_done += n_frames
+
+    def tie_report(self) -> dict:
+        """{"pairs_checked", "ties", ...}: see mdk_rdf_tie_count (synchronises)."""
+        checked, ties = (int(v) for v in self.tie_counts.cpu().tolist())
+        return {"pairs_checked": checked, "ties": ties,
+                "sample": f"first packed frame, pairs (i, j > i) of the first {self.tie_rows} "
+                          "atoms against all atoms, inside the cutoff",
+                "definition": "pairs whose bin under the reference rule (double-step "
+                              "histogram_fixed_width on the correctly rounded fp32 distance; "
+                              "what the kernel counts) differs from plain fp32 binning "
+                              "floor(sqrt(d2) * float(nbins / cutoff))"}
 
     def counts(self) -> np.ndarray:
         """int64 [n_pairs][nbins] (device -> host, synchronises)."""

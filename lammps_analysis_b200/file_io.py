@@ -72,21 +72,31 @@ class ScriptInput:
 
     def __init__(self, data: Dict[str, Dict[str, np.ndarray]], box_l, sample_rate: int = 1,
                  charges: Optional[Dict[str, float]] = None, atom_major: bool = False,
-                 name: str = "script"):
+                 name: str = "script", rows: Optional[Dict[str, tuple]] = None,
+                 n_particles: Optional[Dict[str, int]] = None):
+        """``rows`` / ``n_particles`` (multi-rank ingest of an atom-sharded store): the arrays of
+        species ``sp`` hold only the global atom rows ``rows[sp] = (lo, hi)`` of its
+        ``n_particles[sp]`` atoms -- every rank passes the block it owns instead of the whole
+        trajectory."""
         self.name = name
         self.box_l = [float(b) for b in box_l]
         self.sample_rate = int(sample_rate)
         self.charges = charges or {}
         self.atom_major = atom_major
         self.data = data
+        self.rows = rows
+        self.n_particles = n_particles
+        if (rows is None) != (n_particles is None):
+            raise ValueError("rows and n_particles go together")
 
     def arrays(self):
+        """Yields (species, property, atom-major array, global row range or None)."""
         for sp, props in self.data.items():
             for prop, arr in props.items():
                 arr = np.asarray(arr)
                 if not self.atom_major:
                     arr = np.swapaxes(arr, 0, 1)  # simulation_database.py:364-368
-                yield sp, prop, arr
+                yield sp, prop, arr, (self.rows[sp] if self.rows is not None else None)
 
     @property
     def metadata(self) -> TrajectoryMetadata:
@@ -96,6 +106,8 @@ class ScriptInput:
             for prop, arr in props.items():
                 shape = np.shape(arr)
                 n_part = shape[0] if self.atom_major else shape[1]
+                if self.n_particles is not None:
+                    n_part = int(self.n_particles[sp])
                 n_cfg = shape[1] if self.atom_major else shape[0]
                 infos.append(PropertyInfo(prop, shape[2]))
             species.append(SpeciesInfo(sp, n_part, infos, charge=self.charges.get(sp, 0)))

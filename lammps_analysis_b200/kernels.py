@@ -270,6 +270,25 @@ def rdf_hist(pos_soa: torch.Tensor, n_frames: int, layout: RdfLayout, box, cutof
     _count()
 
 
+def rdf_tie_count(pos_frame: torch.Tensor, layout: RdfLayout, n_rows: int, box, cutoff: float,
+                  nbins: int, thr_dev: torch.Tensor, cut2: float, out: torch.Tensor,
+                  exact_div: bool = False):
+    """out[0] += in-cutoff pairs of the first n_rows atoms of one packed frame, out[1] += those
+    whose reference bin differs from a plain fp32 bin (bin-edge ties; mdk.h)."""
+    _need_cuda(pos_frame, torch.float32, "rdf_tie_count pos")
+    _need_cuda(thr_dev, torch.float32, "rdf_tie_count thr")
+    _need_cuda(out, torch.int64, "rdf_tie_count out")
+    if pos_frame.numel() < 3 * layout.n_pad or out.numel() != 2 or thr_dev.numel() != nbins + 1:
+        raise MdkError("rdf_tie_count: bad shapes")
+    box32 = np.asarray(box, dtype=np.float32)
+    check(_lib.load().mdk_rdf_tie_count(_ptr(pos_frame), layout.n_pad, int(min(n_rows, layout.n_pad)),
+                                        box32.ctypes.data_as(C.c_void_p), C.c_float(cut2),
+                                        C.c_float(cutoff), int(nbins), _ptr(thr_dev),
+                                        _lib.MDK_RDF_EXACT_DIV if exact_div else 0, _ptr(out),
+                                        _stream()), "mdk_rdf_tie_count")
+    _count()
+
+
 # --------------------------------------------------------------------------------------
 # Einstein MSD / Green-Kubo ACF
 # --------------------------------------------------------------------------------------

@@ -219,8 +219,8 @@ class Experiment:
                 else:
                     self.store.resize_dataset(path, total)
         if isinstance(proc, ScriptInput):
-            for sp, prop, arr in proc.arrays():
-                self.store.add_data(join_path(sp, prop), arr, start=offset)
+            for sp, prop, arr, rows in proc.arrays():
+                self.store.add_data(join_path(sp, prop), arr, start=offset, rows=rows)
         else:
             pos = offset
             for chunk in proc.get_configurations_generator():

@@ -72,6 +72,13 @@ def test_c1_rdf_bit_exact_and_normalised(nacl_c1):
         assert np.isnan(y[0]) or np.isinf(y[0])          # Q2: r[0] = 0
         np.testing.assert_allclose(y[1:], yr[1:], rtol=RTOL)
     assert ties == 0, f"{ties} bins differ from the oracle"
+    # north_star "tie count reported": the census of pairs on an fp32 bin edge is stored with
+    # the result (outside data_dict, whose keys stay the reference's) and survives the cache
+    rep = res.metadata["tie_report"]
+    assert rep["pairs_checked"] > 100_000 and 0 <= rep["ties"] < rep["pairs_checked"] // 1000
+    again = exp.run.RadialDistributionFunction(number_of_configurations=100, plot=False)
+    assert again.id == res.id and again.metadata["tie_report"] == rep
+    assert set(res.data_dict) == {"Na_Na", "Na_Cl", "Cl_Cl"}
 
 
 def test_cache_returns_stored_computation(nacl_c1):
@@ -522,6 +529,41 @@ def test_flux_transformations_match_oracle(tmp_path, cuda):
         np.testing.assert_allclose(got[0], ref, rtol=2e-7, atol=1e-6 * np.abs(ref).max())
     # a second call finds the datasets and skips (transformations.py:572-579)
     exp.run.MomentumFlux()
+
+
+def test_thermal_flux_from_an_ingested_lammps_dump(tmp_path, cuda):
+    """A dump with c_KE, c_PE and c_Stress[1..6] columns is ingested under the reference's
+    property names (lammps_trajectory_files.py:56-57 -> Kinetic_Energy / Potential_Energy), so
+    the thermal-flux transformation and the calculators behind it find their inputs."""
+    from lammps_analysis_b200.file_io import write_lammps_dump
+    from lammps_analysis_b200.project import Project
+    from oracle import transformations as ot
+
+    rng = np.random.default_rng(77)
+    box = [9.0, 9.0, 9.0]
+    data = {}
+    for sp, n in (("Na", 7), ("Cl", 5)):
+        data[sp] = {
+            "Positions": (rng.random((n, 12, 3)) * 9).astype(np.float32),
+            "Velocities": rng.normal(size=(n, 12, 3)).astype(np.float32),
+            "Kinetic_Energy": rng.uniform(0.5, 1.5, size=(n, 12, 1)).astype(np.float32),
+            "Potential_Energy": rng.normal(-3, 0.3, size=(n, 12, 1)).astype(np.float32),
+            "Stress": rng.normal(size=(n, 12, 6)).astype(np.float32),
+        }
+    dump = str(tmp_path / "flux.lammpstraj")
+    write_lammps_dump(dump, data, box)
+    assert "c_KE c_PE c_Stress[1]" in open(dump).read(400)
+    project = Project("dumpflux", storage_path=str(tmp_path))
+    exp = project.add_experiment("NaCl", timestep=0.002, temperature=300.0, units="metal",
+                                 simulation_data=dump)
+    for prop in ("Kinetic_Energy", "Potential_Energy", "Stress"):
+        assert np.array_equal(exp.store.host(f"Na/{prop}"), data["Na"][prop])
+    exp.run.ThermalFlux()
+    ref = ot.thermal_flux_transform_batch({s: {k: data[s][k] for k in
+                                               ("Stress", "Velocities", "Kinetic_Energy",
+                                                "Potential_Energy")} for s in data})
+    got = exp.store.host("Observables/Thermal_Flux")[0]
+    np.testing.assert_allclose(got, ref, rtol=2e-7, atol=1e-6 * np.abs(ref).max())
 
 
 @pytest.mark.parametrize("which", ["thermal", "viscosity"])

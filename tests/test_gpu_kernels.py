@@ -75,6 +75,47 @@ def test_rdf_kernel_variants_agree(cuda, tuning):
     assert np.array_equal(base.counts(), var.counts())
 
 
+def test_rdf_tie_census_matches_numpy(cuda):
+    """mdk_rdf_tie_count: in-cutoff pairs of the sampled rows and the number whose reference
+    bin (double-step rule) differs from plain fp32 binning, against the same two rules in
+    NumPy.  The engine's packed frame drops the first atom of each species (Q1)."""
+    import torch
+    from lammps_analysis_b200 import kernels as K
+    from lammps_analysis_b200.engine import RdfEngine, to_device_f32
+    from oracle import rdf as orc
+
+    F32 = np.float32
+    data, box_arr = _nacl(1000, 1, 32.0, seed=11)
+    species = ["Na", "Cl"]
+    cutoff = orc.default_cutoff(box_arr)
+    nbins = 9000                      # fine bins: a few dozen ties among ~2e5 sampled pairs
+    eng = RdfEngine([500, 500], box_arr, cutoff, nbins, device=cuda)
+    eng.tie_rows = 300
+    eng.add_frames([to_device_f32(data[s]["Positions"], cuda) for s in species], [0])
+    rep = eng.tie_report()
+    # the same census on the host: packed order = Na[1:], Cl[1:]
+    P = np.concatenate([data[s]["Positions"][1:, 0, :] for s in species]).astype(F32)
+    box = np.asarray(box_arr, dtype=F32)
+    i, j = np.triu_indices(len(P), k=1)
+    keep = i < 300
+    i, j = i[keep], j[keep]
+    r = P[j] - P[i]
+    r = r - np.rint(r / box) * box
+    sq = r * r
+    d = np.sqrt((sq[:, 0] + sq[:, 1]) + sq[:, 2])
+    d = d[d < F32(cutoff)]
+    step = float(F32(cutoff)) / float(nbins)
+    k_ref = np.minimum(d.astype(np.float64) / step, nbins - 1).astype(np.int32)
+    inv_step = F32(float(nbins) / float(F32(cutoff)))
+    k_f32 = np.minimum(np.floor(d * inv_step), nbins - 1).astype(np.int32)
+    assert rep["pairs_checked"] == len(d)
+    assert rep["ties"] == int(np.count_nonzero(k_ref != k_f32))
+    assert 0 < rep["ties"] < len(d) // 100
+    # a second batch does not repeat the census
+    eng.add_frames([to_device_f32(data[s]["Positions"], cuda) for s in species], [0])
+    assert eng.tie_report()["pairs_checked"] == len(d)
+
+
 def test_rdf_exact_division_mode(cuda):
     """cutoff >= L/2 forces the true-division minimum image; still bit-exact."""
     from lammps_analysis_b200.engine import RdfEngine, to_device_f32

@@ -341,6 +341,60 @@ def test_cache_protocol_with_fake_calculator(tmp_path):
     assert Fake(experiment=again.experiments["e"])().id == both["e"].id
 
 
+def test_reopened_project_keeps_units_and_results(tmp_path):
+    """experiment.py:188-191: the unit system is a stored property -- a re-opened experiment
+    must not fall back to REAL; results come back from a JSON + float64 record (never
+    unpickled), with identical structure and values."""
+    import sqlite3
+
+    from lammps_analysis_b200.file_io import ScriptInput
+    from lammps_analysis_b200.project import Project, decode_results, encode_results
+    from lammps_analysis_b200.units import METAL, REAL, Units
+
+    project = Project("u", storage_path=str(tmp_path))
+    exp = project.add_experiment("e", timestep=0.5, temperature=3.0, units="metal")
+    exp.add_data(ScriptInput({"Na": {"Positions": np.zeros((3, 2, 3))}}, [1, 1, 1]))
+    custom = Units(time=2.0, length=3.0, energy=4.0, NkTV2p=5.0, boltzmann=6.0, temperature=7.0,
+                   pressure=8.0)
+    project.add_experiment("c", timestep=0.5, temperature=3.0, units=custom)
+    series = np.linspace(0.0, 1.0, 500)
+    results = {"Na": {"x": series.tolist(), "y": [float("nan"), float("inf")] + [0.25] * 30,
+                      "value": 1.5, "list": [1.0, 2.0], "nested": {"k": [3, 4]}, "none": None},
+               "System": {"msd": (series**2).tolist(), "n": 3}}
+    params = {"a": 1, "version": exp.version}
+    project.store_computation("Calc", "e", params, results, metadata={"tie_report": {"ties": 0}})
+
+    again = Project("u", storage_path=str(tmp_path))
+    assert again.experiments["e"].units == METAL and again.experiments["e"].units != REAL
+    assert again.experiments["c"].units == custom
+    assert again.experiments["e"].time_step == 0.5
+    # units given explicitly on re-creation still win over nothing stored (new experiment)
+    assert again.add_experiment("new", timestep=1.0, temperature=1.0).units == REAL
+    got = again.find_computation("Calc", "e", params)
+    assert got.keys() == ["Na", "System"] and got.metadata == {"tie_report": {"ties": 0}}
+    assert got["Na"]["x"] == series.tolist() and got["System"]["msd"] == (series**2).tolist()
+    assert np.isnan(got["Na"]["y"][0]) and np.isinf(got["Na"]["y"][1])
+    assert got["Na"]["value"] == 1.5 and got["Na"]["list"] == [1.0, 2.0]
+    assert got["Na"]["nested"] == {"k": [3, 4]} and got["Na"]["none"] is None
+    assert got["System"]["n"] == 3
+    # the stored record is the documented format, not a pickle
+    blob = sqlite3.connect(os.path.join(str(tmp_path), "MDSuite_Project_u", "project.db")) \
+        .execute("SELECT results FROM computations").fetchone()[0]
+    assert bytes(blob[:8]) == b"MDKR0001" and b"pickle" not in bytes(blob[:64])
+    assert decode_results(encode_results(results))["Na"]["x"] == series.tolist()
+    with pytest.raises(ValueError):
+        decode_results(b"\x80\x05" + bytes(30))     # a pickle stream is refused, not loaded
+
+
+def test_lammps_column_names_follow_the_reference():
+    """lammps_trajectory_files.py:39-66 + mdsuite_properties.py:80-81."""
+    from lammps_analysis_b200.file_io import var_names
+
+    assert var_names["Kinetic_Energy"] == ["c_KE"] and var_names["Potential_Energy"] == ["c_PE"]
+    assert "KE" not in var_names and "PE" not in var_names
+    assert len(var_names["Stress"]) == 6
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "lammps_analysis_b200")
     for dirpath, _, files in os.walk(pkg):

@@ -481,6 +481,7 @@ def run_gpu_arm(args):
         probes.append((n_short, t_msd, t_acf))
 
     # ---- strong scaling: the fixed C5 problem through the calculators' own sharding -------------
+    spatial_sort = eng.spatial_sort
     del sp_traj, pos, vel, unw, eng, project, exp_rdf, exp_dyn
     torch.cuda.empty_cache()
     strong = None
@@ -542,7 +543,7 @@ def run_gpu_arm(args):
                          algorithmic="20 FLOP per pair-distance x 4.999995e11 pairs per launch "
                                      "(all i<j pairs count, including the blocks the kernel "
                                      "proves to lie beyond the cutoff and skips)",
-                         spatial_sort=eng.spatial_sort,
+                         spatial_sort=spatial_sort,
                          tflops=rdf_tflops),
         "e2e": {"value": pairs_per_frame * steps * world / e_rdf, "unit": UNIT,
                 "h2d_bytes_per_step": h2d_rdf, "d2h_bytes_per_step": d2h_rdf,

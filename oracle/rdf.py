@@ -304,3 +304,24 @@ def rdf_counts_direct(positions: np.ndarray, offsets, counts_n, box_array, cutof
                 h += np.bincount(k, minlength=nbins)
             out[(a, b)] = h
     return out
+
+
+def rdf_counts_slab(rows: np.ndarray, cols: np.ndarray, box_array, cutoff, nbins,
+                    chunk_rows: int = 8) -> np.ndarray:
+    """Histogram of ALL (row, column) pair distances of one frame -- a rows x columns slab of
+    the pair matrix, evaluated with get_dij's fp32 arithmetic (:647-689, linalg.py:84-99) and
+    binned by histogram_fixed_width, a few rows at a time so that a 10^6-column slab fits in
+    memory.  rows: (R, 3), cols: (C, 3) float32.  Used to check the pair kernel against the
+    oracle at full system size (the species-pair block A x B of a frame is such a slab)."""
+    box = np.asarray(box_array, dtype=F32)
+    cutoff_f32 = F32(cutoff)
+    rows = np.asarray(rows, dtype=F32)
+    cols = np.asarray(cols, dtype=F32)
+    h = np.zeros(nbins, dtype=np.int64)
+    for r0 in range(0, len(rows), chunk_rows):
+        r = cols[None, :, :] - rows[r0:r0 + chunk_rows, None, :]
+        r = apply_minimum_image(r, box)
+        sq = r * r
+        d = np.sqrt((sq[..., 0] + sq[..., 1]) + sq[..., 2]).ravel()
+        h += histogram_fixed_width(d[d < cutoff_f32], [0, cutoff], nbins)
+    return h

@@ -154,6 +154,40 @@ int mdk_rdf_bbox(const float* pos_soa, int n_frames, long long n_pad, float* bbo
                  mdk_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
+ * Angular distribution function
+ * (mdsuite/calculators/angular_distribution_function.py, utils/neighbour_list.py)
+ * ------------------------------------------------------------------------- */
+
+/* Bytes of device scratch mdk_adf_hist needs for a batch (cell lists + cell-ordered copy of
+ * the positions); -1 on bad arguments.  box is a HOST float[3]. */
+long long mdk_adf_workspace(long long n_atoms, int n_frames, const float* box, float cutoff);
+
+/* Triplet-angle histograms of a batch of frames.
+ *   pos      : [n_frames][n_atoms][3] fp32, species concatenated in order (device)
+ *   sp_hi    : HOST int[n_species], exclusive end of each species block (sp_hi[last] = n_atoms)
+ *   box      : HOST float[3]; coordinates may lie outside the box
+ *   cutoff   : neighbour cutoff; the test is the reference's half(|r|) < half(cutoff), |r| != 0
+ *   nbins, range_hi : uniform bins on [0, range_hi] (the reference uses 3.15), numpy.histogram's
+ *              bin rule on fp32 edges
+ *   norm_power : weight of a triple = 1 / (|r_ij| |r_ik|)^norm_power
+ *   capacity : neighbours per centre atom held in shared memory; when a centre has more,
+ *              *overflow is raised to that count (atomicMax), the centre is skipped, and the
+ *              caller repeats the batch with a larger capacity
+ *   hist_w   : device fp64 [n_combos][nbins], += sum of weights; hist_c: u64, += triple counts;
+ *              combo order = combinations_with_replacement(species, 3) as (centre, j, k)
+ *   overflow : device int, caller-zeroed
+ * For every centre i and every ORDERED pair of distinct neighbours (j, k) whose species
+ * satisfy s_i <= s_j <= s_k: angle = acos(clip(u_ij . u_ik)), u = r / |r|,
+ * r_ij = (p_i - p_j) - rint((p_i - p_j) / L) * L in fp32.
+ * Replaces: utils/neighbour_list.py:53-177 (all-pairs r_ij, n^3 roll-and-compare triplets),
+ *           utils/linalg.py:30-81 (get_angles),
+ *           angular_distribution_function.py:302-403 (r_ij matrix, species masks, histogram). */
+int mdk_adf_hist(const float* pos, int n_frames, long long n_atoms, const int* sp_hi,
+                 int n_species, const float* box, float cutoff, int nbins, double range_hi,
+                 double norm_power, int capacity, double* hist_w, unsigned long long* hist_c,
+                 int* overflow, void* workspace, long long workspace_bytes, mdk_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
  * Einstein MSD / Green-Kubo ACF
  * ------------------------------------------------------------------------- */
 

@@ -1,4 +1,5 @@
 """Hot-path calculators behind the MDSuite names (mdsuite/calculators/__init__.py:29-87)."""
+from .angular_distribution_function import AngularDistributionFunction
 from .coordination_number_calculation import CoordinationNumbers
 from .einstein_diffusion_coefficients import EinsteinDiffusionCoefficients
 from .einstein_helfand_ionic_conductivity import EinsteinHelfandIonicConductivity
@@ -13,6 +14,7 @@ from .radial_distribution_function import RadialDistributionFunction
 __all__ = [
     "RadialDistributionFunction",
     "CoordinationNumbers",
+    "AngularDistributionFunction",
     "EinsteinDiffusionCoefficients",
     "GreenKuboDiffusionCoefficients",
     "GreenKuboIonicConductivity",

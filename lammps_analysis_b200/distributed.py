@@ -140,3 +140,25 @@ def exchange_frames(local, rows_per_rank, n_frames: int):
     recv = local.new_empty(sum(out_splits))
     d.all_to_all_single(recv, send.contiguous(), out_splits, in_splits)
     return recv.view(int(sum(rows_per_rank)), f_of[r], 3)
+
+
+def exchange_frame_groups(local, rows_per_rank, frames_per_rank):
+    """As ``exchange_frames`` for an arbitrary frame ownership: the frames along axis 1 of
+    ``local`` [A_local][F][3] are grouped by owning rank (``frames_per_rank[q]`` consecutive
+    frames go to rank q); returns [sum(rows_per_rank)][frames_per_rank[rank]][3]."""
+    import torch
+
+    d = _dist()
+    if d is None or d.get_world_size() == 1:
+        return local
+    w, r = d.get_world_size(), d.get_rank()
+    a_loc = local.shape[0]
+    if a_loc != rows_per_rank[r] or local.shape[1] != int(sum(frames_per_rank)):
+        raise ValueError("exchange_frame_groups: local block does not match the layout")
+    starts = np.concatenate([[0], np.cumsum(frames_per_rank)]).astype(int)
+    send = torch.cat([local[:, starts[q]:starts[q + 1]].reshape(-1) for q in range(w)])
+    in_splits = [a_loc * int(f) * 3 for f in frames_per_rank]
+    out_splits = [int(n) * int(frames_per_rank[r]) * 3 for n in rows_per_rank]
+    recv = local.new_empty(sum(out_splits))
+    d.all_to_all_single(recv, send.contiguous(), out_splits, in_splits)
+    return recv.view(int(sum(rows_per_rank)), int(frames_per_rank[r]), 3)

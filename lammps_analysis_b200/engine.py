@@ -185,6 +185,68 @@ class RdfEngine:
         return self.hist.view(self.layout.n_pairs, self.nbins).cpu().numpy()
 
 
+class AdfEngine:
+    """Triplet-angle histograms per frame batch for every species triple (centre, j, k) with
+    a <= b <= c.  Restates AngularDistributionFunction._build_histograms
+    (angular_distribution_function.py:365-403) over the cell-list kernels of csrc/adf.cu: one
+    ``add_batch`` per reference batch returns that batch's un-normalised weight sums and triple
+    counts (the reference density-normalises every batch on its own before summing)."""
+
+    BIN_RANGE_HI = 3.15          # "a chemist's pi" (:192)
+
+    def __init__(self, counts, box, cutoff: float, nbins: int, norm_power, device=None,
+                 capacity: int = None):
+        self.device = _device(device)
+        self.counts = [int(c) for c in counts]
+        self.sp_hi = np.cumsum(self.counts).astype(np.int32)
+        self.n_atoms = int(self.sp_hi[-1]) if len(self.counts) else 0
+        self.box = np.asarray(box, dtype=np.float32)
+        self.cutoff = float(cutoff)
+        self.nbins = int(nbins)
+        self.norm_power = float(norm_power)
+        ns = len(self.counts)
+        self.n_combos = ns * (ns + 1) * (ns + 2) // 6
+        if capacity is None:
+            # three times the mean neighbour count of a uniform system, at least 64
+            rho = self.n_atoms / float(np.prod(self.box.astype(np.float64)))
+            capacity = max(64, int(3 * rho * 4.19 * self.cutoff**3))
+        self.capacity = int(min(max(capacity, 1), 8192))
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._work = None
+        self.max_batch_bytes = 1 << 30
+
+    def add_batch(self, pos: torch.Tensor):
+        """pos: CUDA float32 [F][N][3] (species concatenated).  Returns (weights float64
+        [n_combos][nbins], counts int64 [n_combos][nbins]) of this batch, on the device."""
+        F, N, _ = pos.shape
+        if N != self.n_atoms:
+            raise MdkError("AdfEngine: positions do not match the declared species counts")
+        hw = torch.zeros(self.n_combos * self.nbins, dtype=torch.float64, device=self.device)
+        hc = torch.zeros(self.n_combos * self.nbins, dtype=torch.int64, device=self.device)
+        step = max(1, int(self.max_batch_bytes // max(N * 16, 1)))
+        for f0 in range(0, F, step):
+            chunk = pos[f0:f0 + step].contiguous()
+            while True:
+                need = K.adf_workspace(N, chunk.shape[0], self.box, self.cutoff)
+                if self._work is None or self._work.numel() < need:
+                    self._work = torch.empty(need, dtype=torch.uint8, device=self.device)
+                w, c = torch.zeros_like(hw), torch.zeros_like(hc)
+                self.overflow.zero_()
+                K.adf_hist(chunk, self.sp_hi, self.box, self.cutoff, self.nbins,
+                           self.BIN_RANGE_HI, self.norm_power, self.capacity, w, c,
+                           self.overflow, self._work)
+                over = int(self.overflow.item())
+                if over == 0:
+                    hw += w
+                    hc += c
+                    break
+                if over > 8192:
+                    raise MdkError(f"AdfEngine: {over} neighbours within the cutoff of one atom "
+                                   "exceed the supported 8192")
+                self.capacity = min(8192, max(over, 2 * self.capacity))   # redo this chunk
+        return hw.view(self.n_combos, self.nbins), hc.view(self.n_combos, self.nbins)
+
+
 def plan_windows(plan: dict, data_range: int, correlation_time: int, n_atoms: int):
     """Expand a reference batch plan (oracle-free restatement of data_manager.py:156-339)
     into launch descriptors (a_lo, a_hi, t0, B, W)."""

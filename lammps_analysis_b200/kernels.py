@@ -290,6 +290,51 @@ def rdf_tie_count(pos_frame: torch.Tensor, layout: RdfLayout, n_rows: int, box, 
 
 
 # --------------------------------------------------------------------------------------
+# Angular distribution function
+# --------------------------------------------------------------------------------------
+def adf_workspace(n_atoms: int, n_frames: int, box, cutoff: float) -> int:
+    box32 = np.asarray(box, dtype=np.float32)
+    n = int(_lib.load().mdk_adf_workspace(int(n_atoms), int(n_frames),
+                                          box32.ctypes.data_as(C.c_void_p), C.c_float(cutoff)))
+    if n < 0:
+        raise MdkError("adf_workspace: bad arguments")
+    return n
+
+
+def adf_hist(pos: torch.Tensor, sp_hi, box, cutoff: float, nbins: int, range_hi: float,
+             norm_power: float, capacity: int, hist_w: torch.Tensor, hist_c: torch.Tensor,
+             overflow: torch.Tensor, workspace: torch.Tensor):
+    """hist_w / hist_c [n_combos][nbins] += weights / counts of the triplet angles of a batch of
+    frames ``pos`` [F][N][3]; ``overflow`` (int32[1], zeroed by the caller) reports a
+    neighbour count beyond ``capacity``.
+
+    Replaces utils/neighbour_list.py:53-177, utils/linalg.py:30-81 and
+    angular_distribution_function.py:302-403.
+    """
+    _need_cuda(pos, torch.float32, "adf_hist pos")
+    _need_cuda(hist_w, torch.float64, "adf_hist hist_w")
+    _need_cuda(hist_c, torch.int64, "adf_hist hist_c")
+    _need_cuda(overflow, torch.int32, "adf_hist overflow")
+    _need_cuda(workspace, torch.uint8, "adf_hist workspace")
+    F, N, D = pos.shape
+    if D != 3:
+        raise MdkError("adf_hist: positions must be [F][N][3]")
+    sp = np.asarray(sp_hi, dtype=np.int32)
+    ns = len(sp)
+    n_combos = ns * (ns + 1) * (ns + 2) // 6
+    if hist_w.numel() != n_combos * nbins or hist_c.numel() != n_combos * nbins:
+        raise MdkError("adf_hist: histograms must hold n_combos * nbins values")
+    box32 = np.asarray(box, dtype=np.float32)
+    check(_lib.load().mdk_adf_hist(_ptr(pos), F, N, sp.ctypes.data_as(C.c_void_p), ns,
+                                   box32.ctypes.data_as(C.c_void_p), C.c_float(cutoff),
+                                   int(nbins), C.c_double(range_hi), C.c_double(norm_power),
+                                   int(capacity), _ptr(hist_w), _ptr(hist_c), _ptr(overflow),
+                                   _ptr(workspace), workspace.numel(), _stream()),
+          "mdk_adf_hist")
+    _count(4)
+
+
+# --------------------------------------------------------------------------------------
 # Einstein MSD / Green-Kubo ACF
 # --------------------------------------------------------------------------------------
 def msd_windowed(traj: torch.Tensor, a_lo: int, a_hi: int, t0: int, W: int, ct: int,

@@ -539,6 +539,11 @@ class RunComputation:
         return RadialDistributionFunction(**self.kwargs)
 
     @property
+    def AngularDistributionFunction(self):
+        from .calculators import AngularDistributionFunction
+        return AngularDistributionFunction(**self.kwargs)
+
+    @property
     def CoordinationNumbers(self):
         from .calculators import CoordinationNumbers
         return CoordinationNumbers(**self.kwargs)

@@ -1,0 +1,124 @@
+"""Parity of the angular-distribution path (csrc/adf.cu behind AngularDistributionFunction)
+against the NumPy restatement of the reference (oracle/adf.py).
+
+Bars: triple counts per bin are integers -- bit-exact except for angles that sit on an fp32
+bin edge (their number is asserted to be tiny and reported); weight sums and the normalised
+ADF within 1e-5 relative of the bin scale."""
+import itertools
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+MEM = 60e9
+
+
+def _system(seed, counts, n_frames, box, spread=1.0, shift=0.0):
+    rng = np.random.default_rng(seed)
+    box = np.asarray(box, dtype=np.float64)
+    return {f"S{k}": ((rng.random((n, n_frames, 3)) * spread + shift) * box).astype(np.float32)
+            for k, n in enumerate(counts)}
+
+
+def _engine_hist(data, species, box, frames, cutoff, nbins, power, cuda, capacity=None):
+    import torch
+    from lammps_analysis_b200.engine import AdfEngine
+
+    eng = AdfEngine([data[s].shape[0] for s in species], box, cutoff, nbins, power, device=cuda,
+                    capacity=capacity)
+    pos = np.concatenate([data[s][:, frames] for s in species], axis=0).transpose(1, 0, 2)
+    w, c = eng.add_batch(torch.from_numpy(np.ascontiguousarray(pos)).to(cuda))
+    return eng, w.cpu().numpy(), c.cpu().numpy()
+
+
+@pytest.mark.parametrize("counts,box,cutoff,nbins,power,spread,shift,capacity", [
+    ((60, 45), (14.0, 14.0, 14.0), 4.0, 100, 4, 1.0, 0.0, None),      # 3 cells per dimension
+    ((90,), (9.0, 11.0, 10.0), 4.2, 64, 4, 1.0, 0.0, None),           # 2 cells: whole-row stencil
+    ((40, 30, 20), (30.0, 26.0, 21.0), 5.0, 500, 2, 1.0, 0.0, None),  # 3 species: 10 triples
+    ((70, 50), (16.0, 16.0, 16.0), 6.0, 200, 0, 2.6, -0.8, None),     # unwrapped coords, counts only
+    ((120,), (12.0, 12.0, 12.0), 5.5, 80, 4, 1.0, 0.0, 8),            # capacity overflow -> retry
+])
+def test_adf_kernel_matches_oracle(cuda, counts, box, cutoff, nbins, power, spread, shift,
+                                   capacity):
+    from oracle import adf as oadf
+
+    data = _system(5, counts, 3, box, spread, shift)
+    species = list(data)
+    frames = np.array([0, 2])
+    eng, w, c = _engine_hist(data, species, box, frames, cutoff, nbins, power, cuda, capacity)
+    _, raw = oadf.adf_histograms(data, species, box, frames, cutoff, nbins, power, 1,
+                                 return_counts=True)
+    names = ["-".join(t) for t in itertools.combinations_with_replacement(species, 3)]
+    assert len(names) == eng.n_combos
+    ties = 0
+    for p, name in enumerate(names):
+        ref_w, ref_c = raw[name][0]
+        assert c[p].sum() == ref_c.sum(), f"{name}: triple totals differ"
+        diff = np.abs(c[p] - ref_c)
+        ties += int(diff.sum()) // 2          # an angle on a bin edge moves one count
+        assert diff.max() <= 2
+        scale = np.abs(ref_w).max() if ref_w.size else 0.0
+        np.testing.assert_allclose(w[p], ref_w, rtol=1e-5, atol=3e-4 * scale + 1e-30)
+    total = int(c.sum())
+    assert total > 1000
+    assert ties <= max(2, total // 20000), f"{ties} of {total} triples changed bins"
+    if capacity is not None:
+        assert eng.capacity > capacity        # the overflow path was taken
+
+
+def test_adf_calculator_matches_oracle(tmp_path, cuda):
+    """Through the API: default batch plan (one batch: density-normalised once), species keys
+    A_B_C, angle axis, max_peak; then a forced per-frame batching (``batches=`` kwarg)."""
+    from lammps_analysis_b200.config import config
+    from lammps_analysis_b200.file_io import ScriptInput
+    from lammps_analysis_b200.project import Project
+    from oracle import adf as oadf
+
+    config.planner_memory_bytes = MEM
+    box = [15.0, 15.0, 15.0]
+    data = {"Na": _system(9, (80,), 12, box)["S0"], "Cl": _system(10, (64,), 12, box)["S0"]}
+    project = Project("adf", storage_path=str(tmp_path))
+    exp = project.add_experiment("NaCl", timestep=0.002, temperature=1400.0, units="metal")
+    exp.add_data(ScriptInput({s: {"Positions": data[s]} for s in data}, box, atom_major=True))
+    for kwargs, n_batches in (({}, None), ({"batches": 5}, 5)):
+        res = exp.run.AngularDistributionFunction(number_of_configurations=5, cutoff=4.5,
+                                                  number_of_bins=120, plot=False, **kwargs)
+        frames = np.linspace(1, 11, 5, dtype=int)
+        nb = n_batches or oadf.adf_plan({"Na": 80, "Cl": 64}, 12, 5, MEM)
+        assert res.metadata["n_batches"] == nb
+        ref = oadf.adf_finish(oadf.adf_histograms(data, ["Na", "Cl"], box, frames, 4.5, 120, 4,
+                                                  nb), 120)
+        assert res.keys() == ["Na_Na_Na", "Na_Na_Cl", "Na_Cl_Cl", "Cl_Cl_Cl"]
+        for key in res.keys():
+            np.testing.assert_allclose(res[key]["angle"], ref[key]["angle"], rtol=1e-12)
+            y, yr = np.array(res[key]["adf"]), np.array(ref[key]["adf"])
+            np.testing.assert_allclose(y, yr, rtol=1e-4, atol=2e-3 * np.abs(yr).max())
+            assert abs(res[key]["max_peak"] - ref[key]["max_peak"]) <= 3.15 * 180 / 3.14159 / 60
+            assert res.metadata["triples"][key] > 0
+    # integral of a density histogram over its bins is 1 per batch
+    y = np.array(exp.run.AngularDistributionFunction(number_of_configurations=5, cutoff=4.5,
+                                                     number_of_bins=120, plot=False)["Na_Na_Na"]["adf"])
+    assert y.sum() * 3.15 / 120 == pytest.approx(1.0, rel=1e-4)
+
+
+def test_adf_scales_past_the_dense_formulation(cuda):
+    """200,000 atoms: the reference's (n, n, 3) matrix would need 480 GB; the cell-list pass
+    must agree with itself under a permutation of the atoms and count the triples a uniform
+    fluid predicts."""
+    import torch
+    from lammps_analysis_b200.engine import AdfEngine
+
+    gen = torch.Generator(device=cuda)
+    gen.manual_seed(3)
+    n, L, rc = 200_000, 158.74, 6.0           # rho = 0.05
+    pos = (torch.rand(1, n, 3, device=cuda, generator=gen) * L).contiguous()
+    eng = AdfEngine([n], [L] * 3, rc, 500, 4, device=cuda)
+    w, c = eng.add_batch(pos)
+    perm = torch.randperm(n, device=cuda)
+    w2, c2 = AdfEngine([n], [L] * 3, rc, 500, 4, device=cuda).add_batch(pos[:, perm].contiguous())
+    assert torch.equal(c, c2)
+    np.testing.assert_allclose(w.cpu().numpy(), w2.cpu().numpy(), rtol=1e-5,
+                               atol=1e-6 * float(w.max()))
+    nn = 0.05 * 4 / 3 * np.pi * 5.998**3      # float16 cutoff: |r| < 5.998
+    expected = n * nn * nn                    # ordered pairs (j, k), Poisson neighbours
+    assert abs(int(c.sum()) - expected) < 0.02 * expected

@@ -246,6 +246,13 @@ int mdk_unwrap(const float* pos, long long A, long long T, const double* box,
 int mdk_unwrap_indices(const float* pos, const float* img, long long n_atom_frames,
                        const double* box, float* out, mdk_stream_t stream);
 
+/* Forward-difference velocities of one species: out[a][t] = (pos[a][t + 1] - pos[a][t]) / dt
+ * in fp32 for t < T - 1, out[a][T - 1] = out[a][T - 2] (zero when T == 1).
+ *   pos, out : [A][T][3] fp32;  dt = float(time_step) * float(sample_rate)
+ * Replaces transformations/velocity_from_positions.py:62-77. */
+int mdk_velocity_from_positions(const float* pos, long long A, long long T, float dt, float* out,
+                                mdk_stream_t stream);
+
 /* J[t][d] += sum_a q_a * v[a][t][d]   (fp64 accumulation)
  *   q_mode 0: scalar *q (HOST double), 1: q device float [A], 2: q device float [A][T]
  * Replaces: transformations/ionic_current.py:48-58. */

@@ -51,6 +51,7 @@ PROTOTYPES = {
     "mdk_acf_windows": [_P, _I, _I, _I, _I, _P, _P, _P],
     "mdk_unwrap": [_P, _LL, _LL, _P, _P, _I, _P, _P, _P],
     "mdk_unwrap_indices": [_P, _P, _LL, _P, _P, _P],
+    "mdk_velocity_from_positions": [_P, _LL, _LL, _F, _P, _P],
     "mdk_ionic_current": [_P, _LL, _LL, _P, _I, _P, _P],
     "mdk_flux_sum": [_P, _LL, _LL, _I, _I, _P, _P, _P, _P],
     "mdk_thermal_flux": [_P, _P, _P, _P, _LL, _LL, _P, _P],

@@ -117,14 +117,20 @@ class TrajectoryCalculator(Calculator):
 
     # -- dependencies (:117-194) ---------------------------------------------------------------------
     def _run_dependency_check(self):
+        """The loaded property is produced by its transformation when it is missing -- or when
+        the experiment has grown since it was written (the transformation then extends it)."""
         store = self.experiment.store
+        n_cfg = self.experiment.number_of_configurations
+
+        def stale(path):
+            return not store.check_existence(path) or store.shape(path)[1] < n_cfg
+
         if self.system_property:
-            path = join_path("Observables", self.loaded_property)
-            if not store.check_existence(path):
+            if stale(join_path("Observables", self.loaded_property)):
                 self._resolve_dependencies(self.loaded_property)
             return
         for sp in self.args.species:
-            if not store.check_existence(join_path(sp, self.loaded_property)):
+            if stale(join_path(sp, self.loaded_property)):
                 self._resolve_dependencies(self.loaded_property)
                 break
 

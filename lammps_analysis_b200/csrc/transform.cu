@@ -253,9 +253,38 @@ ionic_current_kernel(const float* __restrict__ vel, long long A, long long T3, d
   atomicAdd(J + e, acc);
 }
 
+// v(t) = (x(t + 1) - x(t)) / dt in fp32, the last frame repeats the one before it
+// (velocity_from_positions.py:62-77: roll, subtract, divide, drop and re-append the last value).
+__global__ void velocity_from_positions_kernel(const float* __restrict__ pos, long long A,
+                                               long long T, float dt, float* __restrict__ out) {
+  const long long total = A * T * 3;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long t = (e / 3) % T;
+    const long long src = (t == T - 1 && T > 1) ? e - 3 : e;   // last frame: copy of frame T - 2
+    const float v = T > 1 ? __fdiv_rn(__fsub_rn(__ldg(pos + src + 3), __ldg(pos + src)), dt) : 0.f;
+    out[e] = v;
+  }
+}
+
 }  // namespace mdk
 
 using namespace mdk;
+
+extern "C" int mdk_velocity_from_positions(const float* pos, long long A, long long T, float dt,
+                                           float* out, mdk_stream_t stream) {
+  MDK_CHECK_ARG(A >= 0 && T >= 0, "velocity_from_positions: negative size");
+  if (A == 0 || T == 0) return MDK_OK;
+  MDK_CHECK_ARG(pos && out, "velocity_from_positions: null pointer");
+  MDK_CHECK_ARG(dt != 0.f, "velocity_from_positions: dt must not be zero");
+  long long blocks = (A * T * 3 + 255) / 256;
+  const long long cap = (long long)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  velocity_from_positions_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(pos, A, T, dt,
+                                                                                   out);
+  MDK_LAUNCH_CHECK();
+  return MDK_OK;
+}
 
 extern "C" int mdk_unwrap(const float* pos, long long A, long long T, const double* box,
                           float* carry_pos, int have_carry, double* carry_img, float* out,

@@ -443,6 +443,19 @@ def unwrap_indices(pos: torch.Tensor, img: torch.Tensor, box, out: torch.Tensor)
     _count()
 
 
+def velocity_from_positions(pos: torch.Tensor, dt: float, out: torch.Tensor):
+    """out[a][t] = (pos[a][t + 1] - pos[a][t]) / dt (fp32), last frame repeated.
+    Replaces transformations/velocity_from_positions.py:62-77."""
+    _need_cuda(pos, torch.float32, "velocity_from_positions pos")
+    _need_cuda(out, torch.float32, "velocity_from_positions out")
+    if pos.shape != out.shape or pos.shape[-1] != 3:
+        raise MdkError("velocity_from_positions: bad shapes")
+    A, T, _ = pos.shape
+    check(_lib.load().mdk_velocity_from_positions(_ptr(pos), A, T, C.c_float(dt), _ptr(out),
+                                                  _stream()), "mdk_velocity_from_positions")
+    _count()
+
+
 def ionic_current(vel: torch.Tensor, charge, J: torch.Tensor):
     """J[t][d] += sum_a q_a v[a][t][d].  charge: python float, [A] tensor or [A][T] tensor.
 

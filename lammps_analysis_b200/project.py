@@ -478,6 +478,11 @@ class RunComputation:
         return self._transformation(UnwrapViaIndices)
 
     @property
+    def VelocityFromPositions(self):
+        from .transformations import VelocityFromPositions
+        return self._transformation(VelocityFromPositions)
+
+    @property
     def IonicCurrent(self):
         from .transformations import IonicCurrent
         return self._transformation(IonicCurrent)

@@ -1,18 +1,37 @@
-"""Transformations on the hot path: CoordinateUnwrapper, UnwrapViaIndices, IonicCurrent.
+"""Transformations on the hot path and the driver they share.
 
-Mirrors mdsuite/transformations/transformations.py:171-619 (driver: skip-if-exists, dataset
-creation, input resolution, batch loop with carry-over, float32 save) and the three
-``transform_batch`` bodies (unwrap_coordinates.py:51-81, unwrap_via_indices.py:49-57,
-ionic_current.py:48-58), whose arithmetic runs in ``mdk_unwrap`` / ``mdk_unwrap_indices`` /
-``mdk_ionic_current``.
+Mirrors mdsuite/transformations/transformations.py:
+  :171-237  _save_output (float32 store, system observables get a leading axis of 1)
+  :275-326  _prepare_database_entry  -- create the output dataset, or EXTEND it when the
+            experiment has grown (resize + ``offset``: only the appended frames are computed)
+  :328-350  find_property_per_config / find_property_single_val
+  :352-388  get_prop_through_transformation (property -> transformation table, list = fallbacks)
+  :390-433  input resolution: dataset per configuration -> species value -> experiment value ->
+            recursive transformation -> CannotFindPropertyError
+  :436-519  SingleSpeciesTrafo  (one output dataset per species, batch loop with carry-over)
+  :522-619  MultiSpeciesTrafo   (one system observable ``Observables/<name>`` of shape (1, T, d))
+and the ``transform_batch`` bodies whose arithmetic runs in libmdk: unwrap_coordinates.py:51-81,
+unwrap_via_indices.py:49-57, ionic_current.py:48-58, translational_dipole_moment.py:52-62,
+momentum_flux.py:45-55, thermal_flux.py:51-92, integrated_heat_current.py:49-60,
+velocity_from_positions.py:62-77.
 
-The reference sizes its time batches from host RAM; the results do not depend on that plan
-(the unwrap carry is an exact integer image count, the current is a sum over atoms), so batches
-here are sized by HBM only and the carry is threaded through them the same way.
+Differences that are deliberate:
+* the reference sizes its time batches from host RAM; the results do not depend on that plan
+  (the unwrap carry is an exact integer image count, observables are sums over atoms), so batches
+  here are sized by HBM only and the carry is threaded through them the same way;
+* extending after ``Experiment.add_data``: upstream the single-species loop returns early when
+  the dataset exists (:466-473, leaving a stale, too-short output) and the multi-species path
+  reads the ROW count as the old length (:300-309).  Here both follow the documented intent:
+  the dataset is resized, frames [old length, new length) are computed, and the unwrap carry
+  is rebuilt from the last stored frame so that the extended series is what a single run over
+  the whole trajectory gives;
+* atoms shard across ranks (store.py): a rank transforms / reduces the atom block it owns.
 """
 from __future__ import annotations
 
+import collections.abc
 import logging
+from typing import Dict, Iterable, NamedTuple, Optional
 
 import numpy as np
 
@@ -27,78 +46,245 @@ class CannotFindPropertyError(Exception):
     """transformations.py:61-64."""
 
 
+class CannotFindTransformationError(Exception):
+    """transformations.py:55-58."""
+
+
+class PropertyInfo(NamedTuple):
+    """database/simulation_database.py:43-58."""
+    name: str
+    n_dims: int
+
+
+class _Properties:
+    """database/mdsuite_properties.py:34-87 (the names the hot path touches)."""
+    positions = PropertyInfo("Positions", 3)
+    unwrapped_positions = PropertyInfo("Unwrapped_Positions", 3)
+    velocities = PropertyInfo("Velocities", 3)
+    velocities_from_positions = PropertyInfo("Velocities_From_Positions", 3)
+    box_images = PropertyInfo("Box_Images", 3)
+    box_length = PropertyInfo("Box_Array", 3)
+    charge = PropertyInfo("Charge", 1)
+    ionic_current = PropertyInfo("Ionic_Current", 3)
+    translational_dipole_moment = PropertyInfo("Translational_Dipole_Moment", 3)
+    momentum_flux = PropertyInfo("Momentum_Flux", 3)
+    thermal_flux = PropertyInfo("Thermal_Flux", 3)
+    integrated_heat_current = PropertyInfo("Integrated_Heat_Current", 3)
+    kinetic_energy = PropertyInfo("Kinetic_Energy", 1)
+    potential_energy = PropertyInfo("Potential_Energy", 1)
+    stress = PropertyInfo("Stress", 6)
+    time_step = PropertyInfo("Time_Step", 1)
+    sample_rate = PropertyInfo("Sample_Rate", 1)
+
+
+mdsuite_properties = _Properties()
+
+
+def _as_prop(p) -> PropertyInfo:
+    if isinstance(p, PropertyInfo):
+        return p
+    if hasattr(p, "name") and hasattr(p, "n_dims"):
+        return PropertyInfo(p.name, int(p.n_dims))
+    for v in vars(_Properties).values():
+        if isinstance(v, PropertyInfo) and v.name == p:
+            return v
+    return PropertyInfo(str(p), 3)
+
+
 class Transformations:
+    """Driver shared by all transformations (transformations.py:67-433)."""
+
     input_properties: list = []
-    output_property: str = None
-    output_dims: int = 3
+    output_property = None
     # frames per launch are bounded so that input + output of a chunk stay within this budget
     chunk_bytes: int = 8 << 30
 
-    def __init__(self):
+    def __init__(self, input_properties: Iterable = None, output_property=None,
+                 scale_function: dict = None, dtype=None):
+        ins = input_properties if input_properties is not None else type(self).input_properties
+        self.input_properties = [_as_prop(p) for p in ins]
+        out = output_property if output_property is not None else type(self).output_property
+        self.output_property = _as_prop(out) if out is not None else None
+        self.scale_function = scale_function      # accepted for API parity (host-RAM plan)
         self.experiment = None
+        self.offset = 0
 
-    def _require(self, species: str, prop: str):
-        path = join_path(species, prop)
-        if not self.experiment.store.check_existence(path):
-            raise CannotFindPropertyError(
-                f"While performing transformation '{type(self).__name__}': cannot find "
-                f"'{prop}' for species '{species}' in the database, as a species value or as "
-                f"an experiment value")
-        return path
+    # -- :328-350 ----------------------------------------------------------------------------------
+    def find_property_per_config(self, sp_name: str, prop: PropertyInfo) -> Optional[str]:
+        path = join_path(sp_name, prop.name)
+        return path if self.experiment.store.check_existence(path) else None
+
+    def find_property_single_val(self, sp_name: str, prop: PropertyInfo):
+        species_info = self.experiment.species.get(sp_name)
+        val = getattr(species_info, prop.name.lower(), None) if species_info is not None else None
+        if val is not None:
+            return val
+        return getattr(self.experiment, prop.name.lower(), None)
+
+    # -- :352-388 ----------------------------------------------------------------------------------
+    def get_prop_through_transformation(self, sp_name: str, prop: PropertyInfo) -> Optional[str]:
+        candidates = property_to_transformation_dict().get(prop.name)
+        if candidates is None:
+            raise CannotFindTransformationError(
+                f"was asked to get '{prop.name}' for '{sp_name}', but there is no transformation "
+                "to get that property")
+        if not isinstance(candidates, (list, tuple)):
+            self.experiment.cls_transformation_run(candidates(), species=[sp_name])
+        else:
+            for cls in candidates:          # go through the list until one works
+                try:
+                    self.experiment.cls_transformation_run(cls(), species=[sp_name])
+                except CannotFindPropertyError:
+                    continue
+                break
+            else:
+                raise CannotFindTransformationError(
+                    f"was asked to get '{prop.name}' for '{sp_name}'. There are transformations "
+                    f"to get this property ({candidates}), but none of them have the required "
+                    "data")
+        return self.find_property_per_config(sp_name, prop)
+
+    # -- :390-433 ----------------------------------------------------------------------------------
+    def resolve_inputs(self, species_names):
+        """({species: {property: dataset path}}, {species: {property: constant float64 array}})
+        following the reference's order: per-configuration dataset, species value, experiment
+        value, then a transformation that produces the property."""
+        paths: Dict[str, Dict[str, str]] = {}
+        consts: Dict[str, Dict[str, np.ndarray]] = {}
+        for sp in species_names:
+            paths[sp], consts[sp] = {}, {}
+            for prop in self.input_properties:
+                path = self.find_property_per_config(sp, prop)
+                if path is not None:
+                    paths[sp][prop.name] = path
+                    continue
+                val = self.find_property_single_val(sp, prop)
+                if val is not None:
+                    if not isinstance(val, collections.abc.Iterable):
+                        val = [val]
+                    consts[sp][prop.name] = np.asarray(val, dtype=np.float64)
+                    continue
+                try:
+                    path = self.get_prop_through_transformation(sp, prop)
+                except CannotFindTransformationError:
+                    path = None
+                if path is None:
+                    raise CannotFindPropertyError(
+                        f"While performing transformation '{self.output_property.name}': "
+                        f"Property '{prop.name}' for species '{sp}' cannot be found in the "
+                        "simulation database nor in the simulation metadata, nor can it be "
+                        "obtained by a transformation")
+                paths[sp][prop.name] = path
+        return paths, consts
+
+    # -- :275-326 ----------------------------------------------------------------------------------
+    def _output_path(self, species: str, system_tensor: bool = False):
+        if system_tensor:
+            return 1, join_path("Observables", self.output_property.name)
+        return (self.experiment.species[species].n_particles,
+                join_path(species, self.output_property.name))
+
+    def _is_complete(self, species: str, system_tensor: bool = False) -> bool:
+        _, path = self._output_path(species, system_tensor)
+        store = self.experiment.store
+        return (store.check_existence(path)
+                and store.shape(path)[1] >= self.experiment.number_of_configurations)
+
+    def _prepare_database_entry(self, species: str, system_tensor: bool = False):
+        """Create the output dataset, or extend it when the experiment has grown since it was
+        written (:300-311).  Returns (path, offset): ``offset`` is the first frame that still
+        has to be computed.  Called after the inputs have been resolved, so that a
+        transformation that cannot find its inputs leaves no empty dataset behind."""
+        exp, store = self.experiment, self.experiment.store
+        n_rows, path = self._output_path(species, system_tensor)
+        n_cfg = exp.number_of_configurations
+        if store.check_existence(path):
+            self.offset = store.shape(path)[1]
+            store.resize_dataset(path, n_cfg)
+        else:
+            store.add_dataset(path, (n_rows, n_cfg, self.output_property.n_dims))
+            self.offset = 0
+        return path, self.offset
+
+    def run_transformation(self, species: Iterable[str] = None):
+        raise NotImplementedError
+
+    def transform_batch(self, batch: dict, carryover=None):
+        raise NotImplementedError("transformation of a batch must be implemented")
 
 
-class _SingleSpeciesTrafo(Transformations):
-    """transformations.py:436-519: one output dataset per species."""
+class SingleSpeciesTrafo(Transformations):
+    """transformations.py:436-519: the transformation is applied to each species separately.
 
-    def run_transformation(self, species: list = None):
+    ``transform_batch(batch, carryover)`` receives {property name: CUDA float32 tensor
+    [atoms][frames][dims] | constant float64 array} for the atom block this rank owns and
+    returns the CUDA tensor [atoms][frames][out dims] (or [1][frames][dims], broadcast over the
+    atoms), optionally with a carry-over for the next batch."""
+
+    def initial_carry(self, species: str, paths: dict, offset: int):
+        """Carry-over with which an EXTENDING run starts at frame ``offset`` > 0."""
+        return None
+
+    def run_transformation(self, species: Iterable[str] = None):
         import torch
 
         exp = self.experiment
-        species = list(exp.species) if species is None else species
+        store = exp.store
+        species = list(exp.species) if species is None else list(species)
         for sp in species:
-            out_path = join_path(sp, self.output_property)
-            if exp.store.check_existence(out_path):
-                log.info("%s already exists for %s, skipping", self.output_property, sp)
-                continue  # transformations.py:466-473
-            paths = [self._require(sp, p) for p in self.input_properties]
-            n_atoms, n_frames, _ = exp.store.shape(paths[0])
-            exp.store.add_dataset(out_path, (n_atoms, n_frames, self.output_dims))
+            if self._is_complete(sp):
+                log.info("%s already exists for %s, skipping transformation",
+                         self.output_property.name, sp)
+                continue  # :466-473
+            paths, consts = self.resolve_inputs([sp])
+            paths, consts = paths[sp], consts[sp]
+            out_path, offset = self._prepare_database_entry(sp)
+            n_atoms, n_frames, _ = store.shape(out_path)
             # every atom is an independent series: a rank transforms the atom block it owns
             # (store.py) and writes back only those rows -- no communication
-            lo, hi = exp.store.owned_rows(out_path)
+            lo, hi = store.owned_rows(out_path)
             if hi <= lo:
                 continue
-            per_frame = (hi - lo) * 12 * (len(paths) + 1)
+            dims_in = sum(p.n_dims for p in self.input_properties if p.name in paths)
+            per_frame = (hi - lo) * 4 * (dims_in + self.output_property.n_dims)
             frames_per_chunk = max(1, min(n_frames, self.chunk_bytes // max(per_frame, 1)))
-            carry = None
+            carry = self.initial_carry(sp, paths, offset) if offset else None
             whole = None
-            for t0 in range(0, n_frames, frames_per_chunk):
+            for t0 in range(offset, n_frames, frames_per_chunk):
                 t1 = min(n_frames, t0 + frames_per_chunk)
-                if t0 == 0 and t1 == n_frames:
-                    inputs = [exp.store.device(p) for p in paths]
-                else:
-                    inputs = [torch.from_numpy(np.ascontiguousarray(exp.store.host(p)[:, t0:t1]))
-                              .cuda() for p in paths]
-                out_dev = torch.empty_like(inputs[0])
-                carry = self.transform_batch(inputs, out_dev, carry)
-                exp.store.write_from_device(out_path, out_dev, t0)
-                whole = out_dev if (t0 == 0 and t1 == n_frames) else None
-            exp.store.invalidate(out_path)
+                full = t0 == 0 and t1 == n_frames
+                batch = dict(consts)
+                for name, path in paths.items():
+                    if full:
+                        batch[name] = store.device(path)
+                    else:
+                        batch[name] = torch.from_numpy(
+                            np.ascontiguousarray(store.host(path)[:, t0:t1])).cuda()
+                ret = self.transform_batch(batch, carryover=carry)
+                out_dev, carry = ret if isinstance(ret, tuple) else (ret, carry)
+                if out_dev.shape[0] == 1 and hi - lo != 1:
+                    out_dev = out_dev.expand(hi - lo, -1, -1).contiguous()
+                store.write_from_device(out_path, out_dev, t0)
+                whole = out_dev if full else None
+            store.invalidate(out_path)
             if whole is not None:
-                exp.store.adopt_device(out_path, whole)  # stays resident for the calculator
+                store.adopt_device(out_path, whole)  # stays resident for the calculator
 
 
-class CoordinateUnwrapper(_SingleSpeciesTrafo):
+class CoordinateUnwrapper(SingleSpeciesTrafo):
     """Box-jump unwrapping (unwrap_coordinates.py:51-81)."""
 
-    input_properties = ["Positions"]
-    output_property = "Unwrapped_Positions"
+    input_properties = [mdsuite_properties.positions, mdsuite_properties.box_length]
+    output_property = mdsuite_properties.unwrapped_positions
 
-    def transform_batch(self, inputs, out_dev, carry):
+    def _box(self, batch):
+        return np.asarray(batch["Box_Array"], dtype=np.float64).reshape(3)
+
+    def transform_batch(self, batch, carryover=None):
         import torch
 
-        (pos,) = inputs
-        box = np.asarray(self.experiment.box_array, dtype=np.float64)
+        pos = batch["Positions"]
+        carry = carryover
         if carry is None:
             carry = {
                 "last_pos": torch.zeros(pos.shape[0], 3, dtype=torch.float32, device=pos.device),
@@ -106,64 +292,165 @@ class CoordinateUnwrapper(_SingleSpeciesTrafo):
                                               device=pos.device),
                 "have": False,
             }
-        K.unwrap(pos, box, carry["last_pos"], carry["last_image_box"], carry["have"], out_dev)
+        out = torch.empty_like(pos)
+        K.unwrap(pos, self._box(batch), carry["last_pos"], carry["last_image_box"], carry["have"],
+                 out)
         carry["have"] = True
-        return carry
+        return out, carry
 
-
-class UnwrapViaIndices(_SingleSpeciesTrafo):
-    """pos + box_images * L (unwrap_via_indices.py:49-57)."""
-
-    input_properties = ["Positions", "Box_Images"]
-    output_property = "Unwrapped_Positions"
-
-    def transform_batch(self, inputs, out_dev, carry):
-        pos, img = inputs
-        K.unwrap_indices(pos, img, np.asarray(self.experiment.box_array, dtype=np.float64),
-                         out_dev)
-        return None
-
-
-class IonicCurrent(Transformations):
-    """J(t) = sum_species sum_atoms q v (ionic_current.py:48-58), stored as
-    ``Observables/Ionic_Current`` with shape (1, n_frames, 3) (transformations.py:204-207,
-    289-291).  Atoms shard across ranks; the partial currents are summed with one all-reduce."""
-
-    input_properties = ["Velocities", "Charge"]
-    output_property = "Ionic_Current"
-    vector_property = "Velocities"
-
-    def _ensure_inputs(self, species):
-        pass
-
-    def run_transformation(self, species: list = None):
+    def initial_carry(self, species, paths, offset):
+        """Rebuild (last wrapped position, image count) at frame offset - 1 from what is
+        stored: the image is the integer rint((unwrapped - wrapped) / L)."""
         import torch
 
+        store = self.experiment.store
+        box = np.asarray(self.experiment.box_array, dtype=np.float64)
+        wrapped = np.asarray(store.host(paths["Positions"])[:, offset - 1], dtype=np.float64)
+        out_path = join_path(species, self.output_property.name)
+        unwrapped = np.asarray(store.host(out_path)[:, offset - 1], dtype=np.float64)
+        image = np.rint((unwrapped - wrapped) / box)
+        return {"last_pos": torch.from_numpy(wrapped.astype(np.float32)).cuda(),
+                "last_image_box": torch.from_numpy(image).cuda(), "have": True}
+
+
+class UnwrapViaIndices(SingleSpeciesTrafo):
+    """pos + box_images * L (unwrap_via_indices.py:49-57)."""
+
+    input_properties = [mdsuite_properties.positions, mdsuite_properties.box_images,
+                        mdsuite_properties.box_length]
+    output_property = mdsuite_properties.unwrapped_positions
+
+    def transform_batch(self, batch, carryover=None):
+        import torch
+
+        pos, img = batch["Positions"], batch["Box_Images"]
+        if not isinstance(img, torch.Tensor):
+            # a constant species / experiment value is not an image-flag series
+            raise CannotFindPropertyError("UnwrapViaIndices needs per-configuration Box_Images")
+        out = torch.empty_like(pos)
+        K.unwrap_indices(pos, img, np.asarray(batch["Box_Array"], dtype=np.float64).reshape(3),
+                         out)
+        return out
+
+    def find_property_single_val(self, sp_name, prop):
+        if prop.name == "Box_Images":
+            return None      # only a stored series will do: lets the unwrap fallback kick in
+        return super().find_property_single_val(sp_name, prop)
+
+    def get_prop_through_transformation(self, sp_name, prop):
+        if prop.name == "Box_Images":
+            raise CannotFindTransformationError("no transformation produces Box_Images")
+        return super().get_prop_through_transformation(sp_name, prop)
+
+
+class VelocityFromPositions(SingleSpeciesTrafo):
+    """v(t) = (x(t + dt) - x(t)) / dt on unwrapped positions (velocity_from_positions.py:45-77)."""
+
+    input_properties = [mdsuite_properties.unwrapped_positions, mdsuite_properties.time_step,
+                        mdsuite_properties.sample_rate]
+    output_property = mdsuite_properties.velocities_from_positions
+
+    def transform_batch(self, batch, carryover=None):
+        import torch
+
+        pos = batch["Unwrapped_Positions"]
+        dt = np.float32(np.asarray(batch["Time_Step"]).ravel()[0]) * \
+            np.float32(np.asarray(batch["Sample_Rate"]).ravel()[0])
+        out = torch.empty_like(pos)
+        K.velocity_from_positions(pos, float(dt), out)
+        return out
+
+
+class MultiSpeciesTrafo(Transformations):
+    """transformations.py:522-619: information of several species is combined into one system
+    observable ``Observables/<name>`` of shape (1, n_frames, n_dims).
+
+    ``transform_batch(batch, carryover)`` receives {species: {property: tensor | constant}} for
+    the atom blocks this rank owns and returns a CUDA tensor [1][frames][dims] (float32 or
+    float64).  ``reduces_over_atoms``: the result is a sum over atoms, so the ranks' partial
+    results are added with one all-reduce; a transformation that is not such a sum can only run
+    on one rank."""
+
+    reduces_over_atoms = False
+
+    def run_transformation(self, species: Iterable[str] = None):
         exp = self.experiment
-        out_path = join_path("Observables", self.output_property)
-        if exp.store.check_existence(out_path):
-            log.info("%s already exists, skipping", self.output_property)
-            return  # transformations.py:572-579
-        species = list(exp.species) if species is None else species
-        self._ensure_inputs(species)
-        n_frames = exp.number_of_configurations
-        J = torch.zeros(n_frames, 3, dtype=torch.float64, device="cuda")
+        store = exp.store
+        species = list(exp.species) if species is None else list(species)
+        if self._is_complete(self.output_property.name, system_tensor=True):
+            log.info("%s already exists for this experiment, skipping transformation",
+                     self.output_property.name)
+            return  # :572-579
+        if D.world_size() > 1 and not self.reduces_over_atoms:
+            raise NotImplementedError(f"{type(self).__name__} is not a sum over atoms and cannot "
+                                      "run on an atom-sharded store")
+        paths, consts = self.resolve_inputs(species)
+        out_path, offset = self._prepare_database_entry(self.output_property.name,
+                                                        system_tensor=True)
+        batch = {}
         for sp in species:
-            vpath = self._require(sp, self.vector_property)
-            lo, hi = exp.store.owned_rows(vpath)
-            if hi <= lo:
-                continue
-            vel = exp.store.device(vpath, rows=(lo, hi))
-            qpath = join_path(sp, "Charge")
-            if exp.store.check_existence(qpath):
-                # per-atom-frame charge dataset (A, T, 1)
-                q = exp.store.device(qpath, rows=(lo, hi)).reshape(hi - lo, n_frames).contiguous()
-            else:
-                # species constant (transformations.py:335-350 find_property_single_val)
-                q = float(exp.species[sp].charge)
-            K.ionic_current(vel, q, J)
-        D.all_reduce_sum_([J])
-        exp.store.put(out_path, J.cpu().numpy()[None])  # float64 -> float32 store rounding
+            batch[sp] = dict(consts[sp])
+            for name, path in paths[sp].items():
+                dev = store.device(path)              # the atom block this rank owns
+                batch[sp][name] = dev if offset == 0 else dev[:, offset:].contiguous()
+        ret = self.transform_batch(batch, carryover=None)
+        out_dev = ret[0] if isinstance(ret, tuple) else ret
+        if out_dev.dim() == 2:
+            out_dev = out_dev[None]
+        if self.reduces_over_atoms:
+            D.all_reduce_sum_([out_dev])
+        # float64 -> float32 store rounding (:171-237)
+        store.add_data(out_path, out_dev.cpu().numpy(), start=offset)
+
+
+class _AtomSumObservable(MultiSpeciesTrafo):
+    """Observables that are plain sums over atoms and species, accumulated in fp64 by an
+    HBM-bound reduction kernel (12 B per atom-frame)."""
+
+    reduces_over_atoms = True
+
+    def _accumulate(self, props: dict, J):
+        raise NotImplementedError
+
+    def transform_batch(self, batch, carryover=None):
+        import torch
+
+        n_frames = None
+        for props in batch.values():
+            for v in props.values():
+                if isinstance(v, torch.Tensor):
+                    n_frames = v.shape[1]
+        J = torch.zeros(n_frames, 3, dtype=torch.float64, device="cuda")
+        for props in batch.values():
+            first = next(v for v in props.values() if isinstance(v, torch.Tensor))
+            if first.shape[0] > 0:
+                self._accumulate(props, J)
+        return J[None]
+
+
+def _per_atom_frame(t):
+    """[A][T][1] dataset -> contiguous [A][T]."""
+    return t.reshape(t.shape[0], -1).contiguous()
+
+
+class IonicCurrent(_AtomSumObservable):
+    """J(t) = sum_species sum_atoms q v (ionic_current.py:48-58), stored as
+    ``Observables/Ionic_Current`` with shape (1, n_frames, 3) (transformations.py:204-207,
+    289-291).  The charge is a per-configuration dataset or the species constant."""
+
+    input_properties = [mdsuite_properties.velocities, mdsuite_properties.charge]
+    output_property = mdsuite_properties.ionic_current
+    vector_property = "Velocities"
+
+    def _accumulate(self, props, J):
+        import torch
+
+        q = props["Charge"]
+        if isinstance(q, torch.Tensor):
+            q = _per_atom_frame(q)                       # per-atom-frame charge dataset (A, T, 1)
+        else:
+            q = float(np.asarray(q).ravel()[0])          # species constant (:335-350)
+        K.ionic_current(props[self.vector_property], q, J)
 
 
 class TranslationalDipoleMoment(IonicCurrent):
@@ -171,92 +458,57 @@ class TranslationalDipoleMoment(IonicCurrent):
     same charge-weighted atom reduction as the ionic current, applied to unwrapped positions
     (which are produced first when missing, transformations.py:352-388)."""
 
-    input_properties = ["Unwrapped_Positions", "Charge"]
-    output_property = "Translational_Dipole_Moment"
+    input_properties = [mdsuite_properties.unwrapped_positions, mdsuite_properties.charge]
+    output_property = mdsuite_properties.translational_dipole_moment
     vector_property = "Unwrapped_Positions"
-
-    def _ensure_inputs(self, species):
-        exp = self.experiment
-        missing = [sp for sp in species
-                   if not exp.store.check_existence(join_path(sp, "Unwrapped_Positions"))]
-        if missing:
-            first = next(iter(exp.species))
-            if exp.store.check_existence(join_path(first, "Box_Images")):
-                exp.run.UnwrapViaIndices(species=missing)
-            else:
-                exp.run.CoordinateUnwrapper(species=missing)
-
-
-class _AtomSumObservable(Transformations):
-    """MultiSpeciesTrafo pattern (transformations.py:522-619) for observables that are plain
-    sums over atoms and species: ``Observables/{output_property}`` of shape (1, n_frames, 3).
-    Atoms shard across ranks; the partial sums meet in one all-reduce (as IonicCurrent)."""
-
-    def _ensure_inputs(self, species):
-        pass
-
-    def _accumulate(self, sp, lo, hi, J):
-        raise NotImplementedError
-
-    def run_transformation(self, species: list = None):
-        import torch
-
-        exp = self.experiment
-        out_path = join_path("Observables", self.output_property)
-        if exp.store.check_existence(out_path):
-            log.info("%s already exists, skipping", self.output_property)
-            return  # transformations.py:572-579
-        species = list(exp.species) if species is None else species
-        self._ensure_inputs(species)
-        n_frames = exp.number_of_configurations
-        J = torch.zeros(n_frames, 3, dtype=torch.float64, device="cuda")
-        for sp in species:
-            paths = [self._require(sp, p) for p in self.input_properties]
-            lo, hi = exp.store.owned_rows(paths[0])
-            if hi > lo:
-                self._accumulate(sp, lo, hi, J)
-        D.all_reduce_sum_([J])
-        exp.store.put(out_path, J.cpu().numpy()[None])  # float64 -> float32 store rounding
-
-    def _dev(self, sp, prop, lo, hi):
-        return self.experiment.store.device(join_path(sp, prop), rows=(lo, hi))
 
 
 class MomentumFlux(_AtomSumObservable):
     """Sum over atoms of the off-diagonal stress components xy, xz, yz
     (momentum_flux.py:45-55)."""
 
-    input_properties = ["Stress"]
-    output_property = "Momentum_Flux"
+    input_properties = [mdsuite_properties.stress]
+    output_property = mdsuite_properties.momentum_flux
 
-    def _accumulate(self, sp, lo, hi, J):
-        K.flux_sum(self._dev(sp, "Stress", lo, hi), J, comp0=3)
+    def _accumulate(self, props, J):
+        K.flux_sum(props["Stress"], J, comp0=3)
 
 
 class IntegratedHeatCurrent(_AtomSumObservable):
     """sum_a r_a (KE_a + PE_a) on unwrapped positions (integrated_heat_current.py:49-60)."""
 
-    input_properties = ["Unwrapped_Positions", "Kinetic_Energy", "Potential_Energy"]
-    output_property = "Integrated_Heat_Current"
+    input_properties = [mdsuite_properties.unwrapped_positions, mdsuite_properties.kinetic_energy,
+                        mdsuite_properties.potential_energy]
+    output_property = mdsuite_properties.integrated_heat_current
 
-    def _ensure_inputs(self, species):
-        TranslationalDipoleMoment._ensure_inputs(self, species)
-
-    def _accumulate(self, sp, lo, hi, J):
-        ke = self._dev(sp, "Kinetic_Energy", lo, hi)
-        pe = self._dev(sp, "Potential_Energy", lo, hi)
-        K.flux_sum(self._dev(sp, "Unwrapped_Positions", lo, hi), J, comp0=0,
-                   w1=ke.reshape(hi - lo, -1).contiguous(), w2=pe.reshape(hi - lo, -1).contiguous())
+    def _accumulate(self, props, J):
+        K.flux_sum(props["Unwrapped_Positions"], J, comp0=0,
+                   w1=_per_atom_frame(props["Kinetic_Energy"]),
+                   w2=_per_atom_frame(props["Potential_Energy"]))
 
 
 class ThermalFlux(_AtomSumObservable):
     """sum_a (KE_a + PE_a) v_a - S_a v_a (thermal_flux.py:51-92)."""
 
-    input_properties = ["Stress", "Velocities", "Kinetic_Energy", "Potential_Energy"]
-    output_property = "Thermal_Flux"
+    input_properties = [mdsuite_properties.stress, mdsuite_properties.velocities,
+                        mdsuite_properties.kinetic_energy, mdsuite_properties.potential_energy]
+    output_property = mdsuite_properties.thermal_flux
 
-    def _accumulate(self, sp, lo, hi, J):
-        ke = self._dev(sp, "Kinetic_Energy", lo, hi).reshape(hi - lo, -1).contiguous()
-        pe = self._dev(sp, "Potential_Energy", lo, hi).reshape(hi - lo, -1).contiguous()
-        K.thermal_flux(self._dev(sp, "Stress", lo, hi), self._dev(sp, "Velocities", lo, hi), ke,
-                       pe, J)
+    def _accumulate(self, props, J):
+        K.thermal_flux(props["Stress"], props["Velocities"],
+                       _per_atom_frame(props["Kinetic_Energy"]),
+                       _per_atom_frame(props["Potential_Energy"]), J)
+
+
+def property_to_transformation_dict() -> dict:
+    """transformations/transformation_dict.py:46-63 (hot-path subset): which transformation
+    produces which property; a list is tried in order until one finds its inputs."""
+    return {
+        "Integrated_Heat_Current": IntegratedHeatCurrent,
+        "Ionic_Current": IonicCurrent,
+        "Momentum_Flux": MomentumFlux,
+        "Thermal_Flux": ThermalFlux,
+        "Translational_Dipole_Moment": TranslationalDipoleMoment,
+        "Unwrapped_Positions": [UnwrapViaIndices, CoordinateUnwrapper],
+        "Velocities_From_Positions": VelocityFromPositions,
+    }

@@ -4,7 +4,8 @@ from .coordination_number_calculation import CoordinationNumbers
 from .einstein_diffusion_coefficients import EinsteinDiffusionCoefficients
 from .einstein_helfand_ionic_conductivity import EinsteinHelfandIonicConductivity
 from .einstein_helfand_thermal_conductivity import EinsteinHelfandThermalConductivity
-from .green_kubo_flux_calculators import GreenKuboThermalConductivity, GreenKuboViscosity
+from .green_kubo_flux_calculators import (GreenKuboThermalConductivity, GreenKuboViscosity,
+                                          GreenKuboViscosityFlux)
 from .green_kubo_ionic_conductivity import GreenKuboIonicConductivity
 from .green_kubo_self_diffusion_coefficients import GreenKuboDiffusionCoefficients
 from .kirkwood_buff_integrals import KirkwoodBuffIntegral
@@ -22,6 +23,7 @@ __all__ = [
     "EinsteinHelfandThermalConductivity",
     "GreenKuboThermalConductivity",
     "GreenKuboViscosity",
+    "GreenKuboViscosityFlux",
     "PotentialOfMeanForce",
     "KirkwoodBuffIntegral",
 ]

@@ -85,12 +85,15 @@ class _GreenKuboFlux(TrajectoryCalculator):
         acf, _, wins, _ = acf_series(J, [(0, 1, t0, B, W)], N, ct, per_window=True)
         return acf.cpu().numpy(), wins[0].cpu().numpy()
 
+    def _stored_acf(self, acf_sum: np.ndarray, win: np.ndarray) -> np.ndarray:
+        return self.args.data_range * acf_sum                 # self.jacf += jacf, per window
+
     def run_calculator(self):
         self.check_input()
         prefactor = self._calculate_prefactor()
         acf_sum, win = self.compute_acf()
         N, ir = self.args.data_range, self.args.integration_range
-        jacf = N * acf_sum                                    # self.jacf += jacf, per window
+        jacf = self._stored_acf(acf_sum, win)
         trapz = getattr(np, "trapezoid", None) or np.trapz   # renamed in NumPy 2
         sigma = trapz(N * win[:, :ir], x=self.time[:ir], axis=1)
         result = prefactor * sigma
@@ -113,6 +116,32 @@ class GreenKuboThermalConductivity(_GreenKuboFlux):
         denominator = (3 * (self.args.data_range - 1) * exp.temperature**2 * u.boltzmann
                        * exp.volume)
         return (1 / denominator) * (u.energy / u.length / u.time)
+
+
+class GreenKuboViscosityFlux(_GreenKuboFlux):
+    """green_kubo_viscosity_flux.py:55-290: the autocorrelation of the off-diagonal pressure
+    tensor ``Observables/Stress_Visc`` (pxy, pxz, pyz of a LAMMPS log, read by
+    ``LAMMPSFluxFile``; no transformation produces it).  Restated as the reference computes it:
+    the prefactor carries the volume in the NUMERATOR (:149-165), every window adds the single
+    value ``jacf[data_range - 1]`` to the whole stored series (:199) and the series is then
+    divided by its maximum (:167-175) -- the stored "acf" is therefore constant 1 (NaN when the
+    sum is 0); the reported value / "uncertainty" are the integrals of the first two windows."""
+
+    analysis_name = "Viscosity_Flux"
+    loaded_property = "Stress_Visc"
+    value_key = "viscosity"
+    result_keys = ["viscosity", "uncertainty"]
+
+    def _calculate_prefactor(self) -> float:
+        exp, u = self.experiment, self.experiment.units
+        denominator = 3 * (self.args.data_range - 1) * exp.temperature * u.boltzmann
+        return (exp.volume / denominator) * (u.pressure**2 * u.volume * u.time / u.energy)
+
+    def _stored_acf(self, acf_sum: np.ndarray, win: np.ndarray) -> np.ndarray:
+        N = self.args.data_range
+        jacf = np.zeros(self.data_resolution) + (N * win[:, N - 1]).sum()   # broadcast add
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return jacf / np.max(jacf)
 
 
 class GreenKuboViscosity(_GreenKuboFlux):

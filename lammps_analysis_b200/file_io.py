@@ -274,6 +274,74 @@ class LAMMPSTrajectoryFile:
         return chunk
 
 
+# lammps_flux_files.py:41-50 -- column names of a LAMMPS log / flux table -> property names
+flux_var_names = {
+    "Temperature": ["temp"],
+    "Time": ["time"],
+    "Thermal_Flux": ["c_flux_thermal[1]", "c_flux_thermal[2]", "c_flux_thermal[3]"],
+    "Stress_Visc": ["pxy", "pxz", "pyz"],
+}
+
+
+class LAMMPSFluxFile:
+    """Reader for LAMMPS flux / log tables (lammps_flux_files.py:53-156): ``n_header_lines``
+    lines of header, the last of which names the columns, then one row of numbers per sampled
+    step; reading stops at the first line whose column count differs (log files interleave data
+    blocks with text).  The table carries no box or sample rate, so both are passed in.  Every
+    recognised column group becomes a system observable ``Observables/<Property>`` of shape
+    (1, n_steps, n_dims)."""
+
+    def __init__(self, file_path: str, sample_rate: int, box_l: list, n_header_lines: int = 2,
+                 custom_data_map: Optional[Dict[str, List[str]]] = None):
+        self.file_path = str(file_path)
+        self.sample_rate = int(sample_rate)
+        self.box_l = [float(b) for b in box_l]
+        self.n_header_lines = int(n_header_lines)
+        self.column_names = dict(flux_var_names)
+        if custom_data_map:
+            self.column_names.update(custom_data_map)
+        self._table = None
+
+    def _read(self):
+        if self._table is not None:
+            return
+        with open(self.file_path) as fh:
+            header = [fh.readline() for _ in range(self.n_header_lines)]
+            columns = header[-1].split()
+            rows, n_columns = [], None
+            for line in fh:
+                tok = line.split()
+                if n_columns is None:
+                    n_columns = len(tok)
+                if len(tok) != n_columns or not tok:
+                    break
+                rows.append([_to_float(t) for t in tok])
+        if not rows:
+            raise ValueError(f"{self.file_path}: no data rows after {self.n_header_lines} header lines")
+        if len(columns) > n_columns and columns[0] == "#":
+            columns = columns[1:]          # '# time temp ...' style header
+        self._table = np.asarray(rows, dtype=np.float64)
+        self._props = {prop: [columns.index(c) for c in cols]
+                       for prop, cols in self.column_names.items()
+                       if all(c in columns for c in cols)}
+
+    @property
+    def metadata(self) -> TrajectoryMetadata:
+        self._read()
+        props = [PropertyInfo(p, len(c)) for p, c in self._props.items()]
+        return TrajectoryMetadata(len(self._table), [SpeciesInfo("Observables", 1, props)],
+                                  box_l=self.box_l, sample_rate=self.sample_rate)
+
+    def get_configurations_generator(self, batch_size: int = 4096):
+        self._read()
+        for t0 in range(0, len(self._table), batch_size):
+            block = self._table[t0:t0 + batch_size]
+            chunk = TrajectoryChunkData(len(block))
+            chunk.data["Observables"] = {p: block[None][:, :, cols]
+                                         for p, cols in self._props.items()}
+            yield chunk
+
+
 def _to_float(tok: str) -> float:
     try:
         return float(tok)

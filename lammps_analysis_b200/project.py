@@ -24,7 +24,7 @@ from typing import Dict, List, Optional, Union
 import numpy as np
 
 from . import distributed as D
-from .file_io import LAMMPSTrajectoryFile, ScriptInput, TrajectoryMetadata
+from .file_io import LAMMPSFluxFile, LAMMPSTrajectoryFile, ScriptInput, TrajectoryMetadata
 from .store import TrajectoryStore, join_path
 from .units import Units, resolve_units
 
@@ -202,6 +202,8 @@ class Experiment:
 
     def _add_from_processor(self, proc):
         meta: TrajectoryMetadata = proc.metadata
+        if all(sp.name == "Observables" for sp in meta.species_list):
+            return self._add_observables(proc, meta)
         offset = self.number_of_configurations
         if offset == 0:
             self.box_array = [float(b) for b in meta.box_l]
@@ -230,6 +232,28 @@ class Experiment:
                 pos += chunk.chunk_size
         self.number_of_configurations = total
         self.version += 1  # new data invalidates cached computations (calculator_database.py:139-150)
+
+    def _add_observables(self, proc, meta: TrajectoryMetadata):
+        """System observables from a flux / log table (lammps_flux_files.py): stored as
+        ``Observables/<Property>`` (1, n_steps, n_dims).  Unlike upstream, "Observables" is not
+        registered as a particle species.  An experiment that has no trajectory yet takes its
+        length, box and sample rate from the table."""
+        n = meta.n_configurations
+        if self.number_of_configurations == 0:
+            self.box_array = [float(b) for b in meta.box_l]
+            self.sample_rate = int(meta.sample_rate)
+            self.number_of_configurations = n
+        pos = 0
+        for prop in meta.species_list[0].properties:
+            path = join_path("Observables", prop.name)
+            if self.store.check_existence(path):
+                self.store.remove(path)
+            self.store.add_dataset(path, (1, n, prop.n_dims))
+        for chunk in proc.get_configurations_generator():
+            for prop, arr in chunk.data["Observables"].items():
+                self.store.add_data(join_path("Observables", prop), arr, start=pos)
+            pos += chunk.chunk_size
+        self.version += 1
 
     # -- transformations (experiment.py:270-282) -----------------------------------------------------
     def cls_transformation_run(self, transformation, *args, **kwargs):
@@ -517,6 +541,11 @@ class RunComputation:
     def GreenKuboThermalConductivity(self):
         from .calculators import GreenKuboThermalConductivity
         return GreenKuboThermalConductivity(**self.kwargs)
+
+    @property
+    def GreenKuboViscosityFlux(self):
+        from .calculators import GreenKuboViscosityFlux
+        return GreenKuboViscosityFlux(**self.kwargs)
 
     @property
     def GreenKuboViscosity(self):

@@ -278,3 +278,32 @@ def gk_flux(flux: np.ndarray, plan: dict, data_range: int, correlation_time: int
 def eh_thermal_prefactor(units, temperature, volume):
     denominator = volume * temperature * units.boltzmann
     return (1 / denominator) * (units.energy / units.length / units.time / units.temperature)
+
+
+# --- green_kubo_viscosity_flux.py:149-225 -----------------------------------------------------
+def gk_viscosity_flux_prefactor(units, temperature, volume, data_range):
+    denominator = 3 * (data_range - 1) * temperature * units.boltzmann
+    return (volume / denominator) * (units.pressure**2 * units.volume * units.time / units.energy)
+
+
+def gk_viscosity_flux(flux: np.ndarray, plan: dict, data_range: int, correlation_time: int,
+                      time: np.ndarray, integration_range: int, prefactor: float):
+    """As ``gk_flux`` except for the stored series: ``self.jacf += jacf[data_range - 1:]`` adds
+    ONE value per window to every element (:199), then ``self.jacf /= max(self.jacf)`` (:167-175)."""
+    jacf_sum = np.zeros(data_range)
+    sigma = []
+    for _atom_sel, start, stop, data_size in iter_batches(plan, system=True):
+        batch = np.asarray(flux[start:stop], dtype=np.float64)
+        if batch.shape[0] == 0:
+            raise ValueError("system observable requested with more than one batch (Q7)")
+        for s, e in iter_ensembles(data_size, data_range, correlation_time):
+            ensemble = batch[0, s:e]
+            acf = tfp_auto_correlation(ensemble[None])[0]
+            jacf = data_range * acf.sum(axis=-1)
+            jacf_sum += jacf[int(data_range - 1):]
+            sigma.append(_trapz(jacf[:integration_range], x=time[:integration_range]))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        jacf_sum = jacf_sum / max(jacf_sum)
+    result = prefactor * np.array(sigma)
+    return {"viscosity": result[0], "uncertainty": result[1], "time": np.asarray(time).tolist(),
+            "acf": jacf_sum.tolist()}

@@ -597,6 +597,50 @@ def test_green_kubo_flux_calculators(tmp_path, cuda, which):
     assert got["uncertainty"] == pytest.approx(ref["uncertainty"], rel=1e-4)
 
 
+def test_green_kubo_viscosity_flux_from_a_flux_file(tmp_path, cuda):
+    """GreenKuboViscosityFlux: Stress_Visc read from a LAMMPS flux table by
+    LAMMPSFluxFile, windowed ACF on the device, the reference's reporting (volume in the
+    numerator of the prefactor, first two windows' integrals, normalised constant acf)."""
+    from lammps_analysis_b200.config import config
+    from lammps_analysis_b200.file_io import LAMMPSFluxFile
+    from lammps_analysis_b200.project import Project
+    from lammps_analysis_b200.units import REAL
+    from oracle import dynamics as od
+
+    config.planner_memory_bytes = MEM
+    rng = np.random.default_rng(61)
+    T, N, ir = 900, 120, 100
+    p = np.empty((T, 3))
+    p[0] = rng.normal(size=3)
+    for t in range(1, T):
+        p[t] = 0.95 * p[t - 1] + rng.normal(0, 0.3, size=3)
+    path = str(tmp_path / "visc.lmp")
+    with open(path, "w") as fh:
+        fh.write("# Fix print output\ntime temp pxy pxz pyz\n")
+        for t in range(T):
+            fh.write("%d 300.0 %r %r %r\n" % (t, p[t, 0], p[t, 1], p[t, 2]))
+    box = [20.0, 20.0, 20.0]
+    project = Project("visc", storage_path=str(tmp_path))
+    exp = project.add_experiment("LJ", timestep=0.004, temperature=85.0, units="real",
+                                 simulation_data=LAMMPSFluxFile(path, sample_rate=2, box_l=box))
+    res = exp.run.GreenKuboViscosityFlux(data_range=N, integration_range=ir)
+    J = exp.store.host("Observables/Stress_Visc").astype(np.float64)
+    _, _, _, times = od.handle_tau_values(np.s_[:], N, 0.004, 2)
+    pref = od.gk_viscosity_flux_prefactor(REAL, 85.0, float(np.prod(box)), N)
+    ref = od.gk_viscosity_flux(J, _system_plan(T, N), N, 1, times, ir, pref)
+    got = res["System"]
+    assert set(got) == {"viscosity", "uncertainty", "time", "acf"}
+    assert got["viscosity"] == pytest.approx(ref["viscosity"], rel=1e-4)
+    assert got["uncertainty"] == pytest.approx(ref["uncertainty"], rel=1e-4)
+    np.testing.assert_allclose(got["acf"], ref["acf"], rtol=1e-6)
+    assert np.allclose(got["acf"], 1.0)
+    # no transformation produces Stress_Visc (trajectory_calculator.py:171-174)
+    exp2 = project.add_experiment("empty", timestep=0.004, temperature=85.0, units="real")
+    exp2.box_array, exp2.number_of_configurations = box, T
+    with pytest.raises(KeyError):
+        exp2.run.GreenKuboViscosityFlux(data_range=N)
+
+
 def test_einstein_helfand_thermal_conductivity(tmp_path, cuda):
     from lammps_analysis_b200.units import METAL
     from oracle import dynamics as od

@@ -395,6 +395,52 @@ def test_lammps_column_names_follow_the_reference():
     assert len(var_names["Stress"]) == 6
 
 
+def _write_flux_log(path, table, columns, n_header_lines=2, tail=True):
+    with open(path, "w") as fh:
+        for k in range(n_header_lines - 1):
+            fh.write("# LAMMPS flux output, header line %d\n" % k)
+        fh.write(" ".join(columns) + "\n")
+        for row in table:
+            fh.write(" ".join(repr(float(v)) for v in row) + "\n")
+        if tail:
+            fh.write("Loop time of 12.3 on 4 procs for 1000 steps\n1.0 2.0\n")
+
+
+def test_lammps_flux_file_reader(tmp_path):
+    """lammps_flux_files.py:41-156: header lines, column-name mapping (incl. a custom map),
+    reading stops where the column count changes, observables stored as (1, n_steps, n_dims)."""
+    from lammps_analysis_b200.file_io import LAMMPSFluxFile
+    from lammps_analysis_b200.project import Project
+
+    rng = np.random.default_rng(3)
+    cols = ["time", "temp", "c_flux_thermal[1]", "c_flux_thermal[2]", "c_flux_thermal[3]",
+            "pxy", "pxz", "pyz", "v_extra"]
+    table = rng.normal(size=(37, len(cols)))
+    path = str(tmp_path / "flux.lmp")
+    _write_flux_log(path, table, cols, n_header_lines=3)
+    reader = LAMMPSFluxFile(path, sample_rate=5, box_l=[10.0, 11.0, 12.0], n_header_lines=3,
+                            custom_data_map={"Extra": ["v_extra"]})
+    meta = reader.metadata
+    assert meta.n_configurations == 37 and meta.sample_rate == 5
+    assert [s.name for s in meta.species_list] == ["Observables"]
+    assert {p.name: p.n_dims for p in meta.species_list[0].properties} == {
+        "Temperature": 1, "Time": 1, "Thermal_Flux": 3, "Stress_Visc": 3, "Extra": 1}
+    project = Project("flux", storage_path=str(tmp_path))
+    exp = project.add_experiment("e", timestep=0.001, temperature=300.0, units="real",
+                                 simulation_data=reader)
+    assert exp.number_of_configurations == 37 and exp.box_array == [10.0, 11.0, 12.0]
+    assert "Observables" not in exp.species and exp.sample_rate == 5
+    visc = exp.store.host("Observables/Stress_Visc")
+    assert visc.shape == (1, 37, 3) and visc.dtype == np.float32
+    assert np.array_equal(visc[0], table[:, 5:8].astype(np.float32))
+    assert np.array_equal(exp.store.host("Observables/Extra")[0, :, 0],
+                          table[:, 8].astype(np.float32))
+    with pytest.raises(ValueError):
+        empty = str(tmp_path / "empty.lmp")
+        open(empty, "w").write("# a\ntime temp\n")
+        LAMMPSFluxFile(empty, 1, [1, 1, 1]).metadata
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "lammps_analysis_b200")
     for dirpath, _, files in os.walk(pkg):

@@ -163,10 +163,14 @@ def _cpu_dyn_task(args):
 def cpu_reference(workers: int, rdf_atoms=8000, msd_atoms=160, acf_atoms=32):
     """Times the oracle on `workers` processes (each runs an independent sample of the same
     workload shape).  Returns dict metric -> (units/s, sample description)."""
+    import multiprocessing
     from concurrent.futures import ProcessPoolExecutor
 
     out = {}
-    with ProcessPoolExecutor(max_workers=workers) as ex:
+    # spawn, not fork: the parent may hold a CUDA context, and a forked child that garbage
+    # collects inherited CUDA tensors dies with an initialisation error
+    with ProcessPoolExecutor(max_workers=workers,
+                             mp_context=multiprocessing.get_context("spawn")) as ex:
         def run(task, argl):
             t0 = time.perf_counter()
             res = list(ex.map(task, argl))
@@ -609,7 +613,6 @@ def run_strong_leg(args, world, rank, dev, barrier):
     import torch
 
     from lammps_analysis_b200.config import config as mdk_config
-    from lammps_analysis_b200.file_io import ScriptInput
     from lammps_analysis_b200.project import Project
     from lammps_analysis_b200.synthetic import device_fluid
     import tempfile
@@ -630,27 +633,25 @@ def run_strong_leg(args, world, rank, dev, barrier):
     chunk = n_sp // 8
     t_setup = time.perf_counter()
     from lammps_analysis_b200.distributed import shard_atoms
-    data, rows = {}, {}
-    for si, sp in enumerate(("A", "B")):
-        lo, hi = shard_atoms(0, n_sp, rank, world) if world > 1 else (0, n_sp)
-        rows[sp] = (lo, hi)
-        pos_h = torch.empty(hi - lo, n_frames, 3, dtype=torch.float32, pin_memory=True)
-        vel_h = torch.empty(hi - lo, n_frames, 3, dtype=torch.float32, pin_memory=True)
-        for c0 in range(lo, hi, chunk):
-            c1 = min(hi, c0 + chunk)
-            seed = 4000 + 100 * si + c0 // chunk
-            p = device_fluid(c1 - c0, n_frames, box_l, seed, dev, sigma_step=0.4)
-            pos_h[c0 - lo:c1 - lo].copy_(p)
-            del p
-            gen = torch.Generator(device=dev)
-            gen.manual_seed(seed + 50)
-            v = torch.randn(c1 - c0, n_frames, 3, device=dev, generator=gen)
-            vel_h[c0 - lo:c1 - lo].copy_(v)
-            del v
-        data[sp] = {"Positions": pos_h.numpy(), "Velocities": vel_h.numpy()}
-    exp.add_data(ScriptInput(data, box, atom_major=True, rows=rows,
-                             n_particles={"A": n_sp, "B": n_sp}))
-    del data, pos_h, vel_h
+    from lammps_analysis_b200.file_io import BlockInput
+
+    def blocks():
+        for si, sp in enumerate(("A", "B")):
+            lo, hi = shard_atoms(0, n_sp, rank, world) if world > 1 else (0, n_sp)
+            for c0 in range(lo, hi, chunk):
+                c1 = min(hi, c0 + chunk)
+                seed = 4000 + 100 * si + c0 // chunk
+                p = device_fluid(c1 - c0, n_frames, box_l, seed, dev, sigma_step=0.4)
+                yield sp, "Positions", (c0, c1), p.cpu().numpy()
+                del p
+                gen = torch.Generator(device=dev)
+                gen.manual_seed(seed + 50)
+                v = torch.randn(c1 - c0, n_frames, 3, device=dev, generator=gen)
+                yield sp, "Velocities", (c0, c1), v.cpu().numpy()
+                del v
+
+    props = {"Positions": 3, "Velocities": 3}
+    exp.add_data(BlockInput(n_frames, {"A": (n_sp, props), "B": (n_sp, props)}, box, blocks))
     torch.cuda.empty_cache()
     t_setup = time.perf_counter() - t_setup
 
@@ -684,7 +685,9 @@ def run_strong_leg(args, world, rank, dev, barrier):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return tt.cpu().tolist(), rdf, ein, gk, exp.store.h2d_bytes - h2d0
 
-    timed_pass(2)                   # warm-up: kernels, pinned pools, NCCL channels
+    # warm-up: kernels, NCCL channels, and the page-locked block of the unwrapped positions
+    # (its first allocation costs ~0.4 s per GB on these hosts; the store's pool reuses it)
+    (_, c_ein, c_gk, _), _, _, _, _ = timed_pass(2)
     (t_rdf, t_ein, t_gk, wall), rdf, ein, gk, h2d = timed_pass(n_cfg)
     n_tot = 2 * n_sp
     W = n_frames - N                # one frame batch, correlation_time 1
@@ -703,6 +706,7 @@ def run_strong_leg(args, world, rank, dev, barrier):
         "rdf_pair_distances_per_s": pairs / t_rdf,
         "dynamics_atom_lag_updates_per_s": 2 * updates / (t_ein + t_gk),
         "h2d_bytes_this_rank": h2d, "setup_s": t_setup,
+        "t_dynamics_first_pass_s": c_ein + c_gk,
         "D_A": ein["A"]["diffusion_coefficient"], "gk_D_A": gk["A"]["diffusion_coefficient"][0],
         "rdf_checksum": float(np.nansum(np.array(rdf["A_B"]["y"])[1:])),
         "note": "time-to-solution is the max over ranks (CUDA events around the public calls); "

@@ -18,6 +18,8 @@ class Config:
     planner_memory_bytes: Optional[float] = None
     # device cache budget for store arrays (bytes); None -> 60 % of the free HBM at first use
     device_cache_bytes: Optional[int] = None
+    # page-locked host blocks kept for reuse after a dataset is removed or replaced (store.py)
+    pinned_pool_bytes: int = 96 << 30
     jupyter: bool = False
 
 

@@ -114,6 +114,35 @@ class ScriptInput:
         return TrajectoryMetadata(n_cfg, species, box_l=self.box_l, sample_rate=self.sample_rate)
 
 
+class BlockInput:
+    """Atom-block-wise ingest for trajectories that are produced (or read) a block of atoms at
+    a time and are too large to hold twice: the metadata is given up front, ``blocks()`` then
+    yields ``(species, property, (lo, hi), array[hi - lo][n_frames][n_dims])`` for global atom
+    rows [lo, hi).  Every block is written straight into the store's (page-locked) dataset; on
+    an atom-sharded store a rank keeps the rows it owns, so a producer may skip blocks of other
+    ranks altogether."""
+
+    def __init__(self, n_frames: int, species: Dict[str, tuple], box_l, blocks,
+                 sample_rate: int = 1, charges: Optional[Dict[str, float]] = None,
+                 name: str = "blocks"):
+        """species: name -> (n_particles, {property: n_dims}); blocks: callable -> iterator."""
+        self.name = name
+        self.n_frames = int(n_frames)
+        self.species = species
+        self.box_l = [float(b) for b in box_l]
+        self.sample_rate = int(sample_rate)
+        self.charges = charges or {}
+        self.blocks = blocks
+
+    @property
+    def metadata(self) -> TrajectoryMetadata:
+        sl = [SpeciesInfo(sp, int(n), [PropertyInfo(p, int(d)) for p, d in props.items()],
+                          charge=self.charges.get(sp, 0))
+              for sp, (n, props) in self.species.items()]
+        return TrajectoryMetadata(self.n_frames, sl, box_l=self.box_l,
+                                  sample_rate=self.sample_rate)
+
+
 class LAMMPSTrajectoryFile:
     """Reader for LAMMPS text dumps (``*.lammpstraj``): 9 header lines per frame, then one row
     per atom; rows are sorted by ``id`` per frame; species from the ``element`` column if

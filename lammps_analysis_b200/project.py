@@ -24,7 +24,8 @@ from typing import Dict, List, Optional, Union
 import numpy as np
 
 from . import distributed as D
-from .file_io import LAMMPSFluxFile, LAMMPSTrajectoryFile, ScriptInput, TrajectoryMetadata
+from .file_io import (BlockInput, LAMMPSFluxFile, LAMMPSTrajectoryFile, ScriptInput,
+                      TrajectoryMetadata)
 from .store import TrajectoryStore, join_path
 from .units import Units, resolve_units
 
@@ -220,7 +221,10 @@ class Experiment:
                     self.store.add_dataset(path, (sp.n_particles, total, prop.n_dims))
                 else:
                     self.store.resize_dataset(path, total)
-        if isinstance(proc, ScriptInput):
+        if isinstance(proc, BlockInput):
+            for sp, prop, rows, arr in proc.blocks():
+                self.store.add_data(join_path(sp, prop), arr, start=offset, rows=rows)
+        elif isinstance(proc, ScriptInput):
             for sp, prop, arr, rows in proc.arrays():
                 self.store.add_data(join_path(sp, prop), arr, start=offset, rows=rows)
         else:

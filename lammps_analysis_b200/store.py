@@ -38,6 +38,79 @@ def _cuda_available() -> bool:
         return False
 
 
+class _PinnedBlock:
+    """Exactly-sized page-locked host block: page-aligned memory registered with
+    cudaHostRegister.  (torch's pinned allocator rounds every request up to a power of two --
+    a 12 GB dataset would lock 16 GiB -- and page-locking costs ~0.4 s per GB on the GPU boxes,
+    so the size matters.)"""
+
+    PAGE = 4096
+
+    def __init__(self, nbytes: int):
+        import torch
+
+        self.nbytes = int(nbytes)
+        raw = np.empty(self.nbytes + self.PAGE, dtype=np.uint8)
+        off = (-raw.ctypes.data) % self.PAGE
+        self._raw = raw
+        self.bytes = raw[off:off + self.nbytes]
+        self._registered = False
+        if self.nbytes:
+            rc = torch.cuda.cudart().cudaHostRegister(self.bytes.ctypes.data, self.nbytes, 0)
+            if int(rc) != 0:
+                from ._lib import MdkError
+
+                raise MdkError(f"cudaHostRegister of {self.nbytes} bytes failed with code {int(rc)}")
+            self._registered = True
+
+    def tensor(self, shape):
+        import torch
+
+        n = int(np.prod(shape))
+        return torch.from_numpy(self.bytes[:4 * n].view(np.float32).reshape(shape))
+
+    def __del__(self):
+        if getattr(self, "_registered", False):
+            try:
+                import torch
+
+                torch.cuda.cudart().cudaHostUnregister(self.bytes.ctypes.data)
+            except Exception:  # interpreter shutdown
+                pass
+            self._registered = False
+
+
+class _PinnedPool:
+    """Free list of page-locked blocks keyed by size: a dataset that is removed or replaced
+    hands its block back, the next dataset of that size (a transformation re-run, the next
+    experiment of the same shape) takes it without paying the page-locking again."""
+
+    def __init__(self):
+        self.free: Dict[int, list] = {}
+        self.cached_bytes = 0
+
+    def acquire(self, nbytes: int) -> _PinnedBlock:
+        blocks = self.free.get(nbytes)
+        if blocks:
+            self.cached_bytes -= nbytes
+            return blocks.pop()
+        return _PinnedBlock(nbytes)
+
+    def release(self, block: _PinnedBlock):
+        limit = config.pinned_pool_bytes
+        if block.nbytes == 0 or self.cached_bytes + block.nbytes > limit:
+            return                      # dropped: unregistered when the last reference goes
+        self.free.setdefault(block.nbytes, []).append(block)
+        self.cached_bytes += block.nbytes
+
+    def clear(self):
+        self.free.clear()
+        self.cached_bytes = 0
+
+
+pinned_pool = _PinnedPool()
+
+
 def join_path(*args) -> str:
     """meta_functions.join_path (:73-93): database paths always use '/'."""
     return "/".join(args)
@@ -62,6 +135,7 @@ class TrajectoryStore:
             pinned = directory is None and _cuda_available()
         self.pinned = bool(pinned) and directory is None
         self._pinned: Dict[str, object] = {}
+        self._blocks: Dict[str, _PinnedBlock] = {}
         self._device_cache: "OrderedDict[Tuple, object]" = OrderedDict()
         self._device_bytes = 0
         self.h2d_bytes = 0  # bytes uploaded so far (bench.py reads this)
@@ -169,12 +243,12 @@ class TrajectoryStore:
             local = (hi - lo,) + shape[1:]
             self._row0[path] = lo
             if self.pinned:
-                import torch
-
                 # not zero-filled: every writer (ingest, transformations) covers the whole
                 # dataset, and a memset of gigabytes of page-locked memory costs as much as the
                 # transfer
-                t = torch.empty(local, dtype=torch.float32, pin_memory=True)
+                block = pinned_pool.acquire(int(np.prod(local)) * 4)
+                t = block.tensor(local)
+                self._blocks[path] = block
                 self._pinned[path] = t
                 arr = t.numpy()
             else:
@@ -182,6 +256,13 @@ class TrajectoryStore:
         self._arrays[path] = arr
         self._save_index()
         return arr
+
+    def _drop_pinned(self, path: str):
+        """Forget the page-locked block behind ``path`` and return it to the pool."""
+        self._pinned.pop(path, None)
+        block = self._blocks.pop(path, None)
+        if block is not None:
+            pinned_pool.release(block)
 
     def _drain(self, path: Optional[str] = None):
         """Wait for the asynchronous write-backs of one dataset (or of all of them)."""
@@ -205,7 +286,7 @@ class TrajectoryStore:
         n_rows = self._rows[path]
         self._barrier()                                  # everyone has read the old file
         del self._arrays[path], old
-        self._pinned.pop(path, None)
+        self._drop_pinned(path)
         self.invalidate(path)
         self.add_dataset(path, (n_rows, n_frames, data.shape[2]))
         self._local(path, lo, hi)[:, : data.shape[1]] = data
@@ -247,7 +328,7 @@ class TrajectoryStore:
             self._drain(path)
             self._barrier()
             del self._arrays[path]
-            self._pinned.pop(path, None)
+            self._drop_pinned(path)
             self.invalidate(path)
         self.add_dataset(path, array.shape)
         self.add_data(path, array)
@@ -430,7 +511,7 @@ class TrajectoryStore:
         if self.directory is not None:
             self._barrier()
         arr = self._arrays.pop(path, None)
-        self._pinned.pop(path, None)
+        self._drop_pinned(path)
         self._rows.pop(path, None)
         self._row0.pop(path, None)
         del arr

@@ -57,10 +57,12 @@ def test_adf_kernel_matches_oracle(cuda, counts, box, cutoff, nbins, power, spre
         diff = np.abs(c[p] - ref_c)
         ties += int(diff.sum()) // 2          # an angle on a bin edge moves one count
         assert diff.max() <= 2
+        same = diff == 0                      # bins no tie moved a triple into or out of
         scale = np.abs(ref_w).max() if ref_w.size else 0.0
-        np.testing.assert_allclose(w[p], ref_w, rtol=1e-5, atol=3e-4 * scale + 1e-30)
+        np.testing.assert_allclose(w[p][same], ref_w[same], rtol=1e-5, atol=1e-6 * scale + 1e-30)
+        assert abs(w[p].sum() - ref_w.sum()) <= 1e-6 * abs(ref_w.sum()) + 1e-30
     total = int(c.sum())
-    assert total > 1000
+    assert total > 300
     assert ties <= max(2, total // 20000), f"{ties} of {total} triples changed bins"
     if capacity is not None:
         assert eng.capacity > capacity        # the overflow path was taken
@@ -80,14 +82,16 @@ def test_adf_calculator_matches_oracle(tmp_path, cuda):
     project = Project("adf", storage_path=str(tmp_path))
     exp = project.add_experiment("NaCl", timestep=0.002, temperature=1400.0, units="metal")
     exp.add_data(ScriptInput({s: {"Positions": data[s]} for s in data}, box, atom_major=True))
-    for kwargs, n_batches in (({}, None), ({"batches": 5}, 5)):
+    # ``batches`` is not one of the stored arguments (as upstream), so the second run uses
+    # another bin count to get past the result cache
+    for kwargs, n_batches, nbins in (({}, None, 120), ({"batches": 5}, 5, 90)):
         res = exp.run.AngularDistributionFunction(number_of_configurations=5, cutoff=4.5,
-                                                  number_of_bins=120, plot=False, **kwargs)
+                                                  number_of_bins=nbins, plot=False, **kwargs)
         frames = np.linspace(1, 11, 5, dtype=int)
         nb = n_batches or oadf.adf_plan({"Na": 80, "Cl": 64}, 12, 5, MEM)
         assert res.metadata["n_batches"] == nb
-        ref = oadf.adf_finish(oadf.adf_histograms(data, ["Na", "Cl"], box, frames, 4.5, 120, 4,
-                                                  nb), 120)
+        ref = oadf.adf_finish(oadf.adf_histograms(data, ["Na", "Cl"], box, frames, 4.5, nbins, 4,
+                                                  nb), nbins)
         assert res.keys() == ["Na_Na_Na", "Na_Na_Cl", "Na_Cl_Cl", "Cl_Cl_Cl"]
         for key in res.keys():
             np.testing.assert_allclose(res[key]["angle"], ref[key]["angle"], rtol=1e-12)

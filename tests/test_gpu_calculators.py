@@ -657,6 +657,45 @@ def test_einstein_helfand_thermal_conductivity(tmp_path, cuda):
     assert res["System"]["thermal_conductivity"] == pytest.approx(popt[0] / 6, rel=1e-4)
 
 
+def test_block_input_and_pinned_pool(tmp_path, cuda):
+    """BlockInput writes atom blocks straight into the page-locked datasets (exact-size
+    cudaHostRegister blocks the kernels can read in place); a removed dataset hands its block to
+    the pool and the next dataset of that size reuses it."""
+    from lammps_analysis_b200.file_io import BlockInput
+    from lammps_analysis_b200.project import Project
+    from lammps_analysis_b200.store import pinned_pool
+
+    rng = np.random.default_rng(8)
+    full = {sp: rng.random((n, 20, 3)).astype(np.float32) for sp, n in (("A", 50), ("B", 31))}
+
+    def blocks():
+        for sp, arr in full.items():
+            for lo in range(0, arr.shape[0], 17):
+                hi = min(arr.shape[0], lo + 17)
+                yield sp, "Positions", (lo, hi), arr[lo:hi]
+
+    project = Project("blk", storage_path=str(tmp_path), persist=False)
+    exp = project.add_experiment("e", timestep=1.0, temperature=1.0, units="real")
+    exp.add_data(BlockInput(20, {"A": (50, {"Positions": 3}), "B": (31, {"Positions": 3})},
+                            [9.0, 9.0, 9.0], blocks))
+    assert exp.species["A"].n_particles == 50 and exp.number_of_configurations == 20
+    for sp in full:
+        assert np.array_equal(exp.store.host(f"{sp}/Positions"), full[sp])
+    pin = exp.store.pinned_tensor("A/Positions")
+    assert pin is not None and pin.is_pinned()
+    assert np.array_equal(exp.store.device("A/Positions").cpu().numpy(), full["A"])
+    rdf = exp.run.RadialDistributionFunction(number_of_configurations=5, plot=False)  # zero-copy pack
+    assert np.nansum(rdf["A_B"]["y"][1:]) > 0
+    pinned_pool.clear()
+    ptr = pin.data_ptr()
+    del pin
+    exp.store.remove("A/Positions")
+    assert pinned_pool.cached_bytes == 50 * 20 * 3 * 4
+    again = exp.store.add_dataset("A/Positions", (50, 20, 3))
+    assert exp.store.pinned_tensor("A/Positions").data_ptr() == ptr and pinned_pool.cached_bytes == 0
+    assert again.shape == (50, 20, 3)
+
+
 def test_in_memory_pinned_store_matches_persistent_store(tmp_path, cuda):
     """persist=False keeps datasets in page-locked host memory: the RDF pack kernels gather the
     sampled frames from it in place (zero copy), uploads are single DMA transfers.  Same numbers

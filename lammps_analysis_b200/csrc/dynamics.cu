@@ -895,7 +895,10 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
   if (W == 0 || a_lo == a_hi) return MDK_OK;
   MDK_CHECK_ARG(t0 >= 0 && t0 + (long long)(W - 1) + n_lags <= T,
                 "msd_dense: windows [t0=%lld, W=%d, n_lags=%d] exceed T=%lld", t0, W, n_lags, T);
-  if (n_lags <= 16 && !getenv("MDK_MSD_NO_STREAM")) {  // measured: the ring kernel wins from ~24 lags
+  int stream_max = 16;  // measured: the ring kernel wins from ~24 lags
+  if (const char* e = getenv("MDK_MSD_STREAM_MAX")) stream_max = atoi(e);
+  if (stream_max > 32) stream_max = 32;
+  if (n_lags <= stream_max && !getenv("MDK_MSD_NO_STREAM")) {
     // short lag ranges: HBM-streaming kernel, one warp per atom
     const bool vec = (T % 4 == 0) && (t0 % 4 == 0) && (reinterpret_cast<uintptr_t>(traj) % 16 == 0);
     const long long warps = a_hi - a_lo;
@@ -913,7 +916,8 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
   } while (0)
     if (n_lags <= 4) MDK_MS_LAUNCH(4);
     else if (n_lags <= 8) MDK_MS_LAUNCH(8);
-    else MDK_MS_LAUNCH(16);
+    else if (n_lags <= 16) MDK_MS_LAUNCH(16);
+    else MDK_MS_LAUNCH(32);
 #undef MDK_MS_LAUNCH
     MDK_LAUNCH_CHECK();
     return MDK_OK;
@@ -944,7 +948,9 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
   // Short lag ranges take long window chunks (up to ~4096 frames, 48 KB): with few lags per
   // atom the staging, not the arithmetic, is the cost, and it amortises over more origins.
   const int lag_alloc = grouped ? ((n_lags + R - 1) / R) * R + R : lag_span + R;
-  const int wc_max = grouped ? 4096 - lag_alloc : 512;
+  const char* g2 = getenv("MDK_MSD_GROUPED2");
+  const bool grouped2 = grouped && g2 && g2[0] == '1';  // tuning: two-atom kernel with groups
+  const int wc_max = grouped ? (grouped2 ? 2048 : 4096) - lag_alloc : 512;
   const int Wc = W < wc_max ? W : wc_max;
   const int len_alloc = (Wc + lag_alloc + 3) & ~3;  // multiple of 4: float2 views stay aligned
   // the two-atom kernel stages two atoms per sweep
@@ -956,7 +962,20 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
   const long long groups = (a_hi - a_lo + apc - 1) / apc;
   MDK_CHECK_ARG(groups <= 65535 && lag_blocks <= 65535, "msd_dense: grid too large");
   dim3 grid(chunks, (unsigned)groups, lag_blocks);
-  if (grouped) {
+  if (grouped2) {
+    const size_t smem2 = (size_t)6 * len_alloc * sizeof(float);
+#define MDK_MD2G_LAUNCH(RR)                                                                   \
+  do {                                                                                        \
+    MDK_CUDA(cudaFuncSetAttribute(msd_dense2_kernel<true, RR>,                                \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));  \
+    msd_dense2_kernel<true, RR><<<grid, MD_NT, smem2, as_stream(stream)>>>(                   \
+        traj, T, a_lo, a_hi, apc, t0, W, n_lags, Wc, len_alloc, msd_sum);                     \
+  } while (0)
+    if (R == 5) MDK_MD2G_LAUNCH(5);
+    else if (R == 7) MDK_MD2G_LAUNCH(7);
+    else MDK_MD2G_LAUNCH(9);
+#undef MDK_MD2G_LAUNCH
+  } else if (grouped) {
 #define MDK_MD1_LAUNCH(RR)                                                                    \
   do {                                                                                        \
     MDK_CUDA(cudaFuncSetAttribute(msd_dense_kernel<true, RR>,                                 \

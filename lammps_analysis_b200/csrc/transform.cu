@@ -48,8 +48,8 @@ constexpr int UNW_WARPS = 4;
 // read (and later written) as three fully coalesced 512-byte LDG.128/STG.128 rows and
 // re-distributed through a per-warp shared-memory slab so that lane l owns the 4 consecutive
 // frames 4l .. 4l+3.  Jumps are scanned inside the lane, then across the warp.
-template <bool L32, bool VEC>
-__global__ void __launch_bounds__(32 * UNW_WARPS)
+template <bool L32, bool VEC, int MINB>
+__global__ void __launch_bounds__(32 * UNW_WARPS, MINB)
 unwrap_kernel(const float* __restrict__ pos, long long A, long long T, double lx, double ly,
               double lz, float* __restrict__ carry_pos, int have_carry,
               double* __restrict__ carry_img, float* __restrict__ out) {
@@ -303,9 +303,20 @@ extern "C" int mdk_unwrap(const float* pos, long long A, long long T, const doub
                    (reinterpret_cast<uintptr_t>(out) % 16 == 0);
   const unsigned nb = (unsigned)blocks, nt = 32 * UNW_WARPS;
   cudaStream_t st = as_stream(stream);
+  int minb = 0;  // tuning: resident CTAs per SM the register allocation is capped for
+  if (const char* e = getenv("MDK_UNWRAP_MINB")) minb = atoi(e);
 #define MDK_UNWRAP_LAUNCH(L, V)                                                               \
-  unwrap_kernel<L, V><<<nb, nt, 0, st>>>(pos, A, T, box[0], box[1], box[2], carry_pos, have_carry, \
-                                         carry_img, out)
+  do {                                                                                        \
+    if (minb == 6)                                                                            \
+      unwrap_kernel<L, V, 6><<<nb, nt, 0, st>>>(pos, A, T, box[0], box[1], box[2], carry_pos, \
+                                                have_carry, carry_img, out);                  \
+    else if (minb == 8)                                                                       \
+      unwrap_kernel<L, V, 8><<<nb, nt, 0, st>>>(pos, A, T, box[0], box[1], box[2], carry_pos, \
+                                                have_carry, carry_img, out);                  \
+    else                                                                                      \
+      unwrap_kernel<L, V, 0><<<nb, nt, 0, st>>>(pos, A, T, box[0], box[1], box[2], carry_pos, \
+                                                have_carry, carry_img, out);                  \
+  } while (0)
   if (l32 && vec) MDK_UNWRAP_LAUNCH(true, true);
   else if (l32) MDK_UNWRAP_LAUNCH(true, false);
   else if (vec) MDK_UNWRAP_LAUNCH(false, true);

@@ -109,8 +109,9 @@ int mdk_coord_extent(const float* pos_soa, int n_frames, long long n_pad, float*
  *   bbox    : NULL, or the tile boxes from mdk_rdf_bbox (enables block culling and, for species
  *             blocks beyond 8192 atoms, the uniform-image fast path: blocks of pairs whose boxes
  *             prove one common periodic image take d + (-n L) instead of the per-pair rint)
- *   flags   : MDK_RDF_* bits; bits 8..11 (tile configuration) and 12..15 (binning / atomic
- *             mode) are tuning overrides used by the tests and benchmarks, 0 = automatic
+ *   flags   : MDK_RDF_* bits; bits 8..11 (tile configuration), 12..15 (binning / atomic mode),
+ *             16..19 (column chunk of a work item, 2^(v-1) tiles) and 20..23 (persistent grid
+ *             shrunk to v/15) are overrides used by the tests and benchmarks, 0 = automatic
  * Pairs counted: i < j within a species block, all (i, j) across blocks, for each
  * frame: r = p_j - p_i; r -= rint(r / L) * L; d2 = (x*x + y*y) + z*z (fp32, each op
  * rounded); counted iff sqrt(d2) < cutoff.

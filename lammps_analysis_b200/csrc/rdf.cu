@@ -24,13 +24,14 @@
 //     periodic image replace the per-pair rint by a warp-uniform shift (AM 7, sub_tile_uni).
 //
 // Variants (template parameter AM, selected in mdk_rdf_hist; all produce the same integers):
-//   0 / 1 / 2  table compare for every in-cutoff lane; predicated / per-lane dump / POPC.INC
-//   3          bin from 7 fraction bits of the guess, table compare under a warp vote
+//   2          table compare for every in-cutoff lane, unconditional ATOMS.POPC.INC with one
+//              dump word for the lanes outside the cutoff (general coordinates, small tiles)
 //   4          tables and histogram in global memory (bin counts beyond shared memory)
 //   5          as 2 with the wrapped-coordinate minimum image min(|d|, L - |d|)
-//   6          as 5 with a quarter-bit gated table compare
 //   7          DEFAULT on sorted frames: uniform-image blocks + clamped gated compare
 //   8          DEFAULT on unsorted wrapped frames: wrapped minimum image + clamped gated compare
+// (round 1 also carried a predicated-red, a per-lane-dump, a 7-fraction-bit and a quarter-bit
+// gated variant -- AM 0, 1, 3, 6; all measured slower, removed in round 2)
 #include "mdk_common.cuh"
 
 #include <cmath>
@@ -154,13 +155,9 @@ __device__ __forceinline__ void bin_one_global(float d2, bool valid, const float
 //   tg = thr[g]                           (shared, predicated on p)
 //   k  = g - (d2 < tg) ;  p -> ++cnt[k]
 // thr_c = smem address of thr[0] minus 4*bits(1.5*2^23); delta = &cnt[0] - &thr[0] (bytes).
-// ptxas never predicates ATOMS (it wraps it in BSSY/BRA/BSYNC), so there are three ways
-// to issue the increment (AM):
-//   0: predicated red (ptxas emits a branch around ATOMS.ADD)
-//   1: unconditional ATOMS.ADD; lanes outside the cutoff hit a per-lane dump slot
-//   2: as 1 with a literal 1 (ATOMS.POPC.INC)
-// `one` is 1 but opaque to the compiler (a literal turns the reduction into POPC.INC).
-template <int AM>
+// ptxas never predicates ATOMS (it wraps it in BSSY/BRA/BSYNC), so the increment is issued
+// unconditionally with a literal 1 (ATOMS.POPC.INC): lanes outside the cutoff all hit one dump
+// word, which POPC.INC merges into a single increment.
 __device__ __forceinline__ void bin_two(float2 d2, float cut2, float2 inv_step2, uint32_t thr_c,
                                         uint32_t delta, uint32_t one, uint32_t dump) {
 #define MDK_BIN_HEAD                                   \
@@ -189,138 +186,25 @@ __device__ __forceinline__ void bin_two(float2 d2, float cut2, float2 inv_step2,
 #define MDK_BIN_ARGS                                                                        \
   "f"(d2.x), "f"(d2.y), "f"(cut2), "l"(*reinterpret_cast<unsigned long long*>(&inv_step2)), \
       "l"(0x4B4000004B400000ull), "r"(thr_c), "r"(delta), "r"(one), "r"(dump)
-  if (AM == 0) {
-    asm volatile(MDK_BIN_HEAD
-                 "add.u32 a0, a0, %6;\n"
-                 "add.u32 a1, a1, %6;\n"
-                 "@p0 red.shared.add.u32 [a0], %7;\n"
-                 "@p1 red.shared.add.u32 [a1], %7;\n"
-                 "}\n" ::MDK_BIN_ARGS
-                 : "memory");
-  } else if (AM == 1) {
-    asm volatile(MDK_BIN_HEAD
-                 "selp.u32 a0, a0, %8, p0;\n"
-                 "selp.u32 a1, a1, %8, p1;\n"
-                 "add.u32 a0, a0, %6;\n"
-                 "add.u32 a1, a1, %6;\n"
-                 "red.shared.add.u32 [a0], %7;\n"
-                 "red.shared.add.u32 [a1], %7;\n"
-                 "}\n" ::MDK_BIN_ARGS
-                 : "memory");
-  } else {
-    asm volatile(MDK_BIN_HEAD
-                 "selp.u32 a0, a0, %8, p0;\n"
-                 "selp.u32 a1, a1, %8, p1;\n"
-                 "add.u32 a0, a0, %6;\n"
-                 "add.u32 a1, a1, %6;\n"
-                 "red.shared.add.u32 [a0], 1;\n"
-                 "red.shared.add.u32 [a1], 1;\n"
-                 "}\n" ::MDK_BIN_ARGS
-                 : "memory");
-  }
+  asm volatile(MDK_BIN_HEAD
+               "selp.u32 a0, a0, %8, p0;\n"
+               "selp.u32 a1, a1, %8, p1;\n"
+               "add.u32 a0, a0, %6;\n"
+               "add.u32 a1, a1, %6;\n"
+               "red.shared.add.u32 [a0], 1;\n"
+               "red.shared.add.u32 [a1], 1;\n"
+               "}\n" ::MDK_BIN_ARGS
+               : "memory");
 #undef MDK_BIN_HEAD
 #undef MDK_BIN_ARGS
 }
 
-// Table-free variant for the common case (AM == 3).  The bin guess carries FRAC_BITS fraction
-// bits: tm = fma(sqrt.approx(d2), 1/step, 1.5 * 2^(23 - FRAC_BITS)) rounds t = d/step to the
-// nearest 1/128, so the mantissa holds (floor-or-carry(t) << 7) | f.  The exact bin (double-step
-// rule on the correctly rounded sqrt) differs from t by at most t * 2.4e-7 + 1/256 < 1/128 for
-// t <= 16000, hence for f != 0 the integer part IS the bin and only f == 0 (one lane in 128)
-// needs the threshold-table compare.  This removes the random shared-memory gather from the
-// hot path; the table lookup runs under a warp vote.
-constexpr int FRAC_BITS = 7;
-constexpr float FRAC_MAGIC = 98304.0f;  // 1.5 * 2^16: ulp = 2^-7
-constexpr int FRAC_MAX_BINS = 15000;
-
-template <bool DUMMY = true>
-__device__ __forceinline__ void bin_two_frac(float2 d2, float cut2, float2 inv_step2,
-                                             uint32_t thr_base, uint32_t cnt_base,
-                                             uint32_t dump_off) {
-  const float2 ee = make_float2(sqrt_approx(d2.x), sqrt_approx(d2.y));
-  const float2 tt = __ffma2_rn(ee, inv_step2, make_float2(FRAC_MAGIC, FRAC_MAGIC));
-  const uint32_t b0 = __float_as_uint(tt.x), b1 = __float_as_uint(tt.y);
-  uint32_t a0 = (b0 >> (FRAC_BITS - 2)) & 0x1fffcu;  // 4 * bin (byte offset)
-  uint32_t a1 = (b1 >> (FRAC_BITS - 2)) & 0x1fffcu;
-  const bool p0 = d2.x < cut2, p1 = d2.y < cut2;
-  const bool m0 = p0 && ((b0 & ((1u << FRAC_BITS) - 1u)) == 0u);
-  const bool m1 = p1 && ((b1 & ((1u << FRAC_BITS) - 1u)) == 0u);
-  if (__any_sync(0xffffffffu, m0 | m1)) {
-    if (m0) {
-      float g;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g) : "r"(thr_base + a0));
-      if (d2.x < g) a0 -= 4u;
-    }
-    if (m1) {
-      float g;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g) : "r"(thr_base + a1));
-      if (d2.y < g) a1 -= 4u;
-    }
-  }
-  a0 = p0 ? a0 : dump_off;
-  a1 = p1 ? a1 : dump_off;
-  asm volatile(
-      "{\n"
-      ".reg .u32 t0, t1;\n"
-      "add.u32 t0, %0, %2;\n"
-      "add.u32 t1, %1, %2;\n"
-      "red.shared.add.u32 [t0], 1;\n"
-      "red.shared.add.u32 [t1], 1;\n"
-      "}\n" ::"r"(a0), "r"(a1), "r"(cnt_base)
-      : "memory");
-}
-
-// Quarter-bit gated variant (AM == 6): the guess carries two fraction bits,
+// Clamped, quarter-bit gated variant (AM == 7 / 8).  The guess carries two fraction bits,
 //   tm = fma(sqrt.approx(d2), 4/step, 1.5 * 2^23)  ->  mantissa = round(4 t),  t = d / step,
 // so (mantissa & ~3) is already the byte offset of bin floor(t) and (mantissa & 3) == 0 says
-// that t lies within 1/8 of an integer.  The exact bin differs from t by < 0.01, hence only
-// those lanes (one in four) need the threshold-table compare; the others skip the random
-// shared-memory gather, which (with the histogram atomics) is what bounds the kernel.
-__device__ __forceinline__ void bin_two_q(float2 d2, float cut2, float2 inv_step4, uint32_t thr_s,
-                                          uint32_t cnt_s, uint32_t dump_off) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p0, p1, m0, m1, q0, q1;\n"
-      ".reg .f32 e0, e1, t0, t1;\n"
-      ".reg .b64 ee, tt;\n"
-      ".reg .u32 a0, a1, b0, b1, f0, f1, u0, u1;\n"
-      "setp.lt.f32 p0, %0, %2;\n"
-      "setp.lt.f32 p1, %1, %2;\n"
-      "sqrt.approx.ftz.f32 e0, %0;\n"
-      "sqrt.approx.ftz.f32 e1, %1;\n"
-      "mov.b64 ee, {e0, e1};\n"
-      "fma.rn.f32x2 tt, ee, %3, %4;\n"
-      "mov.b64 {t0, t1}, tt;\n"
-      "mov.b32 b0, t0;\n"
-      "mov.b32 b1, t1;\n"
-      "and.b32 a0, b0, 0x003ffffc;\n"
-      "and.b32 a1, b1, 0x003ffffc;\n"
-      "and.b32 f0, b0, 3;\n"
-      "and.b32 f1, b1, 3;\n"
-      "setp.eq.and.u32 m0, f0, 0, p0;\n"
-      "setp.eq.and.u32 m1, f1, 0, p1;\n"
-      "add.u32 u0, a0, %5;\n"
-      "add.u32 u1, a1, %5;\n"
-      "@m0 ld.shared.f32 e0, [u0];\n"
-      "@m1 ld.shared.f32 e1, [u1];\n"
-      "setp.lt.and.f32 q0, %0, e0, m0;\n"
-      "setp.lt.and.f32 q1, %1, e1, m1;\n"
-      "@q0 add.u32 a0, a0, -4;\n"
-      "@q1 add.u32 a1, a1, -4;\n"
-      "selp.u32 a0, a0, %7, p0;\n"
-      "selp.u32 a1, a1, %7, p1;\n"
-      "add.u32 a0, a0, %6;\n"
-      "add.u32 a1, a1, %6;\n"
-      "red.shared.add.u32 [a0], 1;\n"
-      "red.shared.add.u32 [a1], 1;\n"
-      "}\n" ::"f"(d2.x),
-      "f"(d2.y), "f"(cut2), "l"(*reinterpret_cast<unsigned long long*>(&inv_step4)),
-      "l"(0x4B4000004B400000ull), "r"(thr_s), "r"(cnt_s), "r"(dump_off)
-      : "memory");
-}
-
-// Clamped, quarter-bit gated variant (AM == 7 / 8).  As bin_two_q, but without the in-cutoff
-// predicate and without the dump-slot select: d2 is first clamped to clamp2 = ((nbins + 1/2) *
+// that t lies within 1/8 of an integer: the exact bin differs from t by < 0.01, hence only those
+// lanes (one in four) need the threshold-table compare.  There is no in-cutoff predicate and
+// no dump-slot select: d2 is first clamped to clamp2 = ((nbins + 1/2) *
 // step)^2 (min.f32 also maps the NaN of padding atoms to it), so every lane well outside the
 // cutoff computes M = 4 * nbins + 2, needs no table compare and increments the unused word
 // cnt[nbins] (one address for all such lanes: ATOMS.POPC.INC merges them).  Lanes whose guess
@@ -455,8 +339,7 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
                                          const float* __restrict__ sz, int jj0,
                                          const float2 (&nxi)[R], const float2 (&nyi)[R],
                                          const float2 (&nzi)[R], const GeoConst& c) {
-  constexpr bool WRAP = (AM == 5 || AM == 6 || AM == 8);  // wrapped-coordinate minimum image
-  const float2 inv_step4 = dup2(4.0f * c.inv_step);
+  constexpr bool WRAP = (AM == 5 || AM == 8);  // wrapped-coordinate minimum image
   const float2 magic_thr = dup2(bin_magic(c.thr_s));  // see bin_two_c
   const float2 magic2 = dup2(RINT_MAGIC), nmagic2 = dup2(-RINT_MAGIC);
   const float2 inv_step2 = dup2(c.inv_step);
@@ -505,14 +388,10 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
         const float2 yy = __fmul2_rn(ry, ry);
         const float2 zz = __fmul2_rn(rz, rz);
         const float2 d2 = __ffma2_rn(zz, one2, __ffma2_rn(xx, one2, yy));
-        if (AM == 3)
-          bin_two_frac(d2, c.cut2, inv_step2, c.thr_s, c.cnt_s, c.dump_off);
-        else if (AM == 6)
-          bin_two_q(d2, c.cut2, inv_step4, c.thr_s, c.cnt_s, c.dump_off);
-        else if (AM == 7 || AM == 8)
+        if (AM == 7 || AM == 8)
           bin_two_c(d2, c.clamp2, dup2(bin_scale(c.inv_step)), magic_thr, c.cnt_delta);
         else
-          bin_two<(AM >= 3 ? 2 : AM)>(d2, c.cut2, inv_step2, c.thr_c, c.cnt_delta, c.one, c.dump);
+          bin_two(d2, c.cut2, inv_step2, c.thr_c, c.cnt_delta, c.one, c.dump);
       }
     }
   }
@@ -1164,7 +1043,7 @@ int launch_rdf_cfg(const RdfParams& P, size_t smem, int grid, cudaStream_t s, bo
   if (am == 4)
     return exact ? launch_rdf<NT, R, true, 4, false>(P, smem, grid, s)
                  : launch_rdf<NT, R, false, 4, false>(P, smem, grid, s);
-  if (exact) return launch_rdf<NT, R, true, 0, false>(P, smem, grid, s);
+  if (exact) return launch_rdf<NT, R, true, 2, false>(P, smem, grid, s);
   if constexpr (NT == 256 && R == 4) {
     if (P.bbox && am == 7) return launch_rdf<NT, R, false, 7, true>(P, smem, grid, s);
     if (am == 8)
@@ -1173,20 +1052,11 @@ int launch_rdf_cfg(const RdfParams& P, size_t smem, int grid, cudaStream_t s, bo
   }
   if (am == 8) am = 5;
   if (am == 7) am = 2;  // uniform-image blocks need the culling boxes and the 256 x 4 tile
-  if (P.bbox) {  // culling variants: AM 2 (table), AM 3 (fraction bits), AM 5 (wrapped)
-    if (am == 3) return launch_rdf<NT, R, false, 3, true>(P, smem, grid, s);
-    if (am == 5) return launch_rdf<NT, R, false, 5, true>(P, smem, grid, s);
-    if (am == 6) return launch_rdf<NT, R, false, 6, true>(P, smem, grid, s);
-    return launch_rdf<NT, R, false, 2, true>(P, smem, grid, s);
-  }
-  switch (am) {
-    case 0: return launch_rdf<NT, R, false, 0, false>(P, smem, grid, s);
-    case 1: return launch_rdf<NT, R, false, 1, false>(P, smem, grid, s);
-    case 3: return launch_rdf<NT, R, false, 3, false>(P, smem, grid, s);
-    case 5: return launch_rdf<NT, R, false, 5, false>(P, smem, grid, s);
-    case 6: return launch_rdf<NT, R, false, 6, false>(P, smem, grid, s);
-    default: return launch_rdf<NT, R, false, 2, false>(P, smem, grid, s);
-  }
+  if (P.bbox)           // culling variants: AM 2 (table), AM 5 (wrapped)
+    return am == 5 ? launch_rdf<NT, R, false, 5, true>(P, smem, grid, s)
+                   : launch_rdf<NT, R, false, 2, true>(P, smem, grid, s);
+  return am == 5 ? launch_rdf<NT, R, false, 5, false>(P, smem, grid, s)
+                 : launch_rdf<NT, R, false, 2, false>(P, smem, grid, s);
 }
 
 }  // namespace mdk
@@ -1333,21 +1203,21 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
   int cfg = (flags >> 8) & 0xf;   // 0 = auto, 1: 128x2, 2: 128x4, 3: 256x2, 4: 256x4
   int am = (flags >> 12) & 0xf;   // 0 = auto, else AM = am - 1
   if (cfg == 0) cfg = max_len <= 8192 ? 1 : 4;
-  am = am == 0 ? 2 : am - 1;  // auto: unconditional ATOMS.POPC.INC (fastest measured)
-  MDK_CHECK_ARG(cfg >= 1 && cfg <= 5 && am >= 0 && am <= 8, "rdf_hist: bad tuning flags");
-  const bool auto_am = ((flags >> 12) & 0xf) == 0;
-  if (am == 3 && nbins > FRAC_MAX_BINS) am = 2;  // fraction-bit binning needs nbins <= 15000
+  const bool auto_am = am == 0;
+  am = auto_am ? 2 : am - 1;
+  MDK_CHECK_ARG(cfg >= 1 && cfg <= 5 && (am == 2 || am == 4 || am == 5 || am == 7 || am == 8),
+                "rdf_hist: bad tuning flags (atomic modes: 2, 4, 5, 7, 8)");
+  const bool wrapped = !exact && (flags & MDK_RDF_WRAPPED);
   // coordinates verified to span less than one box length: cheaper minimum image
-  const bool want_q = ((flags >> 12) & 0xf) == 7;  // tuning: quarter-bit gated table compare
-  if ((am == 2 || want_q) && !exact && (flags & MDK_RDF_WRAPPED)) am = want_q ? 6 : 5;
-  else if (want_q) am = 2;
+  if (auto_am && wrapped) am = 5;
+  if (am == 5 && !wrapped) am = 2;
   // sorted frames with bounding boxes: uniform-image blocks + gated compare (any coordinates)
   if ((auto_am || am == 7) && !exact && bbox && cfg >= 4) am = 7;
-  else if (am == 7) am = (flags & MDK_RDF_WRAPPED) ? 5 : 2;
+  else if (am == 7) am = wrapped ? 5 : 2;
   // wrapped minimum image + clamped gated compare (needs wrapped coordinates; instantiated for
   // the 256 x 4 tile): +4..6 % over AM 5 on unsorted frames
   if (auto_am && am == 5 && cfg >= 4) am = 8;
-  if (am == 8 && (exact || !(flags & MDK_RDF_WRAPPED))) am = 2;
+  if (am == 8 && !wrapped) am = 2;
   if (am == 8 && cfg < 4) am = 5;
   const int NT = cfg == 5 ? 384 : (cfg <= 2) ? 128 : 256;
   const int R = (cfg == 1 || cfg == 3) ? 2 : 4;
@@ -1383,7 +1253,7 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
                       6 * sizeof(unsigned long long) +
                       (size_t)((nbins + 1 + 3) & ~3) * sizeof(float) +
                       (size_t)(((nbins + 31) & ~31) + 32) * sizeof(unsigned);
-  const bool global_hist = smem > 227 * 1024 || ((flags >> 12) & 0xf) == 5;
+  const bool global_hist = smem > 227 * 1024 || am == 4;
   size_t smem_used = smem;
   if (global_hist) {
     // threshold table + private histogram do not fit: slow path with both in global memory
@@ -1426,6 +1296,18 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
     CJ /= 2;
     total = count_items(CJ);
   }
+  // stress-test overrides (tests/test_gpu_kernels.py::test_rdf_schedule_stress): bits 16..19
+  // force the column chunk (CJ = 2^(v-1)), bits 20..23 shrink the persistent grid to v/15 of
+  // its size -- the counts must not depend on how the work items are cut or interleaved
+  int grid_used = grid;
+  if (const int v = (flags >> 16) & 0xf) {
+    CJ = 1 << (v - 1);
+    total = count_items(CJ);
+  }
+  if (const int v = (flags >> 20) & 0xf) {
+    grid_used = (int)((long long)grid * v / 15);
+    if (grid_used < 1) grid_used = 1;
+  }
   P.CJ = CJ;
   P.total_items = total;
   // u32 private counters: flush before a bin could overflow (TI * TJ pairs per tile)
@@ -1445,14 +1327,14 @@ extern "C" int mdk_rdf_hist(const float* pos_soa, int n_frames, long long n_pad,
 
   MDK_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s));
   switch (cfg) {
-    case 1: return launch_rdf_cfg<128, 2>(P, smem_used, grid, s, exact, am);
-    case 2: return launch_rdf_cfg<128, 4>(P, smem_used, grid, s, exact, am);
-    case 3: return launch_rdf_cfg<256, 2>(P, smem_used, grid, s, exact, am);
+    case 1: return launch_rdf_cfg<128, 2>(P, smem_used, grid_used, s, exact, am);
+    case 2: return launch_rdf_cfg<128, 4>(P, smem_used, grid_used, s, exact, am);
+    case 3: return launch_rdf_cfg<256, 2>(P, smem_used, grid_used, s, exact, am);
     case 5:  // tuning: 12 warps per CTA (AM 7 / 8 only)
-      if (am == 7 && P.bbox) return launch_rdf<384, 4, false, 7, true>(P, smem_used, grid, s);
-      if (am == 8 && !P.bbox) return launch_rdf<384, 4, false, 8, false>(P, smem_used, grid, s);
+      if (am == 7 && P.bbox) return launch_rdf<384, 4, false, 7, true>(P, smem_used, grid_used, s);
+      if (am == 8 && !P.bbox) return launch_rdf<384, 4, false, 8, false>(P, smem_used, grid_used, s);
       set_error("rdf_hist: tile configuration 5 needs atomic mode 7 (sorted) or 8 (unsorted)");
       return MDK_EINVAL;
-    default: return launch_rdf_cfg<256, 4>(P, smem_used, grid, s, exact, am);
+    default: return launch_rdf_cfg<256, 4>(P, smem_used, grid_used, s, exact, am);
   }
 }

@@ -96,8 +96,10 @@ class Transformations:
 
     input_properties: list = []
     output_property = None
-    # frames per launch are bounded so that input + output of a chunk stay within this budget
+    # an extension run (new frames appended) works in time chunks of at most this many bytes;
+    # a full run works in blocks of rows (all frames of some atoms) of at most block_bytes
     chunk_bytes: int = 8 << 30
+    block_bytes: int = 3 << 30
 
     def __init__(self, input_properties: Iterable = None, output_property=None,
                  scale_function: dict = None, dtype=None):
@@ -245,30 +247,103 @@ class SingleSpeciesTrafo(Transformations):
             lo, hi = store.owned_rows(out_path)
             if hi <= lo:
                 continue
-            dims_in = sum(p.n_dims for p in self.input_properties if p.name in paths)
-            per_frame = (hi - lo) * 4 * (dims_in + self.output_property.n_dims)
-            frames_per_chunk = max(1, min(n_frames, self.chunk_bytes // max(per_frame, 1)))
-            carry = self.initial_carry(sp, paths, offset) if offset else None
-            whole = None
-            for t0 in range(offset, n_frames, frames_per_chunk):
-                t1 = min(n_frames, t0 + frames_per_chunk)
-                full = t0 == 0 and t1 == n_frames
-                batch = dict(consts)
-                for name, path in paths.items():
-                    if full:
-                        batch[name] = store.device(path)
-                    else:
-                        batch[name] = torch.from_numpy(
-                            np.ascontiguousarray(store.host(path)[:, t0:t1])).cuda()
-                ret = self.transform_batch(batch, carryover=carry)
-                out_dev, carry = ret if isinstance(ret, tuple) else (ret, carry)
-                if out_dev.shape[0] == 1 and hi - lo != 1:
-                    out_dev = out_dev.expand(hi - lo, -1, -1).contiguous()
-                store.write_from_device(out_path, out_dev, t0)
-                whole = out_dev if full else None
+            if offset == 0:
+                self._run_row_blocks(sp, paths, consts, out_path, lo, hi, n_frames)
+            else:
+                self._run_appended_frames(sp, paths, consts, out_path, lo, hi, offset, n_frames)
+
+    def _run_row_blocks(self, sp, paths, consts, out_path, lo, hi, n_frames):
+        """The whole time range of this rank's rows, a block of rows at a time.  Rows are
+        contiguous in the store, so a block is one DMA each way; blocks are pipelined over three
+        streams -- upload of block k + 1, kernel on block k, write-back of block k - 1 -- which
+        keeps both directions of the host link busy.  The result stays resident in HBM for the
+        calculator that follows when it fits."""
+        import torch
+
+        store = self.experiment.store
+        names = list(paths)
+        dims_in = sum(p.n_dims for p in self.input_properties if p.name in paths)
+        row_bytes = n_frames * 4 * (dims_in + self.output_property.n_dims)
+        rows_per = int(max(1, min(hi - lo, self.block_bytes // max(row_bytes, 1))))
+        out_bytes = (hi - lo) * n_frames * 4 * self.output_property.n_dims
+        keep = out_bytes < 0.35 * torch.cuda.mem_get_info()[0]
+        whole = torch.empty(hi - lo, n_frames, self.output_property.n_dims, dtype=torch.float32,
+                            device="cuda") if keep else None
+        resident = {n: store.device(paths[n]) for n in names if store.is_resident(paths[n])}
+        pinned = {n: store.pinned_tensor(paths[n]) for n in names if n not in resident}
+        if any(t is None for t in pinned.values()) or rows_per >= hi - lo:
+            # file-backed (or small) inputs: one upload per dataset through the store's cache
+            batch = dict(consts)
+            for n in names:
+                batch[n] = store.device(paths[n])
+            ret = self.transform_batch(batch, carryover=None)
+            out_dev = ret[0] if isinstance(ret, tuple) else ret
+            if out_dev.shape[0] == 1 and hi - lo != 1:
+                out_dev = out_dev.expand(hi - lo, -1, -1).contiguous()
+            store.write_from_device(out_path, out_dev, 0)
             store.invalidate(out_path)
+            store.adopt_device(out_path, out_dev)
+            return
+        compute = torch.cuda.current_stream()
+        upload = torch.cuda.Stream()
+        stage = [{n: torch.empty((rows_per,) + tuple(pinned[n].shape[1:]), dtype=torch.float32,
+                                 device="cuda") for n in pinned} for _ in range(2)]
+        free_ev = [None, None]          # compute is done with staging buffer i
+        row0 = store.owned_rows(paths[names[0]])[0]
+        for k, r0 in enumerate(range(lo, hi, rows_per)):
+            r1 = min(hi, r0 + rows_per)
+            buf = stage[k & 1]
+            with torch.cuda.stream(upload):
+                if free_ev[k & 1] is not None:
+                    upload.wait_event(free_ev[k & 1])
+                for n, pin in pinned.items():
+                    buf[n][:r1 - r0].copy_(pin[r0 - row0:r1 - row0], non_blocking=True)
+                    store.h2d_bytes += (r1 - r0) * int(np.prod(pin.shape[1:])) * 4
+                up_ev = torch.cuda.Event()
+                up_ev.record()
+            compute.wait_event(up_ev)
+            batch = dict(consts)
+            for n in names:
+                batch[n] = resident[n][r0 - lo:r1 - lo] if n in resident else buf[n][:r1 - r0]
             if whole is not None:
-                store.adopt_device(out_path, whole)  # stays resident for the calculator
+                batch["__out__"] = whole[r0 - lo:r1 - lo]   # a kernel may write its result here
+            ret = self.transform_batch(batch, carryover=None)
+            out_dev = ret[0] if isinstance(ret, tuple) else ret
+            if out_dev.shape[0] == 1 and r1 - r0 != 1:
+                out_dev = out_dev.expand(r1 - r0, -1, -1).contiguous()
+            if whole is not None and out_dev.data_ptr() != whole[r0 - lo:r1 - lo].data_ptr():
+                whole[r0 - lo:r1 - lo].copy_(out_dev)
+                out_dev = whole[r0 - lo:r1 - lo]
+            ev = torch.cuda.Event()
+            ev.record()
+            free_ev[k & 1] = ev
+            store.write_from_device(out_path, out_dev, 0, row0=r0)   # asynchronous, side stream
+        store.invalidate(out_path)
+        if whole is not None:
+            store.adopt_device(out_path, whole)  # stays resident for the calculator
+
+    def _run_appended_frames(self, sp, paths, consts, out_path, lo, hi, offset, n_frames):
+        """Extension after ``Experiment.add_data``: frames [offset, n_frames) only, in time
+        chunks, with the carry-over rebuilt from the last stored frame."""
+        import torch
+
+        store = self.experiment.store
+        dims_in = sum(p.n_dims for p in self.input_properties if p.name in paths)
+        per_frame = (hi - lo) * 4 * (dims_in + self.output_property.n_dims)
+        frames_per_chunk = max(1, min(n_frames, self.chunk_bytes // max(per_frame, 1)))
+        carry = self.initial_carry(sp, paths, offset)
+        for t0 in range(offset, n_frames, frames_per_chunk):
+            t1 = min(n_frames, t0 + frames_per_chunk)
+            batch = dict(consts)
+            for name, path in paths.items():
+                batch[name] = torch.from_numpy(
+                    np.ascontiguousarray(store.host(path)[:, t0:t1])).cuda()
+            ret = self.transform_batch(batch, carryover=carry)
+            out_dev, carry = ret if isinstance(ret, tuple) else (ret, carry)
+            if out_dev.shape[0] == 1 and hi - lo != 1:
+                out_dev = out_dev.expand(hi - lo, -1, -1).contiguous()
+            store.write_from_device(out_path, out_dev, t0)
+        store.invalidate(out_path)
 
 
 class CoordinateUnwrapper(SingleSpeciesTrafo):
@@ -292,7 +367,9 @@ class CoordinateUnwrapper(SingleSpeciesTrafo):
                                               device=pos.device),
                 "have": False,
             }
-        out = torch.empty_like(pos)
+        out = batch.get("__out__")
+        if out is None:
+            out = torch.empty_like(pos)
         K.unwrap(pos, self._box(batch), carry["last_pos"], carry["last_image_box"], carry["have"],
                  out)
         carry["have"] = True

@@ -116,6 +116,44 @@ def test_rdf_tie_census_matches_numpy(cuda):
     assert eng.tie_report()["pairs_checked"] == len(d)
 
 
+def test_rdf_schedule_stress(cuda):
+    """The default kernel on sorted frames (AM 7) hands column tiles through a two-stage
+    mbarrier ring in which the last warp to leave a stage refills it; compute-sanitizer's
+    racecheck is not available on this GPU pool, so the schedule is stressed instead: 200
+    launches on one 60,000-atom frame with random work-item sizes (column chunk) and persistent
+    grid sizes -- every interleaving must give the same integers, which the first launch has
+    in common with the plain all-pairs kernel."""
+    import torch
+    from lammps_analysis_b200.engine import RdfEngine
+    from lammps_analysis_b200.synthetic import device_fluid
+
+    n, L = 60_000, 106.0
+    traj = device_fluid(n, 1, L, 21, cuda)
+    cutoff = L / 2 - 0.1
+    nbins = int(cutoff / 0.01)
+    plain = RdfEngine([n], [L] * 3, cutoff, nbins, device=cuda, spatial_sort=False)
+    plain.add_frames([traj], [0])
+    want = plain.counts()
+    eng = RdfEngine([n], [L] * 3, cutoff, nbins, device=cuda, spatial_sort=True)
+    eng.tie_rows = 0
+    buf = eng._buffer(1)
+    eng.pack_sorted([traj], [0], buf)
+    bbox = eng.boxes(buf, 1)
+    rng = np.random.default_rng(99)
+    for it in range(200):
+        tuning = 0x8400 | (int(rng.integers(1, 8)) << 16) | (int(rng.integers(1, 16)) << 20)
+        if it == 0:
+            tuning = 0x8400
+        eng.hist.zero_()
+        eng.add_packed(buf, 1, tuning=tuning, bbox=bbox)
+        got = eng.hist.view(1, nbins)
+        if it == 0:
+            assert np.array_equal(got.cpu().numpy(), want)
+            first = got.clone()
+        else:
+            assert torch.equal(got, first), f"launch {it} (tuning {tuning:#x}) changed the counts"
+
+
 def test_rdf_exact_division_mode(cuda):
     """cutoff >= L/2 forces the true-division minimum image; still bit-exact."""
     from lammps_analysis_b200.engine import RdfEngine, to_device_f32

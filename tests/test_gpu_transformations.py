@@ -220,3 +220,27 @@ def test_extending_the_hot_path_transformations_matches_one_run(tmp_path, cuda):
         full = exp.run.EinsteinDiffusionCoefficients(data_range=50, plot=False)
         np.testing.assert_allclose(long["Na"]["msd"], full["Na"]["msd"], rtol=1e-12)
         assert long["Na"]["msd"] != short["Na"]["msd"]
+
+
+def test_row_block_pipeline_matches_single_block(tmp_path, cuda, monkeypatch):
+    """In-memory (page-locked) stores run a transformation in blocks of rows pipelined over
+    upload / compute / write-back streams; many small blocks, a ragged last block and the
+    resident result must equal the one-block run and the oracle."""
+    from lammps_analysis_b200.file_io import ScriptInput
+    from lammps_analysis_b200.synthetic import nacl_trajectory
+    from lammps_analysis_b200.transformations import CoordinateUnwrapper
+    from oracle import transformations as ot
+
+    data, box = nacl_trajectory(343, 150, 9.0, seed=45, sigma_step=0.6)
+    project, exp = _exp(tmp_path, name="blocks", timestep=0.002, persist=False)
+    exp.add_data(ScriptInput(data, box, atom_major=True))
+    # 150 frames x 24 B per row: 7 rows per block -> 25 blocks for the 172 / 171 atom species
+    monkeypatch.setattr(CoordinateUnwrapper, "block_bytes", 7 * 150 * 24)
+    exp.run.CoordinateUnwrapper()
+    for sp in ("Na", "Cl"):
+        want = ot.run_unwrap(data[sp]["Positions"], box, batch_size=150)
+        assert np.array_equal(exp.store.host(f"{sp}/Unwrapped_Positions"), want)
+        assert exp.store.is_resident(f"{sp}/Unwrapped_Positions")
+        assert np.array_equal(exp.store.device(f"{sp}/Unwrapped_Positions").cpu().numpy(), want)
+    res = exp.run.EinsteinDiffusionCoefficients(data_range=40, plot=False)
+    assert np.isfinite(res["Na"]["diffusion_coefficient"])

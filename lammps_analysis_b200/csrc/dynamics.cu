@@ -459,6 +459,167 @@ msd_stream_kernel(const float* __restrict__ traj, long long T, long long a_lo, l
   if (lane < n_lags) atomicAdd(msd_sum + lane, total);
 }
 
+// ---- Einstein MSD, medium dense lag ranges (8 .. 128 lags): register-window kernel --------------
+// Between the HBM-bound streaming kernel (one shared-memory read per update) and the register
+// ring (needs ~300 lags to fill a CTA) neither roofline was reached (round-1 review: 18 % of HBM
+// and 20 % of FP32 at 16 lags).  Here one warp owns one atom and walks its row in chunks of
+// 32 x RW_F origins: lane l owns the RW_F CONSECUTIVE origins 7 l .. 7 l + 6 and, per pass of NLP
+// lags, loads the RW_F + NLP - 1 positions they pair with ONCE from shared memory into registers
+// (lane stride 21 words: odd, conflict free) -- 0.6 shared-memory reads per update instead of 3.
+// The RW_F x NLP updates of a pass are fully unrolled register arithmetic (3 FADD + 3 FFMA each).
+// The per-lane partial sums of a pass are folded into a per-warp shared-memory table
+// [lag][lane] (conflict free), which is reduced over the lanes into fp64 once per atom.
+// Chunks (plus the lag halo) are staged by 16-byte cp.async, double buffered.
+constexpr int RW_F = 7;
+constexpr int RW_CH = 32 * RW_F;
+constexpr int RW_WARPS = 4;
+
+__device__ __forceinline__ void rw_cp16(float* dst, const float* src, bool valid) {
+  const unsigned d = smem_u32(dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void rw_cp4(float* dst, const float* src, bool valid) {
+  const unsigned d = smem_u32(dst);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
+template <int NLP, bool VEC>
+__global__ void __launch_bounds__(32 * RW_WARPS)
+msd_rw_kernel(const float* __restrict__ traj, long long T, long long a_lo, long long a_hi,
+              long long t0, int W, int n_lags, int n_pass, int slab_len,
+              double* __restrict__ msd_sum) {
+  extern __shared__ __align__(16) float rw_smem[];
+  // layout per warp: slab[2][3 * slab_len (padded to 4)] | sacc[n_pass * NLP][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slab_fl = (3 * slab_len + 3) & ~3;
+  const int nl_pad = n_pass * NLP;
+  float* __restrict__ wbase = rw_smem + (size_t)warp * (2 * slab_fl + nl_pad * 32);
+  float* __restrict__ sacc = wbase + 2 * slab_fl;
+  const long long warps_total = (long long)gridDim.x * RW_WARPS;
+  const long long n_el = ((long long)W + n_lags - 1) * 3;   // valid floats of a row from t0 on
+  const int n_chunks = (W + RW_CH - 1) / RW_CH;
+
+  for (int k = lane; k < nl_pad * 32; k += 32) sacc[k] = 0.f;
+  double total[4] = {0.0, 0.0, 0.0, 0.0};   // lane l keeps lags l + 32 r
+
+  auto stage = [&](const float* __restrict__ src, int c) {
+    float* dst = wbase + (c & 1) * slab_fl;
+    const long long e0 = (long long)c * (3 * RW_CH);
+    if (VEC) {
+      for (int q = 4 * lane; q < slab_fl; q += 128) {
+        const long long e = e0 + q;
+        if (e + 3 < n_el) {
+          rw_cp16(dst + q, src + e, true);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) rw_cp4(dst + q + u, src + (e + u < n_el ? e + u : 0), e + u < n_el);
+        }
+      }
+    } else {
+      for (int q = lane; q < slab_fl; q += 32) {
+        const long long e = e0 + q;
+        rw_cp4(dst + q, src + (e < n_el ? e : 0), e < n_el);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  for (long long a = a_lo + (long long)blockIdx.x * RW_WARPS + warp; a < a_hi; a += warps_total) {
+    const float* __restrict__ src = traj + ((size_t)a * T + t0) * 3;
+    stage(src, 0);
+    for (int c = 0; c < n_chunks; ++c) {
+      if (c + 1 < n_chunks) {
+        stage(src, c + 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncwarp();
+      const float* __restrict__ sl = wbase + (c & 1) * slab_fl + 3 * RW_F * lane;
+      // origins, negated: {x, y} as a register pair (FADD2 / FFMA2), z scalar
+      float2 nxy[RW_F];
+      float nz[RW_F];
+#pragma unroll
+      for (int f = 0; f < RW_F; ++f) {
+        nxy[f] = make_float2(-sl[3 * f], -sl[3 * f + 1]);
+        nz[f] = -sl[3 * f + 2];
+      }
+      const int n_valid = min(RW_F, max(0, W - (c * RW_CH + RW_F * lane)));
+#pragma unroll 1
+      for (int g = 0; g < n_pass; ++g) {
+        const float* __restrict__ pwp = sl + 3 * g * NLP;
+        float2 pxy[RW_F + NLP - 1];
+        float pz[RW_F + NLP - 1];
+#pragma unroll
+        for (int j = 0; j < RW_F + NLP - 1; ++j) {
+          pxy[j] = make_float2(pwp[3 * j], pwp[3 * j + 1]);
+          pz[j] = pwp[3 * j + 2];
+        }
+        float2 axy[NLP];
+        float az[NLP];
+#pragma unroll
+        for (int k = 0; k < NLP; ++k) {
+          axy[k] = make_float2(0.f, 0.f);
+          az[k] = 0.f;
+        }
+        if (n_valid == RW_F) {
+#pragma unroll
+          for (int f = 0; f < RW_F; ++f)
+#pragma unroll
+            for (int k = 0; k < NLP; ++k) {
+              const float2 d = __fadd2_rn(pxy[f + k], nxy[f]);
+              const float dz = pz[f + k] + nz[f];
+              axy[k] = __ffma2_rn(d, d, axy[k]);
+              az[k] = fmaf(dz, dz, az[k]);
+            }
+        } else {
+#pragma unroll
+          for (int f = 0; f < RW_F; ++f)
+            if (f < n_valid) {
+#pragma unroll
+              for (int k = 0; k < NLP; ++k) {
+                const float2 d = __fadd2_rn(pxy[f + k], nxy[f]);
+                const float dz = pz[f + k] + nz[f];
+                axy[k] = __ffma2_rn(d, d, axy[k]);
+                az[k] = fmaf(dz, dz, az[k]);
+              }
+            }
+        }
+        float acc[NLP];
+#pragma unroll
+        for (int k = 0; k < NLP; ++k) acc[k] = (axy[k].x + axy[k].y) + az[k];
+        float* __restrict__ sa = sacc + (size_t)g * NLP * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < NLP; ++k) sa[k * 32] += acc[k];
+      }
+      __syncwarp();   // all lanes are done with slab (c & 1) before chunk c + 2 overwrites it
+    }
+    // fold: lane l sums the 32 lane-partials of lags l, l + 32, ... (rotated columns: conflict free)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int lag = lane + 32 * r;
+      if (lag < nl_pad) {
+        float v = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+          const int col = (j + lane) & 31;
+          v += sacc[lag * 32 + col];
+          sacc[lag * 32 + col] = 0.f;
+        }
+        total[r] += (double)v;
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int lag = lane + 32 * r;
+    if (lag < n_lags) atomicAdd(msd_sum + lag, total[r]);
+  }
+}
+
 // ---- Green-Kubo lag products ------------------------------------------------------------
 // P[t][m] += sum_a sum_d v[a,t,d] v[a,t+m,d].  grid.x: origin chunk of ACF_TC frames,
 // grid.y: atom group.  Thread k owns lags k + r*NT and keeps ACF_TC x RL fp64 sums.
@@ -895,10 +1056,40 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
   if (W == 0 || a_lo == a_hi) return MDK_OK;
   MDK_CHECK_ARG(t0 >= 0 && t0 + (long long)(W - 1) + n_lags <= T,
                 "msd_dense: windows [t0=%lld, W=%d, n_lags=%d] exceed T=%lld", t0, W, n_lags, T);
-  int stream_max = 16;  // measured: the ring kernel wins from ~24 lags
-  if (const char* e = getenv("MDK_MSD_STREAM_MAX")) stream_max = atoi(e);
-  if (stream_max > 32) stream_max = 32;
-  if (n_lags <= stream_max && !getenv("MDK_MSD_NO_STREAM")) {
+  // medium lag ranges: register-window kernel (MDK_MSD_RW_MIN / _MAX move the hand-over points)
+  int rw_min = 5, rw_max = 128;
+  if (const char* e = getenv("MDK_MSD_RW_MIN")) rw_min = atoi(e);
+  if (const char* e = getenv("MDK_MSD_RW_MAX")) rw_max = atoi(e);
+  if (rw_max > 128) rw_max = 128;
+  if (n_lags >= rw_min && n_lags <= rw_max) {
+    const bool vec = (T % 4 == 0) && (t0 % 4 == 0) && (reinterpret_cast<uintptr_t>(traj) % 16 == 0);
+    const int NLP = n_lags <= 8 ? 8 : 16;
+    const int n_pass = (n_lags + NLP - 1) / NLP;
+    const int slab_len = RW_CH + n_pass * NLP + RW_F;   // chunk + lag halo (+ slack of the last lane)
+    const size_t per_warp = (size_t)(2 * ((3 * slab_len + 3) & ~3) + n_pass * NLP * 32) * sizeof(float);
+    const size_t smem = per_warp * RW_WARPS;
+    const long long warps = a_hi - a_lo;
+    long long blocks = (warps + RW_WARPS - 1) / RW_WARPS;
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm > 12) per_sm = 12;
+    if (per_sm < 1) per_sm = 1;
+    const long long cap = (long long)sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = as_stream(stream);
+#define MDK_RW_LAUNCH(NLPV, V)                                                                  \
+  do {                                                                                          \
+    MDK_CUDA(cudaFuncSetAttribute(msd_rw_kernel<NLPV, V>,                                       \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    msd_rw_kernel<NLPV, V><<<(unsigned)blocks, 32 * RW_WARPS, smem, st>>>(                      \
+        traj, T, a_lo, a_hi, t0, W, n_lags, n_pass, slab_len, msd_sum);                         \
+  } while (0)
+    if (NLP == 8) { if (vec) MDK_RW_LAUNCH(8, true); else MDK_RW_LAUNCH(8, false); }
+    else { if (vec) MDK_RW_LAUNCH(16, true); else MDK_RW_LAUNCH(16, false); }
+#undef MDK_RW_LAUNCH
+    MDK_LAUNCH_CHECK();
+    return MDK_OK;
+  }
+  if (n_lags <= 16 && !getenv("MDK_MSD_NO_STREAM")) {
     // short lag ranges: HBM-streaming kernel, one warp per atom
     const bool vec = (T % 4 == 0) && (t0 % 4 == 0) && (reinterpret_cast<uintptr_t>(traj) % 16 == 0);
     const long long warps = a_hi - a_lo;
@@ -916,8 +1107,7 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
   } while (0)
     if (n_lags <= 4) MDK_MS_LAUNCH(4);
     else if (n_lags <= 8) MDK_MS_LAUNCH(8);
-    else if (n_lags <= 16) MDK_MS_LAUNCH(16);
-    else MDK_MS_LAUNCH(32);
+    else MDK_MS_LAUNCH(16);
 #undef MDK_MS_LAUNCH
     MDK_LAUNCH_CHECK();
     return MDK_OK;
@@ -948,9 +1138,7 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
   // Short lag ranges take long window chunks (up to ~4096 frames, 48 KB): with few lags per
   // atom the staging, not the arithmetic, is the cost, and it amortises over more origins.
   const int lag_alloc = grouped ? ((n_lags + R - 1) / R) * R + R : lag_span + R;
-  const char* g2 = getenv("MDK_MSD_GROUPED2");
-  const bool grouped2 = grouped && g2 && g2[0] == '1';  // tuning: two-atom kernel with groups
-  const int wc_max = grouped ? (grouped2 ? 2048 : 4096) - lag_alloc : 512;
+  const int wc_max = grouped ? 4096 - lag_alloc : 512;
   const int Wc = W < wc_max ? W : wc_max;
   const int len_alloc = (Wc + lag_alloc + 3) & ~3;  // multiple of 4: float2 views stay aligned
   // the two-atom kernel stages two atoms per sweep
@@ -962,20 +1150,7 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
   const long long groups = (a_hi - a_lo + apc - 1) / apc;
   MDK_CHECK_ARG(groups <= 65535 && lag_blocks <= 65535, "msd_dense: grid too large");
   dim3 grid(chunks, (unsigned)groups, lag_blocks);
-  if (grouped2) {
-    const size_t smem2 = (size_t)6 * len_alloc * sizeof(float);
-#define MDK_MD2G_LAUNCH(RR)                                                                   \
-  do {                                                                                        \
-    MDK_CUDA(cudaFuncSetAttribute(msd_dense2_kernel<true, RR>,                                \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));  \
-    msd_dense2_kernel<true, RR><<<grid, MD_NT, smem2, as_stream(stream)>>>(                   \
-        traj, T, a_lo, a_hi, apc, t0, W, n_lags, Wc, len_alloc, msd_sum);                     \
-  } while (0)
-    if (R == 5) MDK_MD2G_LAUNCH(5);
-    else if (R == 7) MDK_MD2G_LAUNCH(7);
-    else MDK_MD2G_LAUNCH(9);
-#undef MDK_MD2G_LAUNCH
-  } else if (grouped) {
+  if (grouped) {
 #define MDK_MD1_LAUNCH(RR)                                                                    \
   do {                                                                                        \
     MDK_CUDA(cudaFuncSetAttribute(msd_dense_kernel<true, RR>,                                 \

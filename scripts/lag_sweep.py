@@ -20,8 +20,8 @@ from lammps_analysis_b200.engine import acf_series, msd_series, plan_windows  # 
 
 VARIANTS = {
     "default": {},
-    "g2": {"MDK_MSD_GROUPED2": "1"},          # two-atom kernel with window groups (short ranges)
-    "s32": {"MDK_MSD_STREAM_MAX": "32"},      # streaming kernel up to 32 lags
+    "norw": {"MDK_MSD_RW_MAX": "0", "MDK_ACF_RW_MAX": "0"},   # round-1 dispatch: stream <= 16, ring beyond
+    "rw4": {"MDK_MSD_RW_MIN": "2"},                            # register-window kernel from 2 lags
     "nostream": {"MDK_MSD_NO_STREAM": "1", "MDK_ACF_NO_STREAM": "1"},
 }
 
@@ -63,8 +63,9 @@ def main():
     fp32 = K.peak_fp32(True)
     plan = dict(batch_size=T, n_batches=1, remainder=0, minibatch=False)
     for var in args.variants.split(","):
-        for k in list(VARIANTS["g2"]) + list(VARIANTS["s32"]) + list(VARIANTS["nostream"]):
-            os.environ.pop(k, None)
+        for v in VARIANTS.values():
+            for k in v:
+                os.environ.pop(k, None)
         os.environ.update(VARIANTS[var])
         for N in [int(v) for v in args.ranges.split(",")]:
             launches = plan_windows(plan, N, 1, A)
@@ -74,7 +75,7 @@ def main():
                 t = timed(lambda: msd_series(x, launches, N, 1, np.arange(N)), flush)
                 row.update(msd_updates_per_s=upd / t, msd_frac_fp32=9 * upd / t * 1e-12 / fp32,
                            msd_frac_hbm=12.0 * A * T / t * 1e-9 / hbm)
-            if "acf" in args.what and var in ("default", "nostream"):
+            if "acf" in args.what:
                 t = timed(lambda: acf_series(x, launches, N, 1, per_window=False), flush)
                 row.update(acf_updates_per_s=upd / t, acf_frac_fp32=6 * upd / t * 1e-12 / fp32,
                            acf_frac_hbm=12.0 * A * T / t * 1e-9 / hbm)

@@ -56,8 +56,8 @@ def test_rdf_counts_bit_exact(cuda, n_atoms, n_frames, box):
     assert got.sum() > 0
 
 
-@pytest.mark.parametrize("tuning", [0x100, 0x200, 0x300, 0x400, 0x1100, 0x2100, 0x3100,
-                                    0x4100, 0x4400, 0x7100, 0x7400, 0x8400, 0x9400])
+@pytest.mark.parametrize("tuning", [0x100, 0x200, 0x300, 0x400, 0x3100, 0x3400, 0x5100, 0x6100,
+                                    0x6400, 0x8400, 0x9400])
 def test_rdf_kernel_variants_agree(cuda, tuning):
     """Every tile configuration / atomic mode yields the same integers."""
     from lammps_analysis_b200.engine import RdfEngine, to_device_f32
@@ -213,7 +213,7 @@ def test_rdf_single_species_and_empty(cuda):
     assert eng2.counts().sum() == 0
 
 
-@pytest.mark.parametrize("tuning", [0, 0x4000, 0x7000, 0x8400])
+@pytest.mark.parametrize("tuning", [0, 0x3000, 0x6000, 0x8400])
 def test_rdf_sorted_culled_matches_oracle(cuda, tuning):
     """Morton-ordered pack + block culling: same integers as the oracle (two species, so the
     cross-species tiles and the diagonal tiles are both exercised)."""
@@ -235,7 +235,7 @@ def test_rdf_sorted_culled_matches_oracle(cuda, tuning):
         assert np.array_equal(got[p], ref[key]), key
 
 
-@pytest.mark.parametrize("tuning", [0, 0x3000, 0x4000, 0x7000])
+@pytest.mark.parametrize("tuning", [0, 0x3000, 0x6000, 0x8400])
 @pytest.mark.parametrize("cutoff_frac", [0.12, 0.3, 0.4999])
 def test_rdf_culling_is_exact_at_scale(cuda, cutoff_frac, tuning):
     """Size-independent property: the culled, spatially sorted pass returns exactly the

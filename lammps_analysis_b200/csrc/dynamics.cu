@@ -947,6 +947,112 @@ acf_stream_kernel(const float* __restrict__ traj, long long T, long long a_lo, l
   flush();
 }
 
+// ---- Green-Kubo lag products, medium lag ranges (5 .. 128 lags): register-window kernel --------
+// The band-Gram tiles are 64 x 64 in (t, t'): for N < ~200 most of a tile lies outside the band
+// 0 <= t' - t < N (19 % useful at N = 24, 52 % at N = 100).  In (t, m) coordinates the band is a
+// rectangle, so a CTA here owns ARW_CH = 32 x ARW_F consecutive origins and an atom slice; warp g
+// owns the lag block [16 g, 16 g + 16) and lane l the ARW_F consecutive origins 5 l .. 5 l + 4:
+// per atom the lane loads its 5 origin and 5 + 15 window velocities from the slab the CTA staged
+// (16-byte cp.async, double buffered over atoms; lane stride 15 words: conflict free) and
+// updates its 5 x 16 fp32 sums in registers (3 FFMA each) -- one shared-memory read per update,
+// no work outside the band.  The sums are folded into the global fp64 P every ARW_FOLD atoms.
+constexpr int ARW_F = 5;
+constexpr int ARW_CH = 32 * ARW_F;   // 160 origins per CTA
+constexpr int ARW_NLP = 16;
+constexpr int ARW_FOLD = 256;
+
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+acf_rw_kernel(const float* __restrict__ traj, long long T, long long a_lo, long long a_hi,
+              int atoms_per_cta, long long t0, int B, int N, int slab_len,
+              double* __restrict__ P) {
+  extern __shared__ __align__(16) float arw_smem[];   // 2 slabs of 3 * slab_len floats (padded)
+  const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+  const int nthreads = blockDim.x;
+  const int slab_fl = (3 * slab_len + 3) & ~3;
+  const int tc = blockIdx.x * ARW_CH;   // first origin of the chunk (relative to t0)
+  if (tc >= B) return;
+  const long long a0 = a_lo + (long long)blockIdx.y * atoms_per_cta;
+  const long long a1 = min(a_hi, a0 + atoms_per_cta);
+  if (a0 >= a1) return;
+  const long long n_el = (long long)(B - tc) * 3;   // floats of an atom row from the chunk on
+  const int m0 = g * ARW_NLP;
+
+  auto stage = [&](long long a, int buf) {
+    const float* __restrict__ src = traj + ((size_t)a * T + t0 + tc) * 3;
+    float* dst = arw_smem + buf * slab_fl;
+    if (VEC) {
+      for (int q = 4 * tid; q < slab_fl; q += 4 * nthreads) {
+        if (q + 3 < n_el) {
+          rw_cp16(dst + q, src + q, true);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) rw_cp4(dst + q + u, src + (q + u < n_el ? q + u : 0), q + u < n_el);
+        }
+      }
+    } else {
+      for (int q = tid; q < slab_fl; q += nthreads) rw_cp4(dst + q, src + (q < n_el ? q : 0), q < n_el);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[ARW_F][ARW_NLP];
+#pragma unroll
+  for (int f = 0; f < ARW_F; ++f)
+#pragma unroll
+    for (int k = 0; k < ARW_NLP; ++k) acc[f][k] = 0.f;
+
+  auto flush = [&]() {
+#pragma unroll
+    for (int f = 0; f < ARW_F; ++f) {
+      const int t = tc + ARW_F * lane + f;
+#pragma unroll
+      for (int k = 0; k < ARW_NLP; ++k) {
+        const int m = m0 + k;
+        if (t < B && m < N && t + m < B) atomicAdd(P + (size_t)t * N + m, (double)acc[f][k]);
+        acc[f][k] = 0.f;
+      }
+    }
+  };
+
+  stage(a0, 0);
+  int since_fold = 0;
+  for (long long a = a0; a < a1; ++a) {
+    const int buf = (int)((a - a0) & 1);
+    if (a + 1 < a1) {
+      stage(a + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* __restrict__ sl = arw_smem + buf * slab_fl + 3 * ARW_F * lane;
+    float po[ARW_F][3];
+#pragma unroll
+    for (int f = 0; f < ARW_F; ++f)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) po[f][d] = sl[3 * f + d];
+    const float* __restrict__ pwp = sl + 3 * m0;
+    float pw[ARW_F + ARW_NLP - 1][3];
+#pragma unroll
+    for (int j = 0; j < ARW_F + ARW_NLP - 1; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) pw[j][d] = pwp[3 * j + d];
+#pragma unroll
+    for (int f = 0; f < ARW_F; ++f)
+#pragma unroll
+      for (int k = 0; k < ARW_NLP; ++k)
+        acc[f][k] = fmaf(po[f][2], pw[f + k][2],
+                         fmaf(po[f][1], pw[f + k][1], fmaf(po[f][0], pw[f + k][0], acc[f][k])));
+    __syncthreads();   // everyone is done with this slab before the atom after next lands in it
+    if (++since_fold == ARW_FOLD) {
+      flush();
+      since_fold = 0;
+    }
+  }
+  flush();
+}
+
 // ---- prefix sum of P along t (in place, inclusive), 8 lags x 128 time chunks per CTA -----
 constexpr int SCAN_M = 8;
 constexpr int SCAN_C = 128;
@@ -1203,6 +1309,38 @@ extern "C" int mdk_acf_lagprod(const float* traj, long long A, long long T, long
     dim3 grid(chunks, (unsigned)groups);
     acf_lagprod_kernel<<<grid, DYN_NT, smem, as_stream(stream)>>>(traj, T, a_lo, a_hi, apc, t0, B,
                                                                   N, P);
+    MDK_LAUNCH_CHECK();
+    return MDK_OK;
+  }
+  // medium lag ranges: register-window kernel (MDK_ACF_RW_MIN / _MAX move the hand-over points)
+  int arw_min = 5, arw_max = 128;
+  if (const char* e = getenv("MDK_ACF_RW_MIN")) arw_min = atoi(e);
+  if (const char* e = getenv("MDK_ACF_RW_MAX")) arw_max = atoi(e);
+  if (arw_max > 128) arw_max = 128;
+  if (N >= arw_min && N <= arw_max) {
+    const bool vec = (T % 4 == 0) && (t0 % 4 == 0) && (reinterpret_cast<uintptr_t>(traj) % 16 == 0);
+    const int n_blk = (N + ARW_NLP - 1) / ARW_NLP;           // warps per CTA (lag blocks)
+    const int slab_len = ARW_CH + n_blk * ARW_NLP + ARW_F;   // chunk + lag halo (+ last-lane slack)
+    const size_t smem = (size_t)2 * ((3 * slab_len + 3) & ~3) * sizeof(float);
+    const int chunks = (B + ARW_CH - 1) / ARW_CH;
+    // one CTA of n_blk warps holds 127 registers per thread: size the atom split for a few
+    // waves of the CTAs that fit
+    int per_sm = 65536 / (128 * 32 * n_blk);
+    if (per_sm < 1) per_sm = 1;
+    long long want = ((long long)sm_count() * per_sm * 3 + chunks - 1) / chunks;
+    if (want < 1) want = 1;
+    long long apc = (n_atoms + want - 1) / want;
+    if (apc < 32) apc = n_atoms < 32 ? n_atoms : 32;
+    const long long groups = (n_atoms + apc - 1) / apc;
+    MDK_CHECK_ARG(groups <= 65535, "acf_lagprod: too many atom groups");
+    dim3 grid((unsigned)chunks, (unsigned)groups);
+    cudaStream_t st = as_stream(stream);
+    if (vec)
+      acf_rw_kernel<true><<<grid, 32 * n_blk, smem, st>>>(traj, T, a_lo, a_hi, (int)apc, t0, B, N,
+                                                          slab_len, P);
+    else
+      acf_rw_kernel<false><<<grid, 32 * n_blk, smem, st>>>(traj, T, a_lo, a_hi, (int)apc, t0, B, N,
+                                                           slab_len, P);
     MDK_LAUNCH_CHECK();
     return MDK_OK;
   }

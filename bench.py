@@ -478,11 +478,13 @@ def run_gpu_arm(args):
         return tot / reps
 
     probes = []
-    for n_short in (2, 4):
+    for n_short in (2, 4, 8, 16, 32, 64, 100):
+        if n_short >= N:
+            continue
         l_short = plan_windows(plan, n_short, 1, shard)
-        t_msd = probe(lambda: msd_series(unw, l_short, n_short, 1, np.arange(n_short)))
-        t_acf = probe(lambda: acf_series(vel, l_short, n_short, 1, per_window=False))
-        probes.append((n_short, t_msd, t_acf))
+        t_msd = probe(lambda: msd_series(unw, l_short, n_short, 1, np.arange(n_short)), reps=3)
+        t_acf = probe(lambda: acf_series(vel, l_short, n_short, 1, per_window=False), reps=3)
+        probes.append((n_short, t_msd, t_acf, l_short[0][4] * shard * n_short))
 
     # ---- strong scaling: the fixed C5 problem through the calculators' own sharding -------------
     spatial_sort = eng.spatial_sort
@@ -582,13 +584,25 @@ def run_gpu_arm(args):
                               kernel="ionic_current_kernel", algorithmic="12 B per atom-frame")},
         ],
     }
-    line["hbm_regime"] = [
-        {"kernel": k, "data_range": n, "GBps": 12.0 * shard * n_frames / t * 1e-9,
+    # the correlation kernels over the lag range: fraction of BOTH rooflines at every lag count
+    # (HBM: 12 B per atom-frame read once; FP32: 9 FLOP per MSD update, 6 per ACF update).  Kernel
+    # by lag count: <= 4 streaming, 5..128 register-window, beyond: register ring / band Gram
+    def _kernel_name(kind, n):
+        if n <= 4:
+            return f"{kind}_stream_kernel"
+        if n <= 128:
+            return f"{kind}_rw_kernel"
+        return "msd_dense_kernel" if kind == "msd" else "acf_band_kernel"
+
+    line["lag_sweep"] = [
+        {"kernel": _kernel_name(kind, n) + (" (+prefix, windows)" if kind == "acf" else ""),
+         "data_range": n, "updates_per_s": upd / t,
+         "GBps": 12.0 * shard * n_frames / t * 1e-9,
          "frac_of_hbm_peak": 12.0 * shard * n_frames / t * 1e-9 / hbm_peak,
-         "algorithmic": "12 B per atom-frame read once (series output negligible)"}
-        for n, t_msd, t_acf in probes
-        for k, t in (("msd_stream_kernel", t_msd),
-                     ("acf_stream_kernel (+prefix, windows)", t_acf))]
+         "frac_of_fp32_peak": flop * upd / t * 1e-12 / fp32_peak}
+        for n, t_msd, t_acf, upd in probes
+        for kind, t, flop in (("msd", t_msd, FLOP_PER_MSD), ("acf", t_acf, FLOP_PER_ACF))]
+    line["hbm_regime"] = [e for e in line["lag_sweep"] if e["data_range"] <= 8]
     if strong is not None:
         line["strong"] = strong
     if cpu is not None:

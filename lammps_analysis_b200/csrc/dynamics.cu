@@ -473,6 +473,7 @@ msd_stream_kernel(const float* __restrict__ traj, long long T, long long a_lo, l
 constexpr int RW_F = 7;
 constexpr int RW_CH = 32 * RW_F;
 constexpr int RW_WARPS = 4;
+constexpr int RW_ST = 3;             // cp.async ring depth (chunks in flight per warp)
 
 __device__ __forceinline__ void rw_cp16(float* dst, const float* src, bool valid) {
   const unsigned d = smem_u32(dst);
@@ -491,12 +492,12 @@ msd_rw_kernel(const float* __restrict__ traj, long long T, long long a_lo, long 
               long long t0, int W, int n_lags, int n_pass, int slab_len,
               double* __restrict__ msd_sum) {
   extern __shared__ __align__(16) float rw_smem[];
-  // layout per warp: slab[2][3 * slab_len (padded to 4)] | sacc[n_pass * NLP][32]
+  // layout per warp: slab[RW_ST][3 * slab_len (padded to 4)] | sacc[n_pass * NLP][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slab_fl = (3 * slab_len + 3) & ~3;
   const int nl_pad = n_pass * NLP;
-  float* __restrict__ wbase = rw_smem + (size_t)warp * (2 * slab_fl + nl_pad * 32);
-  float* __restrict__ sacc = wbase + 2 * slab_fl;
+  float* __restrict__ wbase = rw_smem + (size_t)warp * (RW_ST * slab_fl + nl_pad * 32);
+  float* __restrict__ sacc = wbase + RW_ST * slab_fl;
   const long long warps_total = (long long)gridDim.x * RW_WARPS;
   const long long n_el = ((long long)W + n_lags - 1) * 3;   // valid floats of a row from t0 on
   const int n_chunks = (W + RW_CH - 1) / RW_CH;
@@ -505,7 +506,7 @@ msd_rw_kernel(const float* __restrict__ traj, long long T, long long a_lo, long 
   double total[4] = {0.0, 0.0, 0.0, 0.0};   // lane l keeps lags l + 32 r
 
   auto stage = [&](const float* __restrict__ src, int c) {
-    float* dst = wbase + (c & 1) * slab_fl;
+    float* dst = wbase + (c % RW_ST) * slab_fl;
     const long long e0 = (long long)c * (3 * RW_CH);
     if (VEC) {
       for (int q = 4 * lane; q < slab_fl; q += 128) {
@@ -528,16 +529,17 @@ msd_rw_kernel(const float* __restrict__ traj, long long T, long long a_lo, long 
 
   for (long long a = a_lo + (long long)blockIdx.x * RW_WARPS + warp; a < a_hi; a += warps_total) {
     const float* __restrict__ src = traj + ((size_t)a * T + t0) * 3;
-    stage(src, 0);
+#pragma unroll
+    for (int st = 0; st < RW_ST - 1; ++st) {
+      if (st < n_chunks) stage(src, st);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     for (int c = 0; c < n_chunks; ++c) {
-      if (c + 1 < n_chunks) {
-        stage(src, c + 1);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-      } else {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-      }
-      __syncwarp();
-      const float* __restrict__ sl = wbase + (c & 1) * slab_fl + 3 * RW_F * lane;
+      asm volatile("cp.async.wait_group %0;" ::"n"(RW_ST - 2) : "memory");
+      __syncwarp();   // chunk c is visible to all lanes, and all lanes have left chunk c - 1
+      if (c + RW_ST - 1 < n_chunks) stage(src, c + RW_ST - 1);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+      const float* __restrict__ sl = wbase + (c % RW_ST) * slab_fl + 3 * RW_F * lane;
       // origins, negated: {x, y} as a register pair (FADD2 / FFMA2), z scalar
       float2 nxy[RW_F];
       float nz[RW_F];
@@ -594,8 +596,9 @@ msd_rw_kernel(const float* __restrict__ traj, long long T, long long a_lo, long 
 #pragma unroll
         for (int k = 0; k < NLP; ++k) sa[k * 32] += acc[k];
       }
-      __syncwarp();   // all lanes are done with slab (c & 1) before chunk c + 2 overwrites it
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();     // the ring is idle before the next atom's first chunks are requested
     // fold: lane l sums the 32 lane-partials of lags l, l + 32, ... (rotated columns: conflict free)
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -960,13 +963,14 @@ constexpr int ARW_F = 5;
 constexpr int ARW_CH = 32 * ARW_F;   // 160 origins per CTA
 constexpr int ARW_NLP = 16;
 constexpr int ARW_FOLD = 256;
+constexpr int ARW_ST = 4;            // cp.async ring depth (atoms in flight per CTA)
 
 template <bool VEC>
 __global__ void __launch_bounds__(256)
 acf_rw_kernel(const float* __restrict__ traj, long long T, long long a_lo, long long a_hi,
               int atoms_per_cta, long long t0, int B, int N, int slab_len,
               double* __restrict__ P) {
-  extern __shared__ __align__(16) float arw_smem[];   // 2 slabs of 3 * slab_len floats (padded)
+  extern __shared__ __align__(16) float arw_smem[];   // ARW_ST slabs of 3 * slab_len floats (padded)
   const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
   const int nthreads = blockDim.x;
   const int slab_fl = (3 * slab_len + 3) & ~3;
@@ -1015,17 +1019,21 @@ acf_rw_kernel(const float* __restrict__ traj, long long T, long long a_lo, long 
     }
   };
 
-  stage(a0, 0);
+  // ring of ARW_ST slabs: atom a + ARW_ST - 1 is requested while atom a is processed.  One block
+  // barrier per atom does double duty: the slab of atom a is visible to every warp, and every
+  // warp has left atom a - 1, whose slab the new request overwrites.
+#pragma unroll
+  for (int st = 0; st < ARW_ST - 1; ++st) {
+    if (a0 + st < a1) stage(a0 + st, st);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   int since_fold = 0;
   for (long long a = a0; a < a1; ++a) {
-    const int buf = (int)((a - a0) & 1);
-    if (a + 1 < a1) {
-      stage(a + 1, buf ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
+    const int buf = (int)((a - a0) % ARW_ST);
+    asm volatile("cp.async.wait_group %0;" ::"n"(ARW_ST - 2) : "memory");
     __syncthreads();
+    if (a + ARW_ST - 1 < a1) stage(a + ARW_ST - 1, (buf + ARW_ST - 1) % ARW_ST);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
     const float* __restrict__ sl = arw_smem + buf * slab_fl + 3 * ARW_F * lane;
     float po[ARW_F][3];
 #pragma unroll
@@ -1044,7 +1052,6 @@ acf_rw_kernel(const float* __restrict__ traj, long long T, long long a_lo, long 
       for (int k = 0; k < ARW_NLP; ++k)
         acc[f][k] = fmaf(po[f][2], pw[f + k][2],
                          fmaf(po[f][1], pw[f + k][1], fmaf(po[f][0], pw[f + k][0], acc[f][k])));
-    __syncthreads();   // everyone is done with this slab before the atom after next lands in it
     if (++since_fold == ARW_FOLD) {
       flush();
       since_fold = 0;
@@ -1172,7 +1179,7 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
     const int NLP = n_lags <= 8 ? 8 : 16;
     const int n_pass = (n_lags + NLP - 1) / NLP;
     const int slab_len = RW_CH + n_pass * NLP + RW_F;   // chunk + lag halo (+ slack of the last lane)
-    const size_t per_warp = (size_t)(2 * ((3 * slab_len + 3) & ~3) + n_pass * NLP * 32) * sizeof(float);
+    const size_t per_warp = (size_t)(RW_ST * ((3 * slab_len + 3) & ~3) + n_pass * NLP * 32) * sizeof(float);
     const size_t smem = per_warp * RW_WARPS;
     const long long warps = a_hi - a_lo;
     long long blocks = (warps + RW_WARPS - 1) / RW_WARPS;
@@ -1313,7 +1320,7 @@ extern "C" int mdk_acf_lagprod(const float* traj, long long A, long long T, long
     return MDK_OK;
   }
   // medium lag ranges: register-window kernel (MDK_ACF_RW_MIN / _MAX move the hand-over points)
-  int arw_min = 5, arw_max = 128;
+  int arw_min = 9, arw_max = 72;   // measured: streaming kernel up to 8 lags, band Gram from ~80
   if (const char* e = getenv("MDK_ACF_RW_MIN")) arw_min = atoi(e);
   if (const char* e = getenv("MDK_ACF_RW_MAX")) arw_max = atoi(e);
   if (arw_max > 128) arw_max = 128;
@@ -1321,7 +1328,7 @@ extern "C" int mdk_acf_lagprod(const float* traj, long long A, long long T, long
     const bool vec = (T % 4 == 0) && (t0 % 4 == 0) && (reinterpret_cast<uintptr_t>(traj) % 16 == 0);
     const int n_blk = (N + ARW_NLP - 1) / ARW_NLP;           // warps per CTA (lag blocks)
     const int slab_len = ARW_CH + n_blk * ARW_NLP + ARW_F;   // chunk + lag halo (+ last-lane slack)
-    const size_t smem = (size_t)2 * ((3 * slab_len + 3) & ~3) * sizeof(float);
+    const size_t smem = (size_t)ARW_ST * ((3 * slab_len + 3) & ~3) * sizeof(float);
     const int chunks = (B + ARW_CH - 1) / ARW_CH;
     // one CTA of n_blk warps holds 127 registers per thread: size the atom split for a few
     // waves of the CTAs that fit

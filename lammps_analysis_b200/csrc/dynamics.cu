@@ -473,7 +473,7 @@ msd_stream_kernel(const float* __restrict__ traj, long long T, long long a_lo, l
 constexpr int RW_F = 7;
 constexpr int RW_CH = 32 * RW_F;
 constexpr int RW_WARPS = 4;
-constexpr int RW_ST = 3;             // cp.async ring depth (chunks in flight per warp)
+constexpr int RW_ST = 2;             // cp.async ring depth (chunks in flight per warp; 3 measured slower: fewer CTAs fit)
 
 __device__ __forceinline__ void rw_cp16(float* dst, const float* src, bool valid) {
   const unsigned d = smem_u32(dst);

@@ -505,25 +505,19 @@ msd_rw_kernel(const float* __restrict__ traj, long long T, long long a_lo, long 
   for (int k = lane; k < nl_pad * 32; k += 32) sacc[k] = 0.f;
   double total[4] = {0.0, 0.0, 0.0, 0.0};   // lane l keeps lags l + 32 r
 
+  // a request copies the slab of chunk c: 16-byte copies up to the end of the row; the rest of
+  // the slab (last chunks only) is zero-filled by 4-byte copies with source size 0
   auto stage = [&](const float* __restrict__ src, int c) {
     float* dst = wbase + (c % RW_ST) * slab_fl;
-    const long long e0 = (long long)c * (3 * RW_CH);
-    if (VEC) {
-      for (int q = 4 * lane; q < slab_fl; q += 128) {
-        const long long e = e0 + q;
-        if (e + 3 < n_el) {
-          rw_cp16(dst + q, src + e, true);
-        } else {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) rw_cp4(dst + q + u, src + (e + u < n_el ? e + u : 0), e + u < n_el);
-        }
-      }
-    } else {
-      for (int q = lane; q < slab_fl; q += 32) {
-        const long long e = e0 + q;
-        rw_cp4(dst + q, src + (e < n_el ? e : 0), e < n_el);
-      }
-    }
+    const int e0 = c * (3 * RW_CH);
+    const int left = (int)min(n_el - e0, (long long)slab_fl);   // valid floats of this slab
+    const int n16 = VEC ? (max(left, 0) & ~3) : 0;
+    const float* __restrict__ s0 = src + e0;
+#pragma unroll 1
+    for (int q = 4 * lane; q < n16; q += 128) rw_cp16(dst + q, s0 + q, true);
+#pragma unroll 1
+    for (int q = n16 + lane; q < slab_fl; q += 32)
+      rw_cp4(dst + q, q < left ? s0 + q : src, q < left);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
@@ -982,22 +976,22 @@ acf_rw_kernel(const float* __restrict__ traj, long long T, long long a_lo, long 
   const long long n_el = (long long)(B - tc) * 3;   // floats of an atom row from the chunk on
   const int m0 = g * ARW_NLP;
 
-  auto stage = [&](long long a, int buf) {
-    const float* __restrict__ src = traj + ((size_t)a * T + t0 + tc) * 3;
+  // 16-byte copies cover the slab up to the end of the row; what lies beyond (last chunk only)
+  // is zero-filled by 4-byte copies with source size 0
+  const int n16 = VEC ? (int)(min((long long)slab_fl, n_el) & ~3ll) : 0;
+  const size_t row_stride = (size_t)T * 3;
+  // this thread's slice of the copy: source pointer of the next atom to request (advanced by one
+  // row per request) and fixed offsets, so that a request is a handful of instructions
+  const float* __restrict__ next_src = traj + ((size_t)a0 * T + t0 + tc) * 3;
+  auto stage = [&](int buf) {
     float* dst = arw_smem + buf * slab_fl;
-    if (VEC) {
-      for (int q = 4 * tid; q < slab_fl; q += 4 * nthreads) {
-        if (q + 3 < n_el) {
-          rw_cp16(dst + q, src + q, true);
-        } else {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) rw_cp4(dst + q + u, src + (q + u < n_el ? q + u : 0), q + u < n_el);
-        }
-      }
-    } else {
-      for (int q = tid; q < slab_fl; q += nthreads) rw_cp4(dst + q, src + (q < n_el ? q : 0), q < n_el);
-    }
+#pragma unroll 1
+    for (int q = 4 * tid; q < n16; q += 4 * nthreads) rw_cp16(dst + q, next_src + q, true);
+#pragma unroll 1
+    for (int q = n16 + tid; q < slab_fl; q += nthreads)
+      rw_cp4(dst + q, next_src + (q < n_el ? q : 0), q < n_el);
     asm volatile("cp.async.commit_group;" ::: "memory");
+    next_src += row_stride;
   };
 
   float acc[ARW_F][ARW_NLP];
@@ -1024,15 +1018,14 @@ acf_rw_kernel(const float* __restrict__ traj, long long T, long long a_lo, long 
   // warp has left atom a - 1, whose slab the new request overwrites.
 #pragma unroll
   for (int st = 0; st < ARW_ST - 1; ++st) {
-    if (a0 + st < a1) stage(a0 + st, st);
+    if (a0 + st < a1) stage(st);
     else asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  int since_fold = 0;
+  int since_fold = 0, buf = 0;
   for (long long a = a0; a < a1; ++a) {
-    const int buf = (int)((a - a0) % ARW_ST);
     asm volatile("cp.async.wait_group %0;" ::"n"(ARW_ST - 2) : "memory");
     __syncthreads();
-    if (a + ARW_ST - 1 < a1) stage(a + ARW_ST - 1, (buf + ARW_ST - 1) % ARW_ST);
+    if (a + ARW_ST - 1 < a1) stage(buf == 0 ? ARW_ST - 1 : buf - 1);
     else asm volatile("cp.async.commit_group;" ::: "memory");
     const float* __restrict__ sl = arw_smem + buf * slab_fl + 3 * ARW_F * lane;
     float po[ARW_F][3];
@@ -1052,6 +1045,7 @@ acf_rw_kernel(const float* __restrict__ traj, long long T, long long a_lo, long 
       for (int k = 0; k < ARW_NLP; ++k)
         acc[f][k] = fmaf(po[f][2], pw[f + k][2],
                          fmaf(po[f][1], pw[f + k][1], fmaf(po[f][0], pw[f + k][0], acc[f][k])));
+    buf = buf + 1 == ARW_ST ? 0 : buf + 1;
     if (++since_fold == ARW_FOLD) {
       flush();
       since_fold = 0;

@@ -1170,7 +1170,22 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
   if (rw_max > 128) rw_max = 128;
   if (n_lags >= rw_min && n_lags <= rw_max) {
     const bool vec = (T % 4 == 0) && (t0 % 4 == 0) && (reinterpret_cast<uintptr_t>(traj) % 16 == 0);
-    const int NLP = n_lags <= 8 ? 8 : 16;
+    // lags per pass: the block size in {8, 12, 16, 20} that pads the lag range least (ties go to
+    // the larger block: fewer shared-memory reads per update)
+    int NLP = 16;
+    if (const char* e = getenv("MDK_MSD_RW_NLP")) {
+      NLP = atoi(e);
+    } else {
+      int best_pad = 1 << 30;
+      for (int cand : {8, 12, 16, 20}) {
+        const int pad = (n_lags + cand - 1) / cand * cand;
+        if (pad < best_pad || (pad == best_pad && cand > NLP)) {
+          best_pad = pad;
+          NLP = cand;
+        }
+      }
+    }
+    MDK_CHECK_ARG(NLP == 8 || NLP == 12 || NLP == 16 || NLP == 20, "msd_dense: bad MDK_MSD_RW_NLP");
     const int n_pass = (n_lags + NLP - 1) / NLP;
     const int slab_len = RW_CH + n_pass * NLP + RW_F;   // chunk + lag halo (+ slack of the last lane)
     const size_t per_warp = (size_t)(RW_ST * ((3 * slab_len + 3) & ~3) + n_pass * NLP * 32) * sizeof(float);
@@ -1191,7 +1206,9 @@ extern "C" int mdk_msd_dense(const float* traj, long long A, long long T, long l
         traj, T, a_lo, a_hi, t0, W, n_lags, n_pass, slab_len, msd_sum);                         \
   } while (0)
     if (NLP == 8) { if (vec) MDK_RW_LAUNCH(8, true); else MDK_RW_LAUNCH(8, false); }
-    else { if (vec) MDK_RW_LAUNCH(16, true); else MDK_RW_LAUNCH(16, false); }
+    else if (NLP == 12) { if (vec) MDK_RW_LAUNCH(12, true); else MDK_RW_LAUNCH(12, false); }
+    else if (NLP == 16) { if (vec) MDK_RW_LAUNCH(16, true); else MDK_RW_LAUNCH(16, false); }
+    else { if (vec) MDK_RW_LAUNCH(20, true); else MDK_RW_LAUNCH(20, false); }
 #undef MDK_RW_LAUNCH
     MDK_LAUNCH_CHECK();
     return MDK_OK;

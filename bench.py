@@ -260,6 +260,18 @@ def run_gpu_arm(args):
             os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.strong_only:
+        def _barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+        rec = run_strong_leg(args, world, rank, dev, _barrier)
+        if rank == 0:
+            print(json.dumps({"strong": rec}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     steps, warm = max(1, args.steps), max(3, args.warmup)
     n_iter = steps + warm
     small = args.small
@@ -632,7 +644,7 @@ def run_strong_leg(args, world, rank, dev, barrier):
     import tempfile
 
     small = args.small
-    n_sp = N_SPECIES_ATOMS if not small else 16_000
+    n_sp = args.strong_atoms or (N_SPECIES_ATOMS if not small else 16_000)
     n_frames = args.strong_frames or (N_FRAMES if not small else 600)
     N = DATA_RANGE if not small else 100
     n_cfg = args.strong_rdf_configs if not small else 8
@@ -702,7 +714,15 @@ def run_strong_leg(args, world, rank, dev, barrier):
     # warm-up: kernels, NCCL channels, and the page-locked block of the unwrapped positions
     # (its first allocation costs ~0.4 s per GB on these hosts; the store's pool reuses it)
     (_, c_ein, c_gk, _), _, _, _, _ = timed_pass(2)
+    prof = None
+    if args.strong_profile and rank == 0:      # host-side profile of the timed pass (debug aid)
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     (t_rdf, t_ein, t_gk, wall), rdf, ein, gk, h2d = timed_pass(n_cfg)
+    if prof is not None:
+        prof.disable()
+        prof.dump_stats(args.strong_profile)
     n_tot = 2 * n_sp
     W = n_frames - N                # one frame batch, correlation_time 1
     pairs = n_cfg * n_tot * (n_tot - 1) // 2
@@ -741,6 +761,12 @@ def main():
     ap.add_argument("--strong-frames", type=int, default=None,
                     help="frames of the strong-scaling trajectory (default: the full 2,000)")
     ap.add_argument("--strong-rdf-configs", type=int, default=64)
+    ap.add_argument("--strong-atoms", type=int, default=None,
+                    help="atoms per species of the strong-scaling system (default: 500,000)")
+    ap.add_argument("--strong-profile", default=None,
+                    help="write a cProfile of rank 0's timed strong-scaling pass to this file")
+    ap.add_argument("--strong-only", action="store_true",
+                    help="run only the strong-scaling leg and print its record (debug aid)")
     args = ap.parse_args()
 
     if args.gpus > 1 and "RANK" not in os.environ:

@@ -226,7 +226,8 @@ class RadialDistributionFunction(TrajectoryCalculator):
         counts = self.compute_counts()
         # bin counts are bit-exact with the reference rule; this is how many of the sampled
         # pairs sit on an fp32 bin edge (Computation.metadata["tie_report"])
-        self.queue_metadata(tie_report=self.tie_report)
+        self.queue_metadata(tie_report=self.tie_report,
+                            max_bin_count=int(counts.max()) if counts.size else 0)
         x = (self.experiment.units.length / 1e-9) * np.linspace(0.0, self.args.cutoff,
                                                                 self.args.number_of_bins)
         self.counts = {}
@@ -234,4 +235,5 @@ class RadialDistributionFunction(TrajectoryCalculator):
             self.counts[names] = counts[p]
             with np.errstate(invalid="ignore"):
                 y = counts[p].astype(float) * self._calculate_prefactor(names)
-            self.queue_data(data={"x": x.tolist(), "y": y.tolist()}, subjects=names.split("_"))
+            # float series are stored packed and read back as lists (project.encode_results)
+            self.queue_data(data={"x": x, "y": y}, subjects=names.split("_"))

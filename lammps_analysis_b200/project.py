@@ -422,6 +422,13 @@ def _pack_value(val, payload: list, cursor: list):
     if isinstance(val, dict):
         return {str(k): _pack_value(v, payload, cursor) for k, v in val.items()}
     if isinstance(val, np.ndarray):
+        if val.ndim == 1 and val.dtype.kind == "f" and len(val) >= _SERIES_MIN:
+            # a float series goes to the payload as it is (no per-element Python objects)
+            arr = np.ascontiguousarray(val, dtype=np.float64)
+            ref = {"__f64__": [cursor[0], len(arr)]}
+            payload.append(arr)
+            cursor[0] += len(arr)
+            return ref
         val = val.tolist()
     if isinstance(val, (np.floating, np.integer)):
         return val.item()

@@ -99,8 +99,10 @@ def c4(tmp):
     pairs = 1000 * n * (n - 1) / 2
     cn, dt2 = timed("c4 CoordinationNumbers", lambda: _try_cn(exp, rdf))
     print(json.dumps({"config": "C4", "pair_distances_per_s_e2e": pairs / dt,
+                      "max_bin_count": int(rdf.metadata["max_bin_count"]),
                       "max_bin_count_exceeds_int32": bool(
-                          np.nanmax(np.array(rdf["1_1"]["y"])[1:]) > 0), "cn": cn}))
+                          rdf.metadata["max_bin_count"] > 2**31 - 1),
+                      "cn": cn}))
 
 
 def _try_cn(exp, rdf):

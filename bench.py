@@ -254,7 +254,8 @@ def run_gpu_arm(args):
     if world > 1:
         # NCCL's INFO log is the evidence of which ranks joined the communicator: keep whatever the
         # launcher configured, otherwise send it to stderr (stdout stays the one JSON line)
-        if "NCCL_DEBUG" not in os.environ:
+        # (the GPU image presets NCCL_DEBUG to a quieter level, which would hide the rank lines)
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
             os.environ["NCCL_DEBUG"] = "INFO"
             os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
             os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")

@@ -33,7 +33,9 @@ extern "C" {
 #define MDK_EUNSUPPORTED -3 /* valid request outside what the kernels support */
 
 #define MDK_MAX_SPECIES 8
-#define MDK_RDF_SUBTILE 64 /* atoms per bounding box of mdk_rdf_bbox */
+#ifndef MDK_RDF_SUBTILE
+#define MDK_RDF_SUBTILE 32 /* atoms per bounding box of mdk_rdf_bbox */
+#endif
 
 /* flags for mdk_rdf_hist */
 #define MDK_RDF_EXACT_DIV 1 /* true fp32 division + separate mul/sub in the minimum image

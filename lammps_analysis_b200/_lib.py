@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmdk.so")
+# MDK_LIB_PATH: load another build of the same library (A/B runs of compile-time tuning switches)
+LIB_PATH = os.environ.get("MDK_LIB_PATH") or os.path.join(_HERE, "libmdk.so")
 
 MDK_RDF_EXACT_DIV = 1
 MDK_RDF_WRAPPED = 2

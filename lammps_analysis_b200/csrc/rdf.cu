@@ -217,19 +217,36 @@ __device__ __forceinline__ void bin_two(float2 d2, float cut2, float2 inv_step2,
 // (magic_thr = 1.5 * 2^23 + &thr[0], an integer below 2^24 and a multiple of 4), so the masked
 // mantissa IS the address of thr[floor-or-carry(t)]; cnt_delta = &cnt[0] - &thr[0] rides in the
 // ATOMS address as a uniform register.
-// BIN_FRAC fraction bits in the guess (2: M = round(4 t), one lane in four gathers its
-// threshold; 3: M = round(8 t), one in eight, at the cost of a shift per pair: measured +0.9 %
-// on the sorted 10^6-atom frame, -5 % on the unsorted 10^5-atom one, which is ALU bound).  The
-// magic constant carries the table address scaled by 2^(BIN_FRAC - 2) (bin_magic()).
-constexpr int BIN_FRAC = 2;
+// BIN_FRAC fraction bits in the guess, M = round(2^BIN_FRAC t): a lane needs the threshold
+// compare only when the BIN_FRAC low bits of M are all zero, i.e. t lies within 2^-(BIN_FRAC+1)
+// of an integer.  The guess t is off by at most 0.003 bins at 13.5k bins (sqrt.approx 2^-23
+// relative, the fp32 scale 2^-24, the table's own rounding), so up to BIN_FRAC = 6 (zone half
+// width 1/128 = 0.0078) the decision stays exact; beyond that the margin is gone.
+//   2: M = round(4 t) is the byte offset itself, one lane in four gathers its threshold, and
+//      every predicated LDS carries ~8 random addresses (1.3 wavefronts)
+//   6: one lane in 64 -- six LDS in ten find no active lane at all and cost no shared-memory
+//      wavefront (0.4 on average) -- for one extra shift per pair.  The shared-memory pipe is
+//      the limiter of this kernel (90 % busy in the round-1 capture), the ALU pipe is not.
+// The magic constant carries the table address scaled by 2^(BIN_FRAC - 2) (bin_magic()).
+#ifndef MDK_RDF_BIN_FRAC
+#define MDK_RDF_BIN_FRAC 6
+#endif
+// Measured on B200 (10^6 atoms sorted / 10^5 sorted / 10^5 unsorted): 6 bits +2.4 % / +0.7 % /
+// -4.5 % against 2 bits, so the sorted kernel (AM 7) takes 6 and the unsorted one (AM 8), which
+// is ALU bound, keeps 2.
+__host__ __device__ constexpr int bin_frac_of(int am) { return am == 7 ? MDK_RDF_BIN_FRAC : 2; }
+template <int BIN_FRAC>
 __device__ __forceinline__ float bin_magic(uint32_t thr_s) {
   return RINT_MAGIC + static_cast<float>(thr_s << (BIN_FRAC - 2));
 }
+template <int BIN_FRAC>
 __device__ __forceinline__ float bin_scale(float inv_step) {
   return static_cast<float>(1 << BIN_FRAC) * inv_step;
 }
+template <int BIN_FRAC>
 __device__ __forceinline__ void bin_two_c(float2 d2, float clamp2, float2 inv_step4,
                                           float2 magic_thr, uint32_t cnt_delta) {
+  static_assert(BIN_FRAC >= 2 && BIN_FRAC <= 6, "see the error budget above");
   if (BIN_FRAC == 2) {
     asm volatile(
         "{\n"
@@ -267,6 +284,8 @@ __device__ __forceinline__ void bin_two_c(float2 d2, float clamp2, float2 inv_st
         "l"(*reinterpret_cast<unsigned long long*>(&magic_thr)), "r"(cnt_delta)
         : "memory");
   } else {
+    // mantissa = (table address << (BIN_FRAC - 2)) + M: shift the fraction bits out, clear the
+    // two address bits they leave behind (and the exponent bits of the magic constant)
     asm volatile(
         "{\n"
         ".reg .pred m0, m1, q0, q1;\n"
@@ -282,12 +301,12 @@ __device__ __forceinline__ void bin_two_c(float2 d2, float clamp2, float2 inv_st
         "mov.b64 {t0, t1}, tt;\n"
         "mov.b32 b0, t0;\n"
         "mov.b32 b1, t1;\n"
-        "shr.u32 a0, b0, 1;\n"
-        "shr.u32 a1, b1, 1;\n"
-        "and.b32 a0, a0, 0x001ffffc;\n"
-        "and.b32 a1, a1, 0x001ffffc;\n"
-        "and.b32 f0, b0, 7;\n"
-        "and.b32 f1, b1, 7;\n"
+        "shr.u32 a0, b0, %6;\n"
+        "shr.u32 a1, b1, %6;\n"
+        "and.b32 a0, a0, %7;\n"
+        "and.b32 a1, a1, %7;\n"
+        "and.b32 f0, b0, %8;\n"
+        "and.b32 f1, b1, %8;\n"
         "setp.eq.u32 m0, f0, 0;\n"
         "setp.eq.u32 m1, f1, 0;\n"
         "@m0 ld.shared.f32 e0, [a0];\n"
@@ -302,7 +321,8 @@ __device__ __forceinline__ void bin_two_c(float2 d2, float clamp2, float2 inv_st
         "red.shared.add.u32 [a1], 1;\n"
         "}\n" ::"f"(d2.x),
         "f"(d2.y), "f"(clamp2), "l"(*reinterpret_cast<unsigned long long*>(&inv_step4)),
-        "l"(*reinterpret_cast<unsigned long long*>(&magic_thr)), "r"(cnt_delta)
+        "l"(*reinterpret_cast<unsigned long long*>(&magic_thr)), "r"(cnt_delta),
+        "n"(BIN_FRAC - 2), "n"((0x003fffffu >> (BIN_FRAC - 2)) & ~3u), "n"((1 << BIN_FRAC) - 1)
         : "memory");
   }
 }
@@ -340,7 +360,8 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
                                          const float2 (&nxi)[R], const float2 (&nyi)[R],
                                          const float2 (&nzi)[R], const GeoConst& c) {
   constexpr bool WRAP = (AM == 5 || AM == 8);  // wrapped-coordinate minimum image
-  const float2 magic_thr = dup2(bin_magic(c.thr_s));  // see bin_two_c
+  constexpr int BF = bin_frac_of(AM);
+  const float2 magic_thr = dup2(bin_magic<BF>(c.thr_s));  // see bin_two_c
   const float2 magic2 = dup2(RINT_MAGIC), nmagic2 = dup2(-RINT_MAGIC);
   const float2 inv_step2 = dup2(c.inv_step);
   const float2 one2 = dup2(c.onef);
@@ -389,7 +410,7 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
         const float2 zz = __fmul2_rn(rz, rz);
         const float2 d2 = __ffma2_rn(zz, one2, __ffma2_rn(xx, one2, yy));
         if (AM == 7 || AM == 8)
-          bin_two_c(d2, c.clamp2, dup2(bin_scale(c.inv_step)), magic_thr, c.cnt_delta);
+          bin_two_c<BF>(d2, c.clamp2, dup2(bin_scale<BF>(c.inv_step)), magic_thr, c.cnt_delta);
         else
           bin_two(d2, c.cut2, inv_step2, c.thr_c, c.cnt_delta, c.one, c.dump);
       }
@@ -413,8 +434,9 @@ __device__ __forceinline__ void sub_tile_uni(const float* __restrict__ sx,
                                              const float2 (&nzi)[R], const float (&shx)[R],
                                              const float (&shy)[R], const float (&shz)[R],
                                              const GeoConst& c) {
-  const float2 inv_step4 = dup2(bin_scale(c.inv_step));
-  const float2 magic_thr = dup2(bin_magic(c.thr_s));  // see bin_two_c
+  constexpr int BF = bin_frac_of(7);
+  const float2 inv_step4 = dup2(bin_scale<BF>(c.inv_step));
+  const float2 magic_thr = dup2(bin_magic<BF>(c.thr_s));  // see bin_two_c
   const float2 one2 = dup2(c.onef);
 #pragma unroll 1
   for (int jj = jj0; jj < jj0 + SUB; jj += 4) {
@@ -442,7 +464,7 @@ __device__ __forceinline__ void sub_tile_uni(const float* __restrict__ sx,
         const float2 yy = __fmul2_rn(ry, ry);
         const float2 zz = __fmul2_rn(rz, rz);
         const float2 d2 = __ffma2_rn(zz, one2, __ffma2_rn(xx, one2, yy));
-        bin_two_c(d2, c.clamp2, inv_step4, magic_thr, c.cnt_delta);
+        bin_two_c<BF>(d2, c.clamp2, inv_step4, magic_thr, c.cnt_delta);
       }
     }
   }
@@ -457,8 +479,9 @@ __device__ __forceinline__ void sub_tile_uni_row(const float* __restrict__ sx,
                                                  const float* __restrict__ sz, int jj0,
                                                  float2 nx, float2 ny, float2 nz, float shx,
                                                  float shy, float shz, const GeoConst& c) {
-  const float2 inv_step4 = dup2(bin_scale(c.inv_step));
-  const float2 magic_thr = dup2(bin_magic(c.thr_s));
+  constexpr int BF = bin_frac_of(7);
+  const float2 inv_step4 = dup2(bin_scale<BF>(c.inv_step));
+  const float2 magic_thr = dup2(bin_magic<BF>(c.thr_s));
   const float2 one2 = dup2(c.onef);
 #pragma unroll 1
   for (int jj = jj0; jj < jj0 + SUB; jj += 8) {
@@ -488,7 +511,7 @@ __device__ __forceinline__ void sub_tile_uni_row(const float* __restrict__ sx,
         const float2 yy = __fmul2_rn(ry, ry);
         const float2 zz = __fmul2_rn(rz, rz);
         const float2 d2 = __ffma2_rn(zz, one2, __ffma2_rn(xx, one2, yy));
-        bin_two_c(d2, c.clamp2, inv_step4, magic_thr, c.cnt_delta);
+        bin_two_c<BF>(d2, c.clamp2, inv_step4, magic_thr, c.cnt_delta);
       }
     }
   }
@@ -501,8 +524,9 @@ __device__ __forceinline__ void sub_tile_gen_row(const float* __restrict__ sx,
                                                  const float* __restrict__ sz, int jj0,
                                                  float2 nx, float2 ny, float2 nz,
                                                  const GeoConst& c) {
-  const float2 inv_step4 = dup2(bin_scale(c.inv_step));
-  const float2 magic_thr = dup2(bin_magic(c.thr_s));
+  constexpr int BF = bin_frac_of(7);
+  const float2 inv_step4 = dup2(bin_scale<BF>(c.inv_step));
+  const float2 magic_thr = dup2(bin_magic<BF>(c.thr_s));
   const float2 magic2 = dup2(RINT_MAGIC), nmagic2 = dup2(-RINT_MAGIC);
   const float2 one2 = dup2(c.onef);
 #pragma unroll 1
@@ -534,9 +558,34 @@ __device__ __forceinline__ void sub_tile_gen_row(const float* __restrict__ sx,
         const float2 yy = __fmul2_rn(ry, ry);
         const float2 zz = __fmul2_rn(rz, rz);
         const float2 d2 = __ffma2_rn(zz, one2, __ffma2_rn(xx, one2, yy));
-        bin_two_c(d2, c.clamp2, inv_step4, magic_thr, c.cnt_delta);
+        bin_two_c<BF>(d2, c.clamp2, inv_step4, magic_thr, c.cnt_delta);
       }
     }
+  }
+}
+
+// One row group of the warp against a 64-atom column sub-tile that straddles the diagonal of a
+// same-species tile: only pairs j > i count.  Scalar arithmetic, the reference's rounding
+// sequence (general minimum image); a warp meets at most two such blocks per diagonal tile.
+__device__ __forceinline__ void sub_tile_tri(const float* __restrict__ sx,
+                                             const float* __restrict__ sy,
+                                             const float* __restrict__ sz, int jj0, int j_first,
+                                             int i, float nx, float ny, float nz,
+                                             const GeoConst& c, const float* __restrict__ s_thr,
+                                             unsigned int* __restrict__ s_cnt) {
+#pragma unroll 2
+  for (int jj = jj0; jj < jj0 + SUB; ++jj) {
+    float rx = __fadd_rn(sx[jj], nx);
+    float ry = __fadd_rn(sy[jj], ny);
+    float rz = __fadd_rn(sz[jj], nz);
+    const float qx = __fadd_rn(fmaf(rx, c.invLx, RINT_MAGIC), -RINT_MAGIC);
+    const float qy = __fadd_rn(fmaf(ry, c.invLy, RINT_MAGIC), -RINT_MAGIC);
+    const float qz = __fadd_rn(fmaf(rz, c.invLz, RINT_MAGIC), -RINT_MAGIC);
+    rx = fmaf(qx, c.nLx, rx);
+    ry = fmaf(qy, c.nLy, ry);
+    rz = fmaf(qz, c.nLz, rz);
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
+    bin_one(d2, (d2 < c.cut2) && (j_first + jj > i), s_thr, s_cnt, c.inv_step);
   }
 }
 
@@ -749,18 +798,34 @@ __global__ void __launch_bounds__(NT, NT == 384 ? 2 : (CULL ? 512 : 768) / NT) r
       unsigned rmask = 0xffffffffu;
       unsigned umask = 0u;             // AM 7: blocks with a uniform periodic image
       unsigned smask = 0u;             // AM 7: ... whose image shift is not zero
-      float shx = 0.f, shy = 0.f, shz = 0.f;  // AM 7: image shift of block (lane & 15)
+      unsigned tmask = 0u;             // diagonal tiles: blocks that straddle j == i
+      float shx = 0.f, shy = 0.f, shz = 0.f;  // AM 7: image shift of block (lane % (NSUB * R))
+      // A diagonal tile (same species, columns inside this row tile) splits into blocks whose
+      // pairs all have j > i (counted on the fast path like any other block), blocks with
+      // j <= i throughout (skipped) and the few blocks the diagonal runs through (sub_tile_tri).
+      // Block (q, r) of this warp: rows row_base + r * NT + [32 w, 32 w + 32), columns
+      // j0 + q * SUB + [0, SUB).
+      auto diag_status = [&](int q, int r, bool& full, bool& tri) {
+        const int r_lo = r * NT + (tid & ~31);
+        const int c_lo = (j0 - row_base) + q * SUB;
+        full = c_lo > r_lo + 31;
+        tri = !full && (c_lo + SUB - 1 > r_lo);
+      };
       if constexpr (AM == 7) {
-        static_assert(AM != 7 || (R == 4 && NSUB == 4 && CULL), "AM 7 needs 4 x 4 blocks per tile");
-        if (!diag) {
-          // lane l classifies block (q = (l >> 2) & 3, r = l & 3): bit l of the masks
+        static_assert(AM != 7 || (R == 4 && (NSUB == 4 || NSUB == 8) && CULL),
+                      "AM 7 needs 4 row groups x 4 or 8 sub-tiles per tile (one block per lane)");
+        constexpr unsigned BLOCKS = NSUB * R == 32 ? 0xffffffffu : (1u << (NSUB * R)) - 1u;
+        {
+          // lane l classifies block (q = (l >> 2) % NSUB, r = l & 3): bit l of the masks
           const float* __restrict__ cbp =
-              fbox + (size_t)(col_box0 + jt * NSUB + ((tid >> 2) & 3)) * 6;
+              fbox + (size_t)(col_box0 + jt * NSUB + ((tid >> 2) & (NSUB - 1))) * 6;
           float cb[6];
 #pragma unroll
           for (int d = 0; d < 6; ++d) cb[d] = __ldg(cbp + d);
-          const bool live =
-              (mybox[0] <= mybox[3]) && !boxes_far(mybox, cb, P.box, P.cull_eps, P.cull2);
+          bool full = true, tri = false;
+          if (diag) diag_status((tid >> 2) & (NSUB - 1), tid & 3, full, tri);
+          const bool live = full && (mybox[0] <= mybox[3]) &&
+                            !boxes_far(mybox, cb, P.box, P.cull_eps, P.cull2);
           bool uni = live;
           float sh[3];
 #pragma unroll
@@ -776,22 +841,38 @@ __global__ void __launch_bounds__(NT, NT == 384 ? 2 : (CULL ? 512 : 768) / NT) r
           shx = sh[0];
           shy = sh[1];
           shz = sh[2];
-          rmask = __ballot_sync(0xffffffffu, live) & 0xffffu;
-          umask = __ballot_sync(0xffffffffu, uni) & 0xffffu;
+          rmask = __ballot_sync(0xffffffffu, live) & BLOCKS;
+          umask = __ballot_sync(0xffffffffu, uni) & BLOCKS;
           smask = __ballot_sync(0xffffffffu, shx != 0.f || shy != 0.f || shz != 0.f) & umask;
+          tmask = __ballot_sync(0xffffffffu, tri) & BLOCKS;
         }
-      } else if (CULL && !diag) {
-        rmask = 0u;
+      } else {
+        if (CULL) {
+          rmask = 0u;
 #pragma unroll
-        for (int q = 0; q < NSUB; ++q) {
-          const float* __restrict__ cb6 = fbox + (size_t)(col_box0 + jt * NSUB + q) * 6;
+          for (int q = 0; q < NSUB; ++q) {
+            const float* __restrict__ cb6 = fbox + (size_t)(col_box0 + jt * NSUB + q) * 6;
 #pragma unroll
-          for (int r = 0; r < R; ++r)
-            if (!boxes_far(wbox[r], cb6, P.box, P.cull_eps, P.cull2)) rmask |= 1u << (q * R + r);
+            for (int r = 0; r < R; ++r)
+              if (!boxes_far(wbox[r], cb6, P.box, P.cull_eps, P.cull2)) rmask |= 1u << (q * R + r);
+          }
+        }
+        if (diag) {
+          unsigned fmask = 0u;
+#pragma unroll
+          for (int q = 0; q < NSUB; ++q)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              bool full, tri;
+              diag_status(q, r, full, tri);
+              fmask |= (full ? 1u : 0u) << (q * R + r);
+              tmask |= (tri ? 1u : 0u) << (q * R + r);
+            }
+          rmask &= fmask;
         }
       }
 
-      if (!EXACT && !diag && !GLOBAL_HIST) {
+      if (!EXACT && !GLOBAL_HIST) {
         constexpr unsigned FULL = (1u << R) - 1u;
 #pragma unroll 1
         for (int q = 0; q < NSUB; ++q) {
@@ -829,13 +910,24 @@ __global__ void __launch_bounds__(NT, NT == 384 ? 2 : (CULL ? 512 : 768) / NT) r
                 if ((mm >> r) & 1u)  // warp-uniform
                   sub_tile_gen_row(sx, sy, sz, q * SUB, nxi[r], nyi[r], nzi[r], geo);
             }
-          } else if (!CULL || m == FULL)
+          } else if (m == FULL)
             sub_tile<false, R, AM, (CULL ? 2 : 4)>(m, sx, sy, sz, q * SUB, nxi, nyi, nzi, geo);
           else if (m != 0u)
             sub_tile<true, R, AM, 2>(m, sx, sy, sz, q * SUB, nxi, nyi, nzi, geo);
         }
+        if (tmask != 0u) {  // diagonal tiles only
+#pragma unroll 1
+          for (int q = 0; q < NSUB; ++q) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+              if ((tmask >> (q * R + r)) & 1u)  // warp-uniform
+                sub_tile_tri(sx, sy, sz, q * SUB, j0, row_base + r * NT + tid, nxi[r].x, nyi[r].x,
+                             nzi[r].x, geo, s_thr, s_cnt);
+          }
+        }
       } else {
-        // diagonal tiles (j > i mask) and the exact-division fallback: scalar path
+        // exact-division fallback and global-memory tables: scalar path (j > i mask on diagonal
+        // tiles)
         for (int jj = 0; jj < TJ; ++jj) {
           const float xj = sx[jj], yj = sy[jj], zj = sz[jj];
           const int j = j0 + jj;

@@ -9,6 +9,7 @@ Each function names the reference code it replaces (paths relative to the MDSuit
 from __future__ import annotations
 
 import ctypes as C
+import os
 import functools
 import itertools
 from dataclasses import dataclass, field
@@ -195,7 +196,7 @@ def coord_extent(pos_soa: torch.Tensor, n_frames: int, n_pad: int) -> np.ndarray
     return mm.cpu().numpy()
 
 
-RDF_SUBTILE = 64  # MDK_RDF_SUBTILE
+RDF_SUBTILE = int(os.environ.get("MDK_RDF_SUBTILE", 32))  # MDK_RDF_SUBTILE (env: A/B builds)
 
 
 def rdf_sort_workspace(max_atoms: int) -> int:

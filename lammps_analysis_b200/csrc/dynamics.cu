@@ -534,7 +534,9 @@ msd_rw_kernel(const float* __restrict__ traj, long long T, long long a_lo, long 
       if (c + RW_ST - 1 < n_chunks) stage(src, c + RW_ST - 1);
       else asm volatile("cp.async.commit_group;" ::: "memory");
       const float* __restrict__ sl = wbase + (c % RW_ST) * slab_fl + 3 * RW_F * lane;
-      // origins, negated: {x, y} as a register pair (FADD2 / FFMA2), z scalar
+      // origins, negated: {x, y} as a register pair (FADD2 / FFMA2); the z components of two
+      // CONSECUTIVE origins share a register pair as well, so that a pair of origins costs six
+      // packed instructions per lag (3 FADD2 + 3 FFMA2) instead of eight
       float2 nxy[RW_F];
       float nz[RW_F];
 #pragma unroll
@@ -546,46 +548,62 @@ msd_rw_kernel(const float* __restrict__ traj, long long T, long long a_lo, long 
 #pragma unroll 1
       for (int g = 0; g < n_pass; ++g) {
         const float* __restrict__ pwp = sl + 3 * g * NLP;
-        float2 pxy[RW_F + NLP - 1];
-        float pz[RW_F + NLP - 1];
+        constexpr int WN = RW_F + NLP - 1;      // window positions of a pass
+        float2 pxy[WN];
+        // z of the window as register pairs in both alignments: ze[i] = {z(2i), z(2i+1)},
+        // zo[i] = {z(2i+1), z(2i+2)} (origin pair (f, f+1), f even, at lag k needs the pair
+        // starting at f + k, whose parity is that of k)
+        float2 ze[(WN + 1) / 2], zo[WN / 2];
 #pragma unroll
-        for (int j = 0; j < RW_F + NLP - 1; ++j) {
-          pxy[j] = make_float2(pwp[3 * j], pwp[3 * j + 1]);
-          pz[j] = pwp[3 * j + 2];
-        }
+        for (int j = 0; j < WN; ++j) pxy[j] = make_float2(pwp[3 * j], pwp[3 * j + 1]);
+#pragma unroll
+        for (int i = 0; i < (WN + 1) / 2; ++i)
+          ze[i] = make_float2(pwp[6 * i + 2], 2 * i + 1 < WN ? pwp[6 * i + 5] : 0.f);
+#pragma unroll
+        for (int i = 0; i < WN / 2; ++i)
+          zo[i] = make_float2(ze[i].y, 2 * i + 2 < WN ? ze[i + 1 < (WN + 1) / 2 ? i + 1 : i].x : 0.f);
         float2 axy[NLP];
-        float az[NLP];
 #pragma unroll
-        for (int k = 0; k < NLP; ++k) {
-          axy[k] = make_float2(0.f, 0.f);
-          az[k] = 0.f;
-        }
+        for (int k = 0; k < NLP; ++k) axy[k] = make_float2(0.f, 0.f);
         if (n_valid == RW_F) {
 #pragma unroll
-          for (int f = 0; f < RW_F; ++f)
+          for (int k = 0; k < NLP; ++k) {
 #pragma unroll
-            for (int k = 0; k < NLP; ++k) {
-              const float2 d = __fadd2_rn(pxy[f + k], nxy[f]);
-              const float dz = pz[f + k] + nz[f];
-              axy[k] = __ffma2_rn(d, d, axy[k]);
-              az[k] = fmaf(dz, dz, az[k]);
+            for (int f = 0; f + 1 < RW_F; f += 2) {
+              const int j = f + k;
+              const float2 zp = (j & 1) ? zo[j >> 1] : ze[j >> 1];
+              const float2 d0 = __fadd2_rn(pxy[j], nxy[f]);
+              const float2 d1 = __fadd2_rn(pxy[j + 1], nxy[f + 1]);
+              const float2 dz = __fadd2_rn(zp, make_float2(nz[f], nz[f + 1]));
+              axy[k] = __ffma2_rn(d0, d0, axy[k]);
+              axy[k] = __ffma2_rn(d1, d1, axy[k]);
+              axy[k] = __ffma2_rn(dz, dz, axy[k]);
             }
+            if (RW_F & 1) {   // the last origin of an odd count: z scalar
+              const int f = RW_F - 1, j = f + k;
+              const float2 d = __fadd2_rn(pxy[j], nxy[f]);
+              const float dz = ((j & 1) ? ze[j >> 1].y : ze[j >> 1].x) + nz[f];
+              axy[k] = __ffma2_rn(d, d, axy[k]);
+              axy[k].x = fmaf(dz, dz, axy[k].x);
+            }
+          }
         } else {
 #pragma unroll
           for (int f = 0; f < RW_F; ++f)
             if (f < n_valid) {
 #pragma unroll
               for (int k = 0; k < NLP; ++k) {
-                const float2 d = __fadd2_rn(pxy[f + k], nxy[f]);
-                const float dz = pz[f + k] + nz[f];
+                const int j = f + k;
+                const float2 d = __fadd2_rn(pxy[j], nxy[f]);
+                const float dz = ((j & 1) ? ze[j >> 1].y : ze[j >> 1].x) + nz[f];
                 axy[k] = __ffma2_rn(d, d, axy[k]);
-                az[k] = fmaf(dz, dz, az[k]);
+                axy[k].x = fmaf(dz, dz, axy[k].x);
               }
             }
         }
         float acc[NLP];
 #pragma unroll
-        for (int k = 0; k < NLP; ++k) acc[k] = (axy[k].x + axy[k].y) + az[k];
+        for (int k = 0; k < NLP; ++k) acc[k] = axy[k].x + axy[k].y;
         float* __restrict__ sa = sacc + (size_t)g * NLP * 32 + lane;
 #pragma unroll
         for (int k = 0; k < NLP; ++k) sa[k * 32] += acc[k];

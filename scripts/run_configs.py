@@ -94,8 +94,22 @@ def c4(tmp):
     pos = device_fluid(n, T, L, 4, dev)
     exp.add_data(ScriptInput({"1": {"Positions": pos.cpu().numpy()}}, [L] * 3, atom_major=True))
     del pos
+    # one-off costs (lazy loading of the sorted-path kernels, CUB temporaries) are paid by a short
+    # call first, so that the timed call measures the path
+    timed("c4 warm-up call (16 frames; loads the sorted-path kernels)", lambda:
+          exp.run.RadialDistributionFunction(number_of_configurations=16, plot=False))
+    exp.store.invalidate()
+    prof = None
+    if os.environ.get("MDK_PROFILE"):
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     rdf, dt = timed("c4 RadialDistributionFunction(1000 frames of 100k atoms)", lambda:
                     exp.run.RadialDistributionFunction(number_of_configurations=1000, plot=False))
+    if prof is not None:
+        import pstats
+        prof.disable()
+        pstats.Stats(prof).sort_stats("cumulative").print_stats(30)
     pairs = 1000 * n * (n - 1) / 2
     cn, dt2 = timed("c4 CoordinationNumbers", lambda: _try_cn(exp, rdf))
     print(json.dumps({"config": "C4", "pair_distances_per_s_e2e": pairs / dt,

@@ -698,11 +698,17 @@ def run_strong_leg(args, world, rank, dev, barrier):
         marks[0].record()
         rdf = exp.run.RadialDistributionFunction(number_of_configurations=n_configs, plot=False)
         marks[1].record()
+        from lammps_analysis_b200 import trace as _tr
+        _tr.event("RDF done / Einstein call starts")
         ein = exp.run.EinsteinDiffusionCoefficients(data_range=N, plot=False)
         marks[2].record()
         gk = exp.run.GreenKuboDiffusionCoefficients(data_range=N, plot=False)
         exp.store.flush()           # write-back of the unwrapped positions has landed
         marks[3].record()
+        from lammps_analysis_b200 import trace
+        trace.mark("strong pass: flushed")
+        if rank == 0:
+            trace.dump()
         barrier()
         wall = time.perf_counter() - w0
         t = [marks[i].elapsed_time(marks[i + 1]) * 1e-3 for i in range(3)]

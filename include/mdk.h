@@ -305,6 +305,14 @@ int mdk_lammps_read(const char* path, long long n_atoms, int n_cols, int id_col,
  * measured TFLOP/s in *tflops (2 flop per FMA).  Synchronises the device. */
 int mdk_peak_fp32(int packed, int iters, double* tflops);
 
+/* Store `nbytes` of a device array into page-locked host memory that is mapped into the device
+ * address space (cudaHostAlloc / cudaHostRegister under unified addressing), with SM stores
+ * instead of a copy engine: a result read-back that does not queue behind bulk transfers in
+ * flight on the copy engines.  Both pointers 16-byte aligned.  Replaces the `.numpy()` reads of
+ * the reference's result tensors (einstein_diffusion_coefficients.py:236-248,
+ * green_kubo_self_diffusion_coefficients.py:323-337) on the streamed path. */
+int mdk_store_mapped(const void* src, void* dst_host_mapped, long long nbytes, mdk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

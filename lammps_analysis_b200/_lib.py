@@ -57,6 +57,7 @@ PROTOTYPES = {
     "mdk_flux_sum": [_P, _LL, _LL, _I, _I, _P, _P, _P, _P],
     "mdk_thermal_flux": [_P, _P, _P, _P, _LL, _LL, _P, _P],
     "mdk_peak_fp32": [_I, _I, _P],
+    "mdk_store_mapped": [_P, _P, _LL, _P],
     "mdk_lammps_scan": [C.c_char_p, _P, _P, _P, _P, _P, _I],
     "mdk_lammps_read": [C.c_char_p, _LL, _I, _I, _I, _LL, _P, _P],
 }

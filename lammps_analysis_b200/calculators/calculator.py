@@ -17,6 +17,7 @@ import numpy as np
 from ..planner import BatchPlan, plan_batches
 from ..project import Computation, args_to_parameters, subjects_key
 from ..store import join_path
+from .. import trace
 
 log = logging.getLogger("mdsuite_b200")
 
@@ -36,12 +37,15 @@ def call(func):
             func(cls, *args, **kwargs)
             data = cls.get_computation_data()
             if data is None:
+                trace.mark(f"{cls.analysis_name}: cache miss, running")
                 cls.prepare_db_entry()
                 cls.save_computation_args()
                 cls.run_analysis()
+                trace.mark(f"{cls.analysis_name}: analysis done")
                 cls.save_db_data()
                 func(cls, *args, **kwargs)
                 data = cls.get_computation_data()
+                trace.mark(f"{cls.analysis_name}: stored and read back")
             out[experiment.name] = data
         return out if return_dict else out[self.experiment.name]
 
@@ -193,6 +197,45 @@ class TrajectoryCalculator(Calculator):
                 i0, i1 = (int(v) for v in np.searchsorted(idx, [lo, hi]))
             return store.device(path, row_index=idx[i0:i1]), len(idx), (i0, i1), i0
         return store.device(path, rows=(lo, hi)), store.shape(path)[0], (lo, hi), lo
+
+    def _device_row_blocks(self, path: str, species: str):
+        """``_device_rows`` plus the row blocks the device copy arrives in (store.device_blocks):
+        (traj, n_atoms, a_shard, row_offset, blocks).  ``blocks`` is None when the rows are a
+        fancy selection (uploaded in one piece)."""
+        store = self.experiment.store
+        if isinstance(self.args.atom_selection, dict):
+            return self._device_rows(path, species) + (None,)
+        import torch
+
+        lo, hi = store.owned_rows(path)
+        traj, blocks = store.device_blocks(path)
+        # a block without an event was produced by work already queued on the current stream
+        # (or is complete): one event for "everything queued so far" stands in, so that the
+        # consumer stream never has to wait for the whole current stream -- which, behind an
+        # unwrap pipeline, would mean waiting for its last block
+        fence = None
+        out = []
+        for b0, b1, ev in blocks:
+            if ev is None:
+                if fence is None:
+                    fence = torch.cuda.Event()
+                    fence.record()
+                ev = fence
+            out.append((b0, b1, ev))
+        return traj, store.shape(path)[0], (lo, hi), lo, out
+
+    @staticmethod
+    def _side_stream():
+        """Stream on which a calculator consumes row blocks: the unwrap pipeline queues its
+        kernels on the current stream, so a consumer on the same stream would only start after
+        the last block; on its own stream it follows the blocks as they complete."""
+        import torch
+
+        if TrajectoryCalculator._consumer_stream is None:
+            TrajectoryCalculator._consumer_stream = torch.cuda.Stream()
+        return TrajectoryCalculator._consumer_stream
+
+    _consumer_stream = None
 
     # -- batch plan (:243-297) ------------------------------------------------------------------------------
     def _prepare_managers(self, data_path: list, correct: bool = False) -> BatchPlan:

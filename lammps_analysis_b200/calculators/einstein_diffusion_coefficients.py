@@ -15,6 +15,8 @@ import numpy as np
 from scipy.interpolate import UnivariateSpline
 
 from .. import distributed as D
+from .. import kernels as K
+from .. import trace
 from ..engine import msd_series, plan_windows
 from ..store import join_path
 from .calculator import TrajectoryCalculator, call
@@ -118,13 +120,26 @@ class EinsteinDiffusionCoefficients(TrajectoryCalculator):
         self._prepare_managers([path])
         # only this rank's atom block is uploaded (it is already resident when the unwrap
         # transformation has just produced it)
-        traj, n_atoms, shard, offset = self._device_rows(path, species)
+        # (and the kernel follows the row blocks of that transformation / of the upload)
+        import torch
+
+        traj, n_atoms, shard, offset, blocks = self._device_row_blocks(path, species)
         launches = plan_windows(self.plan.as_dict(), self.args.data_range,
                                 self.args.correlation_time, n_atoms)
-        msd, count = msd_series(traj, launches, self.args.data_range, self.args.correlation_time,
-                                self.args.tau_values, a_shard=shard, row_offset=offset)
-        D.all_reduce_sum_([msd])
-        return msd.cpu().numpy(), count
+        # kernels, reduction and read-back all run on the consumer stream: the current stream
+        # may still hold the unwrap pipeline of the NEXT species, and a read-back queued there
+        # would only complete after its last block
+        cur, side = torch.cuda.current_stream(), self._side_stream()
+        with torch.cuda.stream(side):
+            msd, count = msd_series(traj, launches, self.args.data_range,
+                                    self.args.correlation_time, self.args.tau_values,
+                                    a_shard=shard, row_offset=offset, blocks=blocks)
+            D.all_reduce_sum_([msd])
+            trace.mark(f"Einstein[{species}] MSD kernels enqueued")
+            host, = K.read_back(msd)
+        cur.wait_stream(side)
+        trace.mark(f"Einstein[{species}] MSD on the host")
+        return host, count
 
     # -- :192-215 --------------------------------------------------------------------------------------
     def fit_diff_coeff(self, msd_sum: np.ndarray, count: int, time: np.ndarray) -> dict:
@@ -143,8 +158,11 @@ class EinsteinDiffusionCoefficients(TrajectoryCalculator):
                 "gradient_errors": (np.array(gradient_errors) / 6).tolist()}
 
     def run_calculator(self):
+        trace.mark("Einstein start")
         self.check_input()
+        trace.mark("Einstein dependencies resolved")
         for species in self.args.species:
             time = self._handle_tau_values()
             msd_sum, count = self.compute_msd(species)
             self.queue_data(data=self.fit_diff_coeff(msd_sum, count, time), subjects=[species])
+            trace.mark(f"Einstein[{species}] fit done")

@@ -16,6 +16,8 @@ import numpy as np
 from scipy.integrate import cumulative_trapezoid
 
 from .. import distributed as D
+from .. import kernels as K
+from .. import trace
 from ..engine import acf_series, plan_windows
 from ..store import join_path
 from .calculator import TrajectoryCalculator, call
@@ -69,18 +71,38 @@ class GreenKuboDiffusionCoefficients(TrajectoryCalculator):
         window [W_total]) on the host, in simulation units (no length^2/time^2 factor)."""
         path = join_path(species, self.loaded_property)
         self._prepare_managers([path])
-        traj, n_atoms, shard, offset = self._device_rows(path, species)
+        import torch
+
+        traj, n_atoms, shard, offset, blocks = self._device_row_blocks(path, species)
         launches = plan_windows(self.plan.as_dict(), self.args.data_range,
                                 self.args.correlation_time, n_atoms)
-        acf, count, wins, sizes = acf_series(traj, launches, self.args.data_range,
-                                             self.args.correlation_time, per_window=True,
-                                             a_shard=shard, row_offset=offset)
-        D.all_reduce_sum_([acf] + wins)
-        win_host = np.concatenate([w.cpu().numpy() for w in wins], axis=0) if wins else \
-            np.zeros((0, self.args.data_range))
+        # the lag-product kernel follows the row blocks of the velocity upload
+        cur, side = torch.cuda.current_stream(), self._side_stream()
+        with torch.cuda.stream(side):
+            acf, count, wins, sizes = acf_series(traj, launches, self.args.data_range,
+                                                 self.args.correlation_time, per_window=True,
+                                                 a_shard=shard, row_offset=offset, blocks=blocks)
+            D.all_reduce_sum_([acf] + wins)
+        trace.mark(f"GreenKubo[{species}] kernels enqueued")
+        # the host is about to wait for these kernels and to post-process: queue the upload of
+        # the next species behind this one so that the link stays busy meanwhile
+        self._prefetch_next(species)
+        with torch.cuda.stream(side):
+            got = K.read_back(acf, *wins)
+            acf_host = got[0]
+            win_host = np.concatenate(got[1:], axis=0) if wins else \
+                np.zeros((0, self.args.data_range))
+        cur.wait_stream(side)
         a_sel = np.concatenate([np.full(w.shape[0], s, dtype=float) for w, s in zip(wins, sizes)]) \
             if wins else np.zeros(0)
-        return acf.cpu().numpy(), count, win_host, a_sel
+        trace.mark(f"GreenKubo[{species}] windows on the host")
+        return acf_host, count, win_host, a_sel
+
+    def _prefetch_next(self, species: str):
+        names = list(self.args.species)
+        k = names.index(species) + 1
+        if k < len(names) and not isinstance(self.args.atom_selection, dict):
+            self.experiment.store.device_blocks(join_path(names[k], self.loaded_property))
 
     def postprocessing(self, acf_sum, count, win, a_sel) -> dict:
         units = self.experiment.units
@@ -102,3 +124,4 @@ class GreenKuboDiffusionCoefficients(TrajectoryCalculator):
             acf_sum, count, win, a_sel = self.compute_acf(species)
             self.queue_data(data=self.postprocessing(acf_sum, count, win, a_sel),
                             subjects=[species])
+            trace.mark(f"GreenKubo[{species}] post-processing done")

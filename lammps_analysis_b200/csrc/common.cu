@@ -48,9 +48,41 @@ __global__ void __launch_bounds__(256) peak_fp32_kernel(float* out, int iters, f
   if (s == 12345.678f) out[0] = s;  // keep the chains alive
 }
 
+// Result read-back without a copy engine: the SMs store a (small) device array into page-locked
+// host memory that is mapped into the device address space.
+__global__ void store_mapped_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                    long long n16, const unsigned char* __restrict__ src_tail,
+                                    unsigned char* __restrict__ dst_tail, int tail) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+  if (blockIdx.x == 0 && (int)threadIdx.x < tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+
 }  // namespace mdk
 
 using namespace mdk;
+
+extern "C" int mdk_store_mapped(const void* src, void* dst_host_mapped, long long nbytes,
+                                mdk_stream_t stream) {
+  MDK_CHECK_ARG(nbytes >= 0, "store_mapped: negative size");
+  if (nbytes == 0) return MDK_OK;
+  MDK_CHECK_ARG(src && dst_host_mapped, "store_mapped: null pointer");
+  MDK_CHECK_ARG(reinterpret_cast<uintptr_t>(src) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(dst_host_mapped) % 16 == 0,
+                "store_mapped: pointers must be 16-byte aligned");
+  const long long n16 = nbytes / 16;
+  const int tail = (int)(nbytes - 16 * n16);
+  long long blocks = (n16 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  const unsigned char* s8 = static_cast<const unsigned char*>(src) + 16 * n16;
+  unsigned char* d8 = static_cast<unsigned char*>(dst_host_mapped) + 16 * n16;
+  store_mapped_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      static_cast<const uint4*>(src), static_cast<uint4*>(dst_host_mapped), n16, s8, d8, tail);
+  MDK_LAUNCH_CHECK();
+  return MDK_OK;
+}
 
 extern "C" int mdk_version(void) { return MDK_VERSION; }
 extern "C" const char* mdk_last_error(void) { return g_err; }

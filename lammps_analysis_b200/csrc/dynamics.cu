@@ -716,6 +716,10 @@ acf_lagprod_kernel(const float* __restrict__ traj, long long T, long long a_lo, 
 // [side][dim][64] by 4-byte cp.async (global layout is [A][T][3], so a (atom, 64 frames) slab is
 // 768 contiguous bytes) in a 3-stage ring.  fp32 accumulation runs over at most GB_FOLD atoms
 // (3 * GB_FOLD products), then folds into the global fp64 P with atomicAdd(double).
+// A 12 x 8 tile per thread (96 x 64 per CTA; 4.8 instead of 4 FMAs per operand float, which
+// would leave the FMA pipe as the only limiter) was built and measured in round 2: 4.58e12
+// against 5.46e12 updates/s -- it needs 254 registers (8 warps per SM), capped at 168 it keeps
+// accumulators in local memory, and the wider tiles waste more of the band's edges.  Removed.
 constexpr int GB_T = 64;      // tile edge
 constexpr int GB_NT = 64;     // threads per CTA (2 warps)
 constexpr int GB_KA = 4;      // atoms per pipeline stage (22 KB per CTA with 3 stages)

@@ -56,16 +56,23 @@ __device__ __forceinline__ unsigned hilbert3(unsigned x, unsigned y, unsigned z)
   return (spread3(X[0]) << 2) | (spread3(X[1]) << 1) | spread3(X[2]);
 }
 
+// The frame's coordinates are read from the trajectory ONCE (the trajectory may be page-locked host
+// memory read in place over the host link, 12 bytes at a stride of a whole atom row): the keys
+// kernel parks them in the workspace, the gather after the sort reads them from there.
 __global__ void rdf_keys_kernel(const float* __restrict__ traj, long long T, long long atom_first,
                                 int atom_count, long long frame, float sx, float sy, float sz,
-                                unsigned* __restrict__ keys, unsigned* __restrict__ idx) {
+                                unsigned* __restrict__ keys, unsigned* __restrict__ idx,
+                                float* __restrict__ xyz) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= atom_count) return;
   const float* src = traj + ((size_t)(atom_first + a) * T + frame) * 3;
   const int nc = 1 << SORT_BITS;
+  const float x = __ldg(src), y = __ldg(src + 1), z = __ldg(src + 2);
+  xyz[3 * (size_t)a] = x;
+  xyz[3 * (size_t)a + 1] = y;
+  xyz[3 * (size_t)a + 2] = z;
   // coordinates may lie outside [0, L): wrap the cell index (only the ORDER depends on it)
-  int cx = (int)floorf(__ldg(src) * sx), cy = (int)floorf(__ldg(src + 1) * sy),
-      cz = (int)floorf(__ldg(src + 2) * sz);
+  int cx = (int)floorf(x * sx), cy = (int)floorf(y * sy), cz = (int)floorf(z * sz);
   cx = ((cx % nc) + nc) % nc;
   cy = ((cy % nc) + nc) % nc;
   cz = ((cz % nc) + nc) % nc;
@@ -73,15 +80,14 @@ __global__ void rdf_keys_kernel(const float* __restrict__ traj, long long T, lon
   idx[a] = a;
 }
 
-__global__ void rdf_gather_kernel(const float* __restrict__ traj, long long T, long long atom_first,
-                                  int atom_count, long long frame, const unsigned* __restrict__ idx,
-                                  float* __restrict__ out, long long n_pad, long long dst_first,
-                                  int dst_span) {
+__global__ void rdf_gather_kernel(const float* __restrict__ xyz, int atom_count,
+                                  const unsigned* __restrict__ idx, float* __restrict__ out,
+                                  long long n_pad, long long dst_first, int dst_span) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= dst_span) return;
   float x = __int_as_float(0x7fc00000), y = x, z = x;
   if (a < atom_count) {
-    const float* src = traj + ((size_t)(atom_first + idx[a]) * T + frame) * 3;
+    const float* src = xyz + 3 * (size_t)idx[a];
     x = __ldg(src);
     y = __ldg(src + 1);
     z = __ldg(src + 2);
@@ -143,7 +149,8 @@ using namespace mdk;
 
 extern "C" long long mdk_rdf_sort_workspace(int max_atoms) {
   if (max_atoms < 1) max_atoms = 1;
-  return (long long)(4 * align_up((size_t)max_atoms * 4, 256) + align_up(cub_temp_bytes(max_atoms), 256));
+  return (long long)(4 * align_up((size_t)max_atoms * 4, 256) + align_up((size_t)max_atoms * 12, 256) +
+                     align_up(cub_temp_bytes(max_atoms), 256));
 }
 
 extern "C" int mdk_rdf_pack_sorted(const float* traj, long long A_total, long long T,
@@ -168,20 +175,21 @@ extern "C" int mdk_rdf_pack_sorted(const float* traj, long long A_total, long lo
   unsigned* keys_out = reinterpret_cast<unsigned*>(w + seg);
   unsigned* idx_in = reinterpret_cast<unsigned*>(w + 2 * seg);
   unsigned* idx_out = reinterpret_cast<unsigned*>(w + 3 * seg);
-  void* temp = w + 4 * seg;
-  size_t temp_bytes = (size_t)workspace_bytes - 4 * seg;
+  float* xyz = reinterpret_cast<float*>(w + 4 * seg);
+  const size_t xyz_bytes = align_up((size_t)(atom_count > 0 ? atom_count : 1) * 12, 256);
+  void* temp = w + 4 * seg + xyz_bytes;
+  size_t temp_bytes = (size_t)workspace_bytes - 4 * seg - xyz_bytes;
   const int nc = 1 << SORT_BITS;
   if (atom_count > 0) {
     rdf_keys_kernel<<<(atom_count + 255) / 256, 256, 0, s>>>(
         traj, T, atom_first, atom_count, frame, nc / box[0], nc / box[1], nc / box[2], keys_in,
-        idx_in);
+        idx_in, xyz);
     MDK_LAUNCH_CHECK();
     MDK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, idx_in, idx_out,
                                              atom_count, 0, 3 * SORT_BITS, s));
   }
-  rdf_gather_kernel<<<(dst_span + 255) / 256, 256, 0, s>>>(traj, T, atom_first, atom_count, frame,
-                                                           idx_out, out_frame, n_pad, dst_first,
-                                                           dst_span);
+  rdf_gather_kernel<<<(dst_span + 255) / 256, 256, 0, s>>>(xyz, atom_count, idx_out, out_frame,
+                                                           n_pad, dst_first, dst_span);
   MDK_LAUNCH_CHECK();
   return MDK_OK;
 }

@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import kernels as K
+from . import trace
 from ._lib import MdkError
 
 
@@ -285,46 +286,93 @@ def _local_rows(a_lo, a_hi, a_shard, row_offset, n_rows):
     return lo, hi
 
 
+def _row_blocks(lo, hi, blocks):
+    """[lo, hi) cut along the row blocks a device copy arrives in: yields (l0, l1, event)."""
+    if not blocks:
+        yield lo, hi, None
+        return
+    for b0, b1, ev in blocks:
+        l0, l1 = max(lo, b0), min(hi, b1)
+        if l1 > l0:
+            yield l0, l1, ev
+
+
+def _merge_blocks(blocks, max_launches: int):
+    """Coarsen a block list to at most ``max_launches`` runs of consecutive blocks (each run
+    waits for its last event): for kernels whose per-launch cost is not negligible."""
+    if not blocks or len(blocks) <= max_launches:
+        return blocks
+    per = -(-len(blocks) // max_launches)
+    out = []
+    for i in range(0, len(blocks), per):
+        run = blocks[i:i + per]
+        out.append((run[0][0], run[-1][1], run[-1][2]))
+    return out
+
+
 def msd_series(traj: torch.Tensor, launches, data_range: int, correlation_time: int,
-               tau_values, a_shard=None, row_offset: int = 0):
+               tau_values, a_shard=None, row_offset: int = 0, blocks=None):
     """Returns (msd_sum device float64 [n_tau], count).
 
     ``launches`` are in global atom indices; ``traj`` holds the global rows
     [row_offset, row_offset + traj.shape[0]); ``a_shard`` = (lo, hi) restricts the atoms this
     rank processes (multi-GPU atom sharding).  count is always the full-plan count, computed
-    analytically (einstein_diffusion_coefficients.py:184, :244)."""
+    analytically (einstein_diffusion_coefficients.py:184, :244).
+
+    ``blocks`` = [(r0, r1, event)] (rows of ``traj``; store.device_blocks): the kernel runs per
+    row block as soon as the block's event has fired -- the sums are additive over atoms -- so
+    that it overlaps with the copy / transformation still producing the later blocks."""
     tau_host = np.asarray(tau_values, dtype=np.int32)
     dense = bool(np.array_equal(tau_host, np.arange(len(tau_host))))
     tau = torch.as_tensor(tau_host, device=traj.device)
     out = torch.zeros(len(tau_values), dtype=torch.float64, device=traj.device)
     count = 0
+    stream = torch.cuda.current_stream()
     for a_lo, a_hi, t0, B, W in launches:
         count += W * ((a_hi - a_lo) + 1)
         lo, hi = _local_rows(a_lo, a_hi, a_shard, row_offset, traj.shape[0])
         if hi > lo:
-            K.msd_windowed(traj, lo, hi, t0, W, correlation_time, tau, data_range, out,
-                           dense=dense)
+            for l0, l1, ev in _row_blocks(lo, hi, blocks):
+                if ev is not None:
+                    stream.wait_event(ev)
+                K.msd_windowed(traj, l0, l1, t0, W, correlation_time, tau, data_range, out,
+                               dense=dense)
+                trace.event(f"msd rows [{l0}, {l1}) done")
     return out, count
 
 
 def acf_series(traj: torch.Tensor, launches, data_range: int, correlation_time: int,
-               per_window: bool = True, a_shard=None, row_offset: int = 0):
+               per_window: bool = True, a_shard=None, row_offset: int = 0, blocks=None):
     """Returns (acf_sum device [N], count, [acf_win device [W][N] per launch], [A_sel]).
 
     count follows green_kubo_self_diffusion_coefficients.py:196, :334 (A + 1 per window).
+    ``blocks``: as in msd_series (the lag products are additive over atoms; prefix sums and
+    window sums run once per launch after the last block).
     """
     N = data_range
     out = torch.zeros(N, dtype=torch.float64, device=traj.device)
     wins, sizes = [], []
     count = 0
     scratch = None
+    stream = torch.cuda.current_stream()
+    # every lag-product launch ends with one fp64 atomicAdd per tile element and atom group
+    # (tens of millions per launch): a few launches per dataset, not one per upload block
+    blocks = _merge_blocks(blocks, 4)
     for a_lo, a_hi, t0, B, W in launches:
         count += W * ((a_hi - a_lo) + 1)
         lo, hi = _local_rows(a_lo, a_hi, a_shard, row_offset, traj.shape[0])
         win = torch.zeros(W, N, dtype=torch.float64, device=traj.device) if per_window else None
         if hi > lo:
-            scratch = K.acf_windowed(traj, lo, hi, t0, B, N, W, correlation_time, out, win,
-                                     scratch)
+            if scratch is None or scratch.numel() < B * N:
+                scratch = torch.empty(B * N, dtype=torch.float64, device=traj.device)
+            P = scratch[: B * N]
+            P.zero_()
+            for l0, l1, ev in _row_blocks(lo, hi, blocks):
+                if ev is not None:
+                    stream.wait_event(ev)
+                K.acf_accumulate(traj, l0, l1, t0, B, N, P)
+                trace.event(f"acf rows [{l0}, {l1}) done")
+            K.acf_finish(P, B, N, W, correlation_time, out, win)
         wins.append(win)
         sizes.append(a_hi - a_lo)
     return out, count, wins, sizes

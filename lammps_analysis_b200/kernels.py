@@ -57,6 +57,28 @@ def _need_device_readable(t: torch.Tensor, dtype, what: str):
         raise MdkError(f"{what}: tensor must be contiguous")
 
 
+def read_back(*tensors: torch.Tensor):
+    """Device tensors -> NumPy arrays through ``mdk_store_mapped``: the SMs write the values
+    into mapped page-locked memory on the CURRENT stream and the host waits for that stream
+    only.  A ``.cpu()`` would go through a copy engine, where it queues behind every bulk
+    upload already handed to the engine -- the streamed calculators read their results while
+    the next dataset is on the wire."""
+    lib = _lib.load()
+    outs = []
+    for t in tensors:
+        _need_cuda(t, t.dtype, "read_back source")
+        t = t.contiguous()
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        check(lib.mdk_store_mapped(_ptr(t), C.c_void_p(host.data_ptr()),
+                                   t.numel() * t.element_size(), _stream()), "mdk_store_mapped")
+        _count(1)
+        outs.append((host, t))          # keep the source alive until the stream has run
+    ev = torch.cuda.Event()
+    ev.record()
+    ev.synchronize()
+    return [h.numpy().copy() for h, _ in outs]
+
+
 def sm_count() -> int:
     return _lib.load().mdk_sm_count()
 
@@ -389,16 +411,37 @@ def acf_windowed(traj: torch.Tensor, a_lo: int, a_hi: int, t0: int, B: int, N: i
         scratch = torch.empty(B * N, dtype=torch.float64, device=traj.device)
     P = scratch[: B * N]
     P.zero_()
-    lib = _lib.load()
-    check(lib.mdk_acf_lagprod(_ptr(traj), A, T, a_lo, a_hi, t0, B, N, _ptr(P), _stream()),
+    acf_accumulate(traj, a_lo, a_hi, t0, B, N, P)
+    acf_finish(P, B, N, W, ct, acf_sum, acf_win)
+    return scratch
+
+
+def acf_accumulate(traj: torch.Tensor, a_lo: int, a_hi: int, t0: int, B: int, N: int,
+                   P: torch.Tensor):
+    """P[t][m] += sum over the atoms [a_lo, a_hi) and dimensions of v(t) v(t + m): the lag
+    products of one frame batch.  Additive over atom ranges, so a caller may feed the rows in
+    blocks (as they arrive on the device) before ``acf_finish``."""
+    _need_cuda(traj, torch.float32, "acf traj")
+    _need_cuda(P, torch.float64, "acf lag products")
+    A, T, D = traj.shape
+    if D != 3 or P.numel() < B * N:
+        raise MdkError("acf_accumulate: bad shapes")
+    check(_lib.load().mdk_acf_lagprod(_ptr(traj), A, T, a_lo, a_hi, t0, B, N, _ptr(P), _stream()),
           "mdk_acf_lagprod")
+    _count(1)
+
+
+def acf_finish(P: torch.Tensor, B: int, N: int, W: int, ct: int, acf_sum: torch.Tensor,
+               acf_win: torch.Tensor | None):
+    """Prefix sums of P along t (in place), then acf_sum[m] += sum_w S_w[m] and
+    acf_win[w][m] = S_w[m]."""
+    _need_cuda(acf_sum, torch.float64, "acf out")
     check(
-        lib.mdk_acf_windows(_ptr(P), B, N, W, ct, _ptr(acf_sum),
-                            _ptr(acf_win) if acf_win is not None else None, _stream()),
+        _lib.load().mdk_acf_windows(_ptr(P), B, N, W, ct, _ptr(acf_sum),
+                                    _ptr(acf_win) if acf_win is not None else None, _stream()),
         "mdk_acf_windows",
     )
-    _count(3)
-    return scratch
+    _count(2)
 
 
 # --------------------------------------------------------------------------------------

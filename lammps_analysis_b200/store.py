@@ -26,6 +26,7 @@ from typing import Dict, Optional, Tuple
 import numpy as np
 
 from . import distributed as D
+from . import trace
 from .config import config
 
 
@@ -143,6 +144,12 @@ class TrajectoryStore:
         # dataset's host copy (or replaces it) drains them first (_drain)
         self._copy_stream = None
         self._pending: Dict[str, list] = {}
+        # device copies that are still being filled block by block (an upload in flight on the
+        # upload stream, or a transformation writing row blocks): cache key -> [(r0, r1, event)]
+        # with rows relative to the cached tensor.  device() waits for them; device_blocks() hands
+        # them to a consumer that wants to start on the first rows while the rest arrives.
+        self._upload_stream = None
+        self._block_events: Dict[Tuple, list] = {}
         if directory is not None:
             os.makedirs(directory, exist_ok=True)
             self._load_index()
@@ -381,6 +388,7 @@ class TrajectoryStore:
         for key in [k for k in self._device_cache if path is None or k[0] == path]:
             t = self._device_cache.pop(key)
             self._device_bytes -= t.numel() * t.element_size()
+            self._block_events.pop(key, None)
 
     def device(self, path: str, rows: Optional[Tuple[int, int]] = None,
                row_index: Optional[np.ndarray] = None, device=None):
@@ -403,10 +411,13 @@ class TrajectoryStore:
         hit = self._device_cache.get(key)
         if hit is not None:
             self._device_cache.move_to_end(key)
+            self._wait_blocks(key)
             return hit
         if row_index is None:
-            whole = self._device_cache.get((path, own[0], own[1], str(dev)))
+            wkey = (path, own[0], own[1], str(dev))
+            whole = self._device_cache.get(wkey)
             if whole is not None and own[0] <= lo and hi <= own[1]:
+                self._wait_blocks(wkey)
                 return whole[lo - own[0]:hi - own[0]]   # rows are the leading axis: a view
         self._drain(path)                    # the host copy is read from here on
         r0 = self._row0[path]
@@ -421,8 +432,9 @@ class TrajectoryStore:
         nbytes = int(np.prod(src.shape)) * 4
         budget = self._budget()
         while self._device_cache and self._device_bytes + nbytes > budget:
-            _, old = self._device_cache.popitem(last=False)
+            okey, old = self._device_cache.popitem(last=False)
             self._device_bytes -= old.numel() * old.element_size()
+            self._block_events.pop(okey, None)
         out = torch.empty(src.shape, dtype=torch.float32, device=dev)
         pin = self._pinned.get(path)
         if pin is not None and row_index is None:
@@ -435,6 +447,79 @@ class TrajectoryStore:
         self._device_bytes += nbytes
         return out
 
+    def upload_stream(self, device=None):
+        """The one stream all block-wise host -> device copies of this store are queued on: they
+        share the link anyway, and FIFO order means the dataset requested first is complete
+        first (its consumer starts while the next dataset is still on the wire)."""
+        import torch
+
+        if self._upload_stream is None:
+            self._upload_stream = torch.cuda.Stream(device=device)
+        return self._upload_stream
+
+    def _wait_blocks(self, key):
+        """The current stream waits until a block-wise filled device copy is complete."""
+        import torch
+
+        blocks = self._block_events.pop(key, None)
+        if blocks:
+            cur = torch.cuda.current_stream()
+            for _, _, ev in blocks:
+                if ev is not None:
+                    cur.wait_event(ev)
+
+    def device_blocks(self, path: str, block_bytes: int = 512 << 20, device=None):
+        """The rows this rank owns as a CUDA tensor that may still be filling up, plus the row
+        blocks it arrives in: (tensor, [(r0, r1, event | None), ...]) with rows relative to the
+        tensor.  A consumer launches its kernel on rows [r0, r1) after ``wait_event(event)``
+        and so overlaps with the host -> device copy (or the transformation) that produces the
+        following blocks.  Page-locked datasets are uploaded block by block on a side stream;
+        anything else falls back to ``device()`` and one block."""
+        import torch
+
+        dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        lo, hi = self.owned_rows(path)
+        key = (path, lo, hi, str(dev))
+        hit = self._device_cache.get(key)
+        if hit is not None:
+            self._device_cache.move_to_end(key)
+            return hit, list(self._block_events.get(key) or [(0, hi - lo, None)])
+        pin = self._pinned.get(path)
+        row_bytes = int(np.prod(self._arrays[path].shape[1:])) * 4
+        rows_per = max(1, int(block_bytes // max(row_bytes, 1)))
+        if pin is None or hi - lo <= rows_per:
+            return self.device(path, device=dev), [(0, hi - lo, None)]
+        self._drain(path)
+        nbytes = (hi - lo) * row_bytes
+        budget = self._budget()
+        while self._device_cache and self._device_bytes + nbytes > budget:
+            okey, old = self._device_cache.popitem(last=False)
+            self._device_bytes -= old.numel() * old.element_size()
+            self._block_events.pop(okey, None)
+        out = torch.empty((hi - lo,) + tuple(pin.shape[1:]), dtype=torch.float32, device=dev)
+        up = self.upload_stream(dev)
+        # `out` may be recycled memory whose previous users were queued on the current stream:
+        # the upload is ordered behind what is queued there NOW (not behind later work)
+        fence = torch.cuda.Event()
+        fence.record()
+        up.wait_event(fence)
+        r0 = self._row0[path]
+        blocks = []
+        with torch.cuda.stream(up):
+            for b0 in range(0, hi - lo, rows_per):
+                b1 = min(hi - lo, b0 + rows_per)
+                out[b0:b1].copy_(pin[lo - r0 + b0:lo - r0 + b1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                blocks.append((b0, b1, ev))
+                trace.event(f"{path} upload rows [{b0}, {b1}) done")
+        out.record_stream(up)
+        self.h2d_bytes += nbytes
+        self._device_cache[key] = out
+        self._device_bytes += nbytes
+        self._block_events[key] = blocks
+        return out, list(blocks)
+
     def pinned_tensor(self, path: str):
         """The page-locked host tensor behind this rank's rows of a dataset of an in-memory
         store (or None).  Row 0 of the tensor is global row ``owned_rows(path)[0]``."""
@@ -446,10 +531,11 @@ class TrajectoryStore:
         return any(k[0] == path and k[1] == lo and k[2] == hi
                    for k in self._device_cache if k[1] != "idx")
 
-    def adopt_device(self, path: str, tensor):
+    def adopt_device(self, path: str, tensor, blocks=None):
         """Register a device tensor that already holds this rank's rows of the dataset ``path``
         (e.g. the output a transformation just produced), so that the next calculator does not
-        re-upload it."""
+        re-upload it.  ``blocks`` = [(r0, r1, event)]: the row blocks the producer writes it in
+        (kernels still queued): see device_blocks()."""
         self.invalidate(path)
         lo, hi = self.owned_rows(path)
         if tensor.shape[0] != hi - lo:
@@ -457,6 +543,8 @@ class TrajectoryStore:
         key = (path, lo, hi, str(tensor.device))
         self._device_cache[key] = tensor
         self._device_bytes += tensor.numel() * tensor.element_size()
+        if blocks:
+            self._block_events[key] = list(blocks)
 
     def device_frames(self, path: str, frames, row_index=None, device=None):
         """CUDA float32 [rows][len(frames)][dims] holding only the selected frames of the rows
@@ -499,6 +587,7 @@ class TrajectoryStore:
                 pin[:, t0:t0 + k].copy_(tensor, non_blocking=True)
                 done = torch.cuda.Event()
                 done.record()
+                trace.event(f"{path} write-back rows from {row0} done")
             tensor.record_stream(self._copy_stream)
             self._pending.setdefault(path, []).append(done)
         else:

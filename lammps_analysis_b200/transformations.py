@@ -37,6 +37,7 @@ import numpy as np
 
 from . import distributed as D
 from . import kernels as K
+from . import trace
 from .store import join_path
 
 log = logging.getLogger("mdsuite_b200")
@@ -99,7 +100,7 @@ class Transformations:
     # an extension run (new frames appended) works in time chunks of at most this many bytes;
     # a full run works in blocks of rows (all frames of some atoms) of at most block_bytes
     chunk_bytes: int = 8 << 30
-    block_bytes: int = 3 << 30
+    block_bytes: int = 1 << 30
 
     def __init__(self, input_properties: Iterable = None, output_property=None,
                  scale_function: dict = None, dtype=None):
@@ -247,8 +248,10 @@ class SingleSpeciesTrafo(Transformations):
             lo, hi = store.owned_rows(out_path)
             if hi <= lo:
                 continue
+            trace.mark(f"{type(self).__name__}[{sp}] inputs resolved, output dataset ready")
             if offset == 0:
                 self._run_row_blocks(sp, paths, consts, out_path, lo, hi, n_frames)
+                trace.mark(f"{type(self).__name__}[{sp}] row blocks enqueued")
             else:
                 self._run_appended_frames(sp, paths, consts, out_path, lo, hi, offset, n_frames)
 
@@ -284,11 +287,16 @@ class SingleSpeciesTrafo(Transformations):
             store.invalidate(out_path)
             store.adopt_device(out_path, out_dev)
             return
+        trace.mark("row blocks: device buffers allocated")
         compute = torch.cuda.current_stream()
-        upload = torch.cuda.Stream()
+        upload = store.upload_stream()      # shared: the species queued first is complete first
+        fence = torch.cuda.Event()
+        fence.record()
+        upload.wait_event(fence)            # staging buffers may be recycled memory
         stage = [{n: torch.empty((rows_per,) + tuple(pinned[n].shape[1:]), dtype=torch.float32,
                                  device="cuda") for n in pinned} for _ in range(2)]
         free_ev = [None, None]          # compute is done with staging buffer i
+        done = []                       # (r0, r1, event): rows of `whole` written by the kernel
         row0 = store.owned_rows(paths[names[0]])[0]
         for k, r0 in enumerate(range(lo, hi, rows_per)):
             r1 = min(hi, r0 + rows_per)
@@ -301,6 +309,7 @@ class SingleSpeciesTrafo(Transformations):
                     store.h2d_bytes += (r1 - r0) * int(np.prod(pin.shape[1:])) * 4
                 up_ev = torch.cuda.Event()
                 up_ev.record()
+                trace.event(f"{sp} upload block {k} done")
             compute.wait_event(up_ev)
             batch = dict(consts)
             for n in names:
@@ -316,11 +325,15 @@ class SingleSpeciesTrafo(Transformations):
                 out_dev = whole[r0 - lo:r1 - lo]
             ev = torch.cuda.Event()
             ev.record()
+            trace.event(f"{sp} unwrap block {k} done")
             free_ev[k & 1] = ev
+            done.append((r0 - lo, r1 - lo, ev))
             store.write_from_device(out_path, out_dev, 0, row0=r0)   # asynchronous, side stream
         store.invalidate(out_path)
         if whole is not None:
-            store.adopt_device(out_path, whole)  # stays resident for the calculator
+            # stays resident for the calculator that follows, which may start on the first row
+            # blocks while the later ones are still being uploaded and transformed
+            store.adopt_device(out_path, whole, blocks=done)
 
     def _run_appended_frames(self, sp, paths, consts, out_path, lo, hi, offset, n_frames):
         """Extension after ``Experiment.add_data``: frames [offset, n_frames) only, in time

@@ -20,6 +20,9 @@ class Config:
     device_cache_bytes: Optional[int] = None
     # page-locked host blocks kept for reuse after a dataset is removed or replaced (store.py)
     pinned_pool_bytes: int = 96 << 30
+    # row-block size of block-wise host -> device copies (store.device_blocks): consumers start
+    # on the first block while the rest is on the wire
+    upload_block_bytes: int = 512 << 20
     jupyter: bool = False
 
 

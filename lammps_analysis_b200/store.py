@@ -468,7 +468,7 @@ class TrajectoryStore:
                 if ev is not None:
                     cur.wait_event(ev)
 
-    def device_blocks(self, path: str, block_bytes: int = 512 << 20, device=None):
+    def device_blocks(self, path: str, block_bytes: Optional[int] = None, device=None):
         """The rows this rank owns as a CUDA tensor that may still be filling up, plus the row
         blocks it arrives in: (tensor, [(r0, r1, event | None), ...]) with rows relative to the
         tensor.  A consumer launches its kernel on rows [r0, r1) after ``wait_event(event)``
@@ -478,6 +478,8 @@ class TrajectoryStore:
         import torch
 
         dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if block_bytes is None:
+            block_bytes = config.upload_block_bytes
         lo, hi = self.owned_rows(path)
         key = (path, lo, hi, str(dev))
         hit = self._device_cache.get(key)

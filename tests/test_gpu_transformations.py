@@ -244,3 +244,54 @@ def test_row_block_pipeline_matches_single_block(tmp_path, cuda, monkeypatch):
         assert np.array_equal(exp.store.device(f"{sp}/Unwrapped_Positions").cpu().numpy(), want)
     res = exp.run.EinsteinDiffusionCoefficients(data_range=40, plot=False)
     assert np.isfinite(res["Na"]["diffusion_coefficient"])
+
+
+def test_streamed_calculators_match_one_block(tmp_path, cuda, monkeypatch):
+    """Einstein / Green-Kubo consume their datasets in row blocks as the blocks arrive (unwrap
+    pipeline events, block-wise velocity upload, merged lag-product launches, read-back through
+    mdk_store_mapped): many small ragged blocks must give what one block gives, and the oracle."""
+    from lammps_analysis_b200.config import config
+    from lammps_analysis_b200.file_io import ScriptInput
+    from lammps_analysis_b200.synthetic import nacl_trajectory
+    from lammps_analysis_b200.transformations import CoordinateUnwrapper
+    from oracle import dynamics as od
+    from oracle import transformations as ot
+
+    data, box = nacl_trajectory(250, 160, 9.0, seed=46, sigma_step=0.5)
+    results = []
+    for tag, rows in (("one", 10_000), ("many", 9)):
+        project, exp = _exp(tmp_path / tag, name="stream", timestep=0.002, persist=False)
+        exp.add_data(ScriptInput(data, box, atom_major=True))
+        monkeypatch.setattr(CoordinateUnwrapper, "block_bytes", rows * 160 * 24)
+        monkeypatch.setattr(config, "upload_block_bytes", rows * 160 * 12)
+        ein = exp.run.EinsteinDiffusionCoefficients(data_range=50, plot=False)
+        exp.store.invalidate()          # velocities (and positions) start on the host again
+        gk = exp.run.GreenKuboDiffusionCoefficients(data_range=50, plot=False)
+        results.append((ein.data_dict, gk.data_dict))
+        if tag == "many":
+            _, blocks = exp.store.device_blocks("Na/Velocities")
+            assert len(blocks) == 1     # resident by now: one block
+    (e1, g1), (e2, g2) = results
+    for sp in ("Na", "Cl"):
+        np.testing.assert_allclose(e2[sp]["msd"], e1[sp]["msd"], rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(g2[sp]["acf"], g1[sp]["acf"], rtol=1e-9, atol=1e-18)
+        np.testing.assert_allclose(g2[sp]["integral_uncertainty"], g1[sp]["integral_uncertainty"],
+                                   rtol=1e-7, atol=1e-18)
+        unw = ot.run_unwrap(data[sp]["Positions"], box, batch_size=160)
+        plan = dict(batch_size=160, n_batches=1, remainder=0, minibatch=False)
+        ref, count = od.einstein_msd(unw, plan, 50, 1, np.arange(50))
+        got = np.array(e2[sp]["msd"]) / (exp.units.length ** 2)
+        np.testing.assert_allclose(got, ref / count, rtol=1e-5, atol=1e-12)
+
+
+def test_read_back_equals_cpu_copy(cuda):
+    import torch
+    from lammps_analysis_b200 import kernels as K
+
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(1500, 37, device="cuda", dtype=torch.float64, generator=gen)
+    b = torch.randn(5, device="cuda", dtype=torch.float64, generator=gen)      # 40 bytes: tail path
+    c = torch.arange(1001, device="cuda", dtype=torch.int64)
+    ga, gb, gc = K.read_back(a, b, c)
+    assert np.array_equal(ga, a.cpu().numpy()) and np.array_equal(gb, b.cpu().numpy())
+    assert np.array_equal(gc, c.cpu().numpy())

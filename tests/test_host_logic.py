@@ -459,3 +459,18 @@ def test_kernels_refuse_cpu_tensors():
     with pytest.raises(MdkError):
         K.msd_windowed(torch.zeros(2, 4, 3), 0, 2, 0, 1, 1, torch.zeros(2, dtype=torch.int32), 2,
                        torch.zeros(2, dtype=torch.float64))
+
+
+def test_row_block_helpers():
+    """engine._row_blocks / _merge_blocks: how a launch range is cut along upload blocks."""
+    from lammps_analysis_b200.engine import _merge_blocks, _row_blocks
+
+    blocks = [(0, 10, "a"), (10, 20, "b"), (20, 25, "c")]
+    assert list(_row_blocks(3, 22, blocks)) == [(3, 10, "a"), (10, 20, "b"), (20, 22, "c")]
+    assert list(_row_blocks(12, 15, blocks)) == [(12, 15, "b")]
+    assert list(_row_blocks(4, 9, None)) == [(4, 9, None)]
+    many = [(10 * i, 10 * i + 10, i) for i in range(23)]
+    merged = _merge_blocks(many, 4)
+    assert len(merged) == 4 and merged[0] == (0, 60, 5) and merged[-1] == (180, 230, 22)
+    assert [b[0] for b in merged[1:]] == [b[1] for b in merged[:-1]]      # contiguous
+    assert _merge_blocks(blocks, 4) == blocks and _merge_blocks(None, 4) is None

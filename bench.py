@@ -553,11 +553,13 @@ def run_gpu_arm(args):
         "phases_ms_per_step": {k: 1e3 * v / steps for k, v in t.items()},
         "wall_s_timed_region": wall,
         # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch on this workload
-        # shape (10^6 atoms, 1 frame), ncu --set full capture profiles/r01k_ncu_rdf_final.md
+        # (the bench's own 2 x 500k frame), ncu --set full capture profiles/r02ad_ncu_rdf_final.md
         "roofline": dict(fp32_roof(FLOP_PER_PAIR * pairs_per_frame, t["rdf_kernel"],
-                                   traffic=None if small else 12.64e6),
-                         traffic_unit="bytes per launch (ncu capture r01k; the kernel is "
-                                      "compute bound: 12 MB of coordinates per 5e11 pairs)",
+                                   traffic=None if small else 65.9e6),
+                         traffic_unit="bytes per launch (ncu capture r02ad: 31.4 MB read + 34.5 MB "
+                                      "written; 12 MB of coordinates are algorithmic, the rest is "
+                                      "the flush of the per-CTA histograms -- the kernel is bound "
+                                      "on chip, by the shared-memory pipe)",
                          kernel="rdf_pair_hist_kernel",
                          algorithmic="20 FLOP per pair-distance x 4.999995e11 pairs per launch "
                                      "(all i<j pairs count, including the blocks the kernel "

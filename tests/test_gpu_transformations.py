@@ -257,7 +257,7 @@ def test_streamed_calculators_match_one_block(tmp_path, cuda, monkeypatch):
     from oracle import dynamics as od
     from oracle import transformations as ot
 
-    data, box = nacl_trajectory(250, 160, 9.0, seed=46, sigma_step=0.5)
+    data, box = nacl_trajectory(216, 160, 9.0, seed=46, sigma_step=0.5)
     results = []
     for tag, rows in (("one", 10_000), ("many", 9)):
         project, exp = _exp(tmp_path / tag, name="stream", timestep=0.002, persist=False)
@@ -268,9 +268,8 @@ def test_streamed_calculators_match_one_block(tmp_path, cuda, monkeypatch):
         exp.store.invalidate()          # velocities (and positions) start on the host again
         gk = exp.run.GreenKuboDiffusionCoefficients(data_range=50, plot=False)
         results.append((ein.data_dict, gk.data_dict))
-        if tag == "many":
-            _, blocks = exp.store.device_blocks("Na/Velocities")
-            assert len(blocks) == 1     # resident by now: one block
+        _, blocks = exp.store.device_blocks("Na/Velocities")
+        assert len(blocks) == (12 if tag == "many" else 1)      # 108 rows in blocks of 9
     (e1, g1), (e2, g2) = results
     for sp in ("Na", "Cl"):
         np.testing.assert_allclose(e2[sp]["msd"], e1[sp]["msd"], rtol=1e-12, atol=1e-300)

@@ -73,14 +73,28 @@ def shard_atoms(a_lo: int, a_hi: int, r: int = None, w: int = None) -> Tuple[int
     return lo, lo + base + (1 if r < extra else 0)
 
 
+def _host_staged(d) -> bool:
+    """gloo has no CUDA all-to-all and only some CUDA collectives: with that backend (CPU tests,
+    and the two-ranks-on-one-GPU check of tests/multigpu_check.py) device tensors take a detour
+    through the host.  NCCL, the production backend, works on the device tensors directly."""
+    return d.get_backend() == "gloo"
+
+
 def all_reduce_sum_(tensors: List):
     """In-place sum over ranks of every tensor in ``tensors`` (no-op for one rank).  Issued on
     the current stream right behind the kernels that produced them."""
     d = _dist()
     if d is None or d.get_world_size() == 1:
         return tensors
+    staged = _host_staged(d)
     for t in tensors:
-        if t is not None:
+        if t is None:
+            continue
+        if staged and t.is_cuda:
+            h = t.cpu()
+            d.all_reduce(h, op=d.ReduceOp.SUM)
+            t.copy_(h)
+        else:
             d.all_reduce(t, op=d.ReduceOp.SUM)
     return tensors
 
@@ -118,6 +132,17 @@ def gather_rows(local, n_rows_total: int):
     return out
 
 
+def _all_to_all(d, send, out_splits, in_splits):
+    if _host_staged(d) and send.is_cuda:
+        h_send = send.cpu()
+        h_recv = h_send.new_empty(sum(out_splits))
+        d.all_to_all_single(h_recv, h_send, out_splits, in_splits)
+        return h_recv.to(send.device)
+    recv = send.new_empty(sum(out_splits))
+    d.all_to_all_single(recv, send, out_splits, in_splits)
+    return recv
+
+
 def exchange_frames(local, rows_per_rank, n_frames: int):
     """All-to-all of sampled frames: ``local`` is this rank's atom block of ALL sampled frames,
     a tensor [A_local][n_frames][3]; ``rows_per_rank[q]`` is the block size of rank q.  The
@@ -137,8 +162,7 @@ def exchange_frames(local, rows_per_rank, n_frames: int):
     send = torch.cat([local[:, q::w].reshape(-1) for q in range(w)])
     in_splits = [a_loc * f * 3 for f in f_of]
     out_splits = [int(n) * f_of[r] * 3 for n in rows_per_rank]
-    recv = local.new_empty(sum(out_splits))
-    d.all_to_all_single(recv, send.contiguous(), out_splits, in_splits)
+    recv = _all_to_all(d, send.contiguous(), out_splits, in_splits)
     return recv.view(int(sum(rows_per_rank)), f_of[r], 3)
 
 
@@ -159,6 +183,5 @@ def exchange_frame_groups(local, rows_per_rank, frames_per_rank):
     send = torch.cat([local[:, starts[q]:starts[q + 1]].reshape(-1) for q in range(w)])
     in_splits = [a_loc * int(f) * 3 for f in frames_per_rank]
     out_splits = [int(n) * int(frames_per_rank[r]) * 3 for n in rows_per_rank]
-    recv = local.new_empty(sum(out_splits))
-    d.all_to_all_single(recv, send.contiguous(), out_splits, in_splits)
+    recv = _all_to_all(d, send.contiguous(), out_splits, in_splits)
     return recv.view(int(sum(rows_per_rank)), int(frames_per_rank[r]), 3)

@@ -50,6 +50,7 @@ class RdfEngine:
     # species at least this large are Morton-ordered per frame so that whole blocks of pairs
     # beyond the cutoff can be skipped; below it a tile spans too much of the box to gain
     TIE_ROWS = 1024
+    TIE_PAIRS = 250_000_000
     SORT_BATCH_FRAMES = 16
     SORT_MIN_ATOMS = 80_000    # measured on B200 (uniform-image kernel): -9 % at 50k atoms,
                                # +5 % at 100k, +24 % at 200k, +50 % at 10^6
@@ -84,9 +85,12 @@ class RdfEngine:
         self._bbox = None
         self.record_events = False      # bench.py: CUDA events around every mdk_rdf_hist launch
         self.kernel_events = []
-        # bin-edge tie census on the first packed frame (rows sampled: the first TIE_ROWS atoms
+        # bin-edge tie census on the first packed frame (rows sampled: the first TIE_ROWS atoms,
+        # fewer when that would be more than TIE_PAIRS pair distances -- 1024 rows of a 10^6-atom
+        # frame cost 5 ms, 2 % of a one-frame RDF call --
         # against all atoms); 0 disables it
-        self.tie_rows = self.TIE_ROWS
+        self.tie_rows = int(min(self.TIE_ROWS,
+                                max(64, self.TIE_PAIRS // max(self.layout.n_pad, 1))))
         self.tie_counts = torch.zeros(2, dtype=torch.int64, device=self.device)
         self._tie_done = False
 

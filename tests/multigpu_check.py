@@ -1,4 +1,5 @@
-"""Multi-GPU check, run under torchrun (one rank per GPU, NCCL):
+"""Multi-GPU check, run under torchrun (one rank per GPU, NCCL; MDK_MG_BACKEND=gloo: two ranks on
+one GPU, collectives through the host):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29611 tests/multigpu_check.py
@@ -46,8 +47,15 @@ def run_all(exp):
 def main():
     rank = int(os.environ["RANK"])
     local = int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    if os.environ.get("MDK_MG_BACKEND", "nccl") == "gloo":
+        # a box with ONE GPU: both ranks compute on cuda:0 and exchange through the host (gloo):
+        # the sharding logic, the frame exchange and the reductions are the production code, only
+        # the transport differs
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     config.planner_memory_bytes = 60e9
     sharded = run_all(build(f"sharded{rank}"))
     with D.local_only():
@@ -67,7 +75,7 @@ def main():
                                rtol=1e-6, atol=1e-9 * np.abs(single["ion"]["System"]["acf"]).max())
     dist.barrier()
     if rank == 0:
-        print(f"multigpu_check ok on {dist.get_world_size()} ranks")
+        print(f"multigpu_check ok on {dist.get_world_size()} ranks ({dist.get_backend()})")
     dist.destroy_process_group()
 
 

@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--tunings", default="0")
     ap.add_argument("--sort", type=int, default=-1, help="-1 auto, 0 off, 1 on")
     ap.add_argument("--cutoff-frac", type=float, default=0.0)
+    ap.add_argument("--adf-atoms", type=int, default=100000)
+    ap.add_argument("--adf-frames", type=int, default=4)
     ap.add_argument("--dyn-atoms", type=int, default=20000)
     ap.add_argument("--dyn-frames", type=int, default=2000)
     ap.add_argument("--data-range", type=int, default=500)
@@ -65,6 +67,27 @@ def main():
                  "pairs_per_s": pairs / t, "tflops20": 20 * pairs / t * 1e-12,
                  "inside_frac": float(inside / (n * (n - 1) / 2))}
             print(json.dumps(r), flush=True)
+    if "adf" in what:
+        # triplet-angle histograms (csrc/adf.cu): two species at rho = 0.05 / A^3, cutoff 6 A
+        # (~45 neighbours, ~2,000 ordered neighbour pairs per centre atom)
+        from lammps_analysis_b200.engine import AdfEngine
+
+        n, F = args.adf_atoms, args.adf_frames
+        L = (n / 0.05) ** (1.0 / 3.0)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(11)
+        pos = torch.rand(F, n, 3, device=dev, generator=gen) * L
+        eng = AdfEngine([n // 2, n - n // 2], [L] * 3, 6.0, 500, 4, device=dev)
+        counts = {}
+
+        def run():
+            _, c = eng.add_batch(pos)
+            counts["triples"] = c
+        t = timed(run, reps=2)
+        triples = int(counts["triples"].sum().item())
+        print(json.dumps({"adf_atoms": n, "adf_frames": F, "cutoff": 6.0, "nbins": 500, "s": t,
+                          "triples_histogrammed": triples, "triples_per_s": triples / t,
+                          "centre_atoms_per_s": n * F / t}), flush=True)
     A, T, N = args.dyn_atoms, args.dyn_frames, args.data_range
     if set(what) & {"msd", "acf", "unwrap", "ionic"}:
         traj = device_fluid(A, T, 60.0, 5, dev)

@@ -28,8 +28,12 @@
 //              dump word for the lanes outside the cutoff (general coordinates, small tiles)
 //   4          tables and histogram in global memory (bin counts beyond shared memory)
 //   5          as 2 with the wrapped-coordinate minimum image min(|d|, L - |d|)
-//   7          DEFAULT on sorted frames: uniform-image blocks + clamped gated compare
+//   7          DEFAULT on sorted frames: uniform-image blocks + clamped gated compare (6 fraction
+//              bits in the bin guess: one lane in 64 reads its threshold)
 //   8          DEFAULT on unsorted wrapped frames: wrapped minimum image + clamped gated compare
+//              (2 fraction bits)
+// Same-species tiles on the diagonal run on the same fast paths: blocks above the diagonal are
+// counted, blocks below it skipped, the blocks it crosses go through sub_tile_tri.
 // (round 1 also carried a predicated-red, a per-lane-dump, a 7-fraction-bit and a quarter-bit
 // gated variant -- AM 0, 1, 3, 6; all measured slower, removed in round 2)
 #include "mdk_common.cuh"
@@ -350,7 +354,7 @@ struct GeoConst {
 };
 __device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
 
-// One 64-atom column sub-tile against the row groups selected by the compile-time mask M (bit r
+// One SUB-atom column sub-tile against the row groups selected by the compile-time mask M (bit r
 // = row group r of this warp is within reach).  The arithmetic is the reference's rounding
 // sequence; see the kernel header.
 template <bool MASKED, int R, int AM, int UNROLL>
@@ -419,7 +423,7 @@ __device__ __forceinline__ void sub_tile(unsigned m, const float* __restrict__ s
 }
 
 // Uniform-image variant of sub_tile (AM == 7).  For a block of pairs (32 rows of a warp x one
-// 64-atom column sub-tile) whose bounding boxes show that n = rint((x_j - x_i) / L) is the same
+// SUB-atom column sub-tile) whose bounding boxes show that n = rint((x_j - x_i) / L) is the same
 // integer for every pair of the block (per dimension), the reference's
 //     r = d - rint(d / L) * L          (utils/linalg.py:84-99; here fma(n, -L, d))
 // is d + sh with the warp-uniform sh = -n * L (exact for |n| <= 2): one packed FADD2 per
@@ -470,7 +474,7 @@ __device__ __forceinline__ void sub_tile_uni(const float* __restrict__ sx,
   }
 }
 
-// One row group of the warp against a 64-atom column sub-tile (partially live blocks): eight
+// One row group of the warp against a SUB-atom column sub-tile (partially live blocks): eight
 // columns per trip keep four independent pair couples in flight; no per-row-group branches in
 // the column loop.
 template <bool SHIFT>
@@ -564,7 +568,7 @@ __device__ __forceinline__ void sub_tile_gen_row(const float* __restrict__ sx,
   }
 }
 
-// One row group of the warp against a 64-atom column sub-tile that straddles the diagonal of a
+// One row group of the warp against a SUB-atom column sub-tile that straddles the diagonal of a
 // same-species tile: only pairs j > i count.  Scalar arithmetic, the reference's rounding
 // sequence (general minimum image); a warp meets at most two such blocks per diagonal tile.
 __device__ __forceinline__ void sub_tile_tri(const float* __restrict__ sx,
@@ -794,7 +798,7 @@ __global__ void __launch_bounds__(NT, NT == 384 ? 2 : (CULL ? 512 : 768) / NT) r
       const int j0 = col_base + jt * TJ;
       const bool diag = same && (j0 < row_base + TI);  // tile overlaps this row tile
 
-      // which of this warp's row groups can reach which 64-atom sub-tile: bit (q * R + r)
+      // which of this warp's row groups can reach which SUB-atom sub-tile: bit (q * R + r)
       unsigned rmask = 0xffffffffu;
       unsigned umask = 0u;             // AM 7: blocks with a uniform periodic image
       unsigned smask = 0u;             // AM 7: ... whose image shift is not zero

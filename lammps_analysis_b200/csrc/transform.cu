@@ -31,6 +31,25 @@ __device__ __forceinline__ float jump_of(float p, float prev, float inv_l32, dou
   return n;
 }
 
+// The same decision for two (position, previous position) pairs on packed instructions.  The
+// fast result stands when |q - rint(q)| is clearly below 1/2 (q = rint(q) + r with |r| <= 1/2,
+// so "within 1e-3 of a half-integer" is |r| > 0.499) and |q| < 1000; otherwise the reference's
+// fp64 division decides.
+__device__ __forceinline__ void jump_pair(float2 cur, float2 prev, float inv_l32, double l64,
+                                          float& j0, float& j1) {
+  const float2 q = __fmul2_rn(__fadd2_rn(cur, make_float2(-prev.x, -prev.y)),
+                              make_float2(inv_l32, inv_l32));
+  const float2 n = __fadd2_rn(__fadd2_rn(q, make_float2(12582912.0f, 12582912.0f)),
+                              make_float2(-12582912.0f, -12582912.0f));
+  const float2 r = __fadd2_rn(q, make_float2(-n.x, -n.y));
+  j0 = n.x;
+  j1 = n.y;
+  if (fabsf(r.x) > 0.499f || !(fabsf(q.x) < 1000.f))
+    j0 = (float)rint(((double)cur.x - (double)prev.x) / l64);
+  if (fabsf(r.y) > 0.499f || !(fabsf(q.y) < 1000.f))
+    j1 = (float)rint(((double)cur.y - (double)prev.y) / l64);
+}
+
 template <bool L32>
 __device__ __forceinline__ float shifted(float x, float m, double l64, float l32) {
   if (m == 0.f) return x;
@@ -119,50 +138,51 @@ unwrap_kernel(const float* __restrict__ pos, long long A, long long T, double lx
     const int last_lane = (int)((min((long long)UNW_CH, T - tb) - 1) / UNW_F);
     const int last_f = (int)((min((long long)UNW_CH, T - tb) - 1) % UNW_F);
     float o[UNW_F][3];
-    bool any_jump = false;
     float jl[UNW_F][3];  // inclusive prefix of the jumps inside the lane
+    float off[3] = {0.f, 0.f, 0.f};  // exclusive scan of the lane totals
+    float tot[3] = {0.f, 0.f, 0.f};  // jumps of the whole chunk
+    static_assert(UNW_F == 4, "the packed jump test below pairs frames (0, 1) and (2, 3)");
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       float q = __shfl_up_sync(0xffffffffu, p[UNW_F - 1][d], 1);
       if (lane == 0) q = prevp[d];
+      // two frames per packed instruction: (p0, p1) - (q, p0) and (p2, p3) - (p1, p2)
+      float j4[UNW_F];
+      jump_pair(make_float2(p[0][d], p[1][d]), make_float2(q, p[0][d]), il[d], l64[d], j4[0],
+                j4[1]);
+      jump_pair(make_float2(p[2][d], p[3][d]), make_float2(p[1][d], p[2][d]), il[d], l64[d],
+                j4[2], j4[3]);
       float run = 0.f;
+      bool jumped = false;   // any jump among this lane's frames (two may cancel in `run`)
 #pragma unroll
       for (int f = 0; f < UNW_F; ++f) {
-        float j = 0.f;
-        if (f < n_here) j = jump_of(p[f][d], q, il[d], l64[d]);
-        run += j;
+        const float jv = f < n_here ? j4[f] : 0.f;
+        jumped |= jv != 0.f;
+        run += jv;
         jl[f][d] = run;
-        q = p[f][d];
       }
-      any_jump |= run != 0.f;
-    }
-    float off[3] = {0.f, 0.f, 0.f};  // exclusive scan of the lane totals
-    float tot[3] = {0.f, 0.f, 0.f};  // jumps of the whole chunk
-    if (__any_sync(0xffffffffu, any_jump)) {
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        float inc = jl[UNW_F - 1][d];
+      // most chunks hold no jump in a given dimension: then the image is the same for all of
+      // its frames, and the scan and the per-frame image arithmetic are skipped
+      if (__any_sync(0xffffffffu, jumped)) {
+        float inc = run;
 #pragma unroll
         for (int s2 = 1; s2 < 32; s2 <<= 1) {
           const float u = __shfl_up_sync(0xffffffffu, inc, s2);
           if (lane >= s2) inc += u;
         }
-        off[d] = inc - jl[UNW_F - 1][d];
+        off[d] = inc - run;
         tot[d] = __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+        for (int f = 0; f < UNW_F; ++f)
+          o[f][d] = shifted<L32>(p[f][d], img[d] - (off[d] + jl[f][d]), l64[d], l32[d]);
+      } else if (img[d] != 0.f) {
+#pragma unroll
+        for (int f = 0; f < UNW_F; ++f) o[f][d] = shifted<L32>(p[f][d], img[d], l64[d], l32[d]);
+      } else {
+#pragma unroll
+        for (int f = 0; f < UNW_F; ++f) o[f][d] = p[f][d];
       }
     }
-#pragma unroll
-    for (int f = 0; f < UNW_F; ++f)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const float m = img[d] - (off[d] + jl[f][d]);
-        float v = p[f][d];
-        if (m != 0.f) {
-          if (L32) v = fmaf(m, l32[d], v);
-          else v = __double2float_rn(__dadd_rn((double)v, __dmul_rn((double)m, l64[d])));
-        }
-        o[f][d] = v;
-      }
     *reinterpret_cast<float4*>(wsm + 12 * lane) = make_float4(o[0][0], o[0][1], o[0][2], o[1][0]);
     *reinterpret_cast<float4*>(wsm + 12 * lane + 4) = make_float4(o[1][1], o[1][2], o[2][0], o[2][1]);
     *reinterpret_cast<float4*>(wsm + 12 * lane + 8) = make_float4(o[2][2], o[3][0], o[3][1], o[3][2]);

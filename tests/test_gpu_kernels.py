@@ -503,6 +503,41 @@ def test_unwrap_reference_known_answer(cuda):
     np.testing.assert_allclose(carry_img.cpu().numpy(), np.asarray(g["expected_image_box"]))
 
 
+def test_unwrap_single_frame_excursions(cuda):
+    """An atom that leaves through a face and is back the next frame: the two jumps cancel in the
+    running sum of the lane that owns both frames (and in the chunk total), but the frame in
+    between carries another image.  Excursions at every frame offset of a lane, across lane and
+    chunk boundaries, in both directions, for an fp32-exact and an inexact box length."""
+    import torch
+    from lammps_analysis_b200 import kernels as K
+    from lammps_analysis_b200.engine import to_device_f32
+    from oracle import transformations as ot
+
+    T = 300
+    for L in (32.0, 31.7):
+        box = np.array([L, L * 1.25, L * 0.75])
+        rng = np.random.default_rng(9)
+        pos = np.empty((40, T, 3), dtype=np.float32)
+        pos[:] = (rng.random((40, 1, 3)) * 0.2 + 0.05) * box       # just inside the lower faces
+        pos += (rng.random((40, T, 3)) * 0.01 * box).astype(np.float32)
+        for a in range(40):
+            t = 1 + 3 * a + (a % 7)                                 # every offset mod 4, 127/128, ...
+            d = a % 3
+            sign = 1 if a % 2 else -1
+            pos[a, t, d] = (pos[a, t, d] - sign * 0.1 * box[d]) % box[d] if sign > 0 \
+                else pos[a, t, d]                                   # out through the lower face
+            if sign < 0:
+                pos[a, :, d] = box[d] - pos[a, :, d]                # sit near the upper face ...
+                pos[a, t, d] = 0.03 * box[d]                        # ... and hop over it once
+            if a % 5 == 0 and t + 130 < T:
+                pos[a, t + 127:t + 129, d] = pos[a, t, d]           # a two-frame stay across a chunk edge
+        want = ot.run_unwrap(pos, box, batch_size=T)
+        dev = to_device_f32(pos, cuda)
+        out = torch.empty_like(dev)
+        K.unwrap(dev, box, None, torch.zeros(40, 3, dtype=torch.float64, device=cuda), False, out)
+        assert np.array_equal(out.cpu().numpy(), want), f"box {L}"
+
+
 def test_unwrap_indices(cuda):
     import torch
     from lammps_analysis_b200 import kernels as K

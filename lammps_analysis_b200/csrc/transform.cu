@@ -9,6 +9,8 @@
 // so the kernels form the fp64 value the reference forms and round once to fp32.
 #include "mdk_common.cuh"
 
+#include <type_traits>
+
 namespace mdk {
 
 // One warp per atom; each lane owns one frame of a 32-frame chunk.  The jump count is an
@@ -33,10 +35,11 @@ __device__ __forceinline__ float jump_of(float p, float prev, float inv_l32, dou
 
 // The same decision for two (position, previous position) pairs on packed instructions.  The
 // fast result stands when |q - rint(q)| is clearly below 1/2 (q = rint(q) + r with |r| <= 1/2,
-// so "within 1e-3 of a half-integer" is |r| > 0.499) and |q| < 1000; otherwise the reference's
-// fp64 division decides.
-__device__ __forceinline__ void jump_pair(float2 cur, float2 prev, float inv_l32, double l64,
-                                          float& j0, float& j1) {
+// so "within 1e-3 of a half-integer" is |r| > 0.499) and |q| < 1000; otherwise bit 0 / bit 1 of
+// the return value asks for the reference's fp64 division (jump_exact) for the first / second
+// pair.
+__device__ __forceinline__ unsigned jump_pair(float2 cur, float2 prev, float inv_l32, float& j0,
+                                              float& j1) {
   const float2 q = __fmul2_rn(__fadd2_rn(cur, make_float2(-prev.x, -prev.y)),
                               make_float2(inv_l32, inv_l32));
   const float2 n = __fadd2_rn(__fadd2_rn(q, make_float2(12582912.0f, 12582912.0f)),
@@ -44,10 +47,12 @@ __device__ __forceinline__ void jump_pair(float2 cur, float2 prev, float inv_l32
   const float2 r = __fadd2_rn(q, make_float2(-n.x, -n.y));
   j0 = n.x;
   j1 = n.y;
-  if (fabsf(r.x) > 0.499f || !(fabsf(q.x) < 1000.f))
-    j0 = (float)rint(((double)cur.x - (double)prev.x) / l64);
-  if (fabsf(r.y) > 0.499f || !(fabsf(q.y) < 1000.f))
-    j1 = (float)rint(((double)cur.y - (double)prev.y) / l64);
+  const unsigned s0 = (fabsf(r.x) > 0.499f || !(fabsf(q.x) < 1000.f)) ? 1u : 0u;
+  const unsigned s1 = (fabsf(r.y) > 0.499f || !(fabsf(q.y) < 1000.f)) ? 2u : 0u;
+  return s0 | s1;
+}
+__device__ __noinline__ float jump_exact(float p, float prev, double l64) {
+  return (float)rint(((double)p - (double)prev) / l64);
 }
 
 template <bool L32>
@@ -94,12 +99,16 @@ unwrap_kernel(const float* __restrict__ pos, long long A, long long T, double lx
   }
 
   // element e of a chunk is loaded by lane (e/4)%32 in row (e/128): 16-byte vectors when the
-  // row start is 16-byte aligned (VEC: T % 4 == 0 and an aligned base), scalars otherwise
-  auto load_chunk = [&](long long tb, float4 (&r)[3]) {
+  // row start is 16-byte aligned (VEC: T % 4 == 0 and an aligned base), scalars otherwise.
+  // FULL chunks (this chunk and the one being prefetched lie wholly inside the row, VEC) run
+  // without any bounds arithmetic: the 64-bit index compares and selects of the general path were
+  // 40 % of the instructions of this kernel, which is bound by instruction issue, not by HBM.
+  auto load_chunk = [&](long long tb, float4 (&r)[3], auto full_tag) {
+    constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const long long e = tb * 3 + j * 128 + 4 * lane;
-      if (VEC && e + 3 < n_el) {
+      if (FULL || (VEC && e + 3 < n_el)) {
         r[j] = __ldg(reinterpret_cast<const float4*>(src + e));
       } else {
         r[j].x = e + 0 < n_el ? __ldg(src + e + 0) : 0.f;
@@ -111,16 +120,17 @@ unwrap_kernel(const float* __restrict__ pos, long long A, long long T, double lx
   };
   float4 pre[UNW_PF][3];
 #pragma unroll
-  for (int k = 0; k < UNW_PF; ++k) load_chunk((long long)k * UNW_CH, pre[k]);
+  for (int k = 0; k < UNW_PF; ++k) load_chunk((long long)k * UNW_CH, pre[k], std::false_type{});
 
-  for (long long tb = 0; tb < T; tb += UNW_CH) {
+  auto chunk = [&](long long tb, auto full_tag) {
+    constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
     for (int j = 0; j < 3; ++j) *reinterpret_cast<float4*>(wsm + j * 128 + 4 * lane) = pre[0][j];
 #pragma unroll
     for (int k = 0; k + 1 < UNW_PF; ++k)
 #pragma unroll
       for (int j = 0; j < 3; ++j) pre[k][j] = pre[k + 1][j];
-    load_chunk(tb + (long long)UNW_PF * UNW_CH, pre[UNW_PF - 1]);
+    load_chunk(tb + (long long)UNW_PF * UNW_CH, pre[UNW_PF - 1], full_tag);
     __syncwarp();
     // lane l owns frames tb + 4l .. tb + 4l + 3: floats [12 l, 12 l + 12) of the slab
     float p[UNW_F][3];
@@ -134,32 +144,38 @@ unwrap_kernel(const float* __restrict__ pos, long long A, long long T, double lx
     }
     __syncwarp();
     const long long t_first = tb + UNW_F * lane;
-    const int n_here = (int)min((long long)UNW_F, max(0ll, T - t_first));  // valid frames
-    const int last_lane = (int)((min((long long)UNW_CH, T - tb) - 1) / UNW_F);
-    const int last_f = (int)((min((long long)UNW_CH, T - tb) - 1) % UNW_F);
+    const int n_here = FULL ? UNW_F : (int)min((long long)UNW_F, max(0ll, T - t_first));
+    const int last_lane = FULL ? 31 : (int)((min((long long)UNW_CH, T - tb) - 1) / UNW_F);
+    const int last_f = FULL ? UNW_F - 1 : (int)((min((long long)UNW_CH, T - tb) - 1) % UNW_F);
     float o[UNW_F][3];
-    float jl[UNW_F][3];  // inclusive prefix of the jumps inside the lane
-    float off[3] = {0.f, 0.f, 0.f};  // exclusive scan of the lane totals
     float tot[3] = {0.f, 0.f, 0.f};  // jumps of the whole chunk
     static_assert(UNW_F == 4, "the packed jump test below pairs frames (0, 1) and (2, 3)");
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       float q = __shfl_up_sync(0xffffffffu, p[UNW_F - 1][d], 1);
       if (lane == 0) q = prevp[d];
-      // two frames per packed instruction: (p0, p1) - (q, p0) and (p2, p3) - (p1, p2)
+      // two frames per packed instruction: (p0, p1) - (q, p0) and (p2, p3) - (p1, p2); the rare
+      // exact re-evaluations of the four frames share one branch
       float j4[UNW_F];
-      jump_pair(make_float2(p[0][d], p[1][d]), make_float2(q, p[0][d]), il[d], l64[d], j4[0],
-                j4[1]);
-      jump_pair(make_float2(p[2][d], p[3][d]), make_float2(p[1][d], p[2][d]), il[d], l64[d],
-                j4[2], j4[3]);
+      const unsigned s01 = jump_pair(make_float2(p[0][d], p[1][d]), make_float2(q, p[0][d]),
+                                     il[d], j4[0], j4[1]);
+      const unsigned s23 = jump_pair(make_float2(p[2][d], p[3][d]),
+                                     make_float2(p[1][d], p[2][d]), il[d], j4[2], j4[3]);
+      if (s01 | s23) {
+        if (s01 & 1u) j4[0] = jump_exact(p[0][d], q, l64[d]);
+        if (s01 & 2u) j4[1] = jump_exact(p[1][d], p[0][d], l64[d]);
+        if (s23 & 1u) j4[2] = jump_exact(p[2][d], p[1][d], l64[d]);
+        if (s23 & 2u) j4[3] = jump_exact(p[3][d], p[2][d], l64[d]);
+      }
+      float jl[UNW_F];       // inclusive prefix of the jumps inside the lane
       float run = 0.f;
       bool jumped = false;   // any jump among this lane's frames (two may cancel in `run`)
 #pragma unroll
       for (int f = 0; f < UNW_F; ++f) {
-        const float jv = f < n_here ? j4[f] : 0.f;
+        const float jv = (FULL || f < n_here) ? j4[f] : 0.f;
         jumped |= jv != 0.f;
         run += jv;
-        jl[f][d] = run;
+        jl[f] = run;
       }
       // most chunks hold no jump in a given dimension: then the image is the same for all of
       // its frames, and the scan and the per-frame image arithmetic are skipped
@@ -170,11 +186,11 @@ unwrap_kernel(const float* __restrict__ pos, long long A, long long T, double lx
           const float u = __shfl_up_sync(0xffffffffu, inc, s2);
           if (lane >= s2) inc += u;
         }
-        off[d] = inc - run;
+        const float off = inc - run;   // exclusive scan of the lane totals
         tot[d] = __shfl_sync(0xffffffffu, inc, 31);
 #pragma unroll
         for (int f = 0; f < UNW_F; ++f)
-          o[f][d] = shifted<L32>(p[f][d], img[d] - (off[d] + jl[f][d]), l64[d], l32[d]);
+          o[f][d] = shifted<L32>(p[f][d], img[d] - (off + jl[f]), l64[d], l32[d]);
       } else if (img[d] != 0.f) {
 #pragma unroll
         for (int f = 0; f < UNW_F; ++f) o[f][d] = shifted<L32>(p[f][d], img[d], l64[d], l32[d]);
@@ -191,7 +207,7 @@ unwrap_kernel(const float* __restrict__ pos, long long A, long long T, double lx
     for (int j = 0; j < 3; ++j) {
       const long long e = tb * 3 + j * 128 + 4 * lane;
       const float4 v = *reinterpret_cast<const float4*>(wsm + j * 128 + 4 * lane);
-      if (VEC && e + 3 < n_el) {
+      if (FULL || (VEC && e + 3 < n_el)) {
         *reinterpret_cast<float4*>(dst + e) = v;
       } else {
         if (e + 0 < n_el) dst[e + 0] = v.x;
@@ -211,6 +227,13 @@ unwrap_kernel(const float* __restrict__ pos, long long A, long long T, double lx
       if (last_f == 0) lp = p[0][d];
       prevp[d] = __shfl_sync(0xffffffffu, lp, last_lane);
     }
+  };
+
+  for (long long tb = 0; tb < T; tb += UNW_CH) {
+    if (VEC && tb + (long long)(UNW_PF + 1) * UNW_CH <= T)
+      chunk(tb, std::true_type{});
+    else
+      chunk(tb, std::false_type{});
   }
   if (lane == 0) {
 #pragma unroll

@@ -148,6 +148,19 @@ int mdk_rdf_pack_sorted(const float* traj, long long A_total, long long T, long 
                         long long dst_first, int dst_span, const float* box, void* workspace,
                         long long workspace_bytes, mdk_stream_t stream);
 
+/* The same for a whole launch batch of frames of one species with ONE radix sort (the batch-local
+ * frame number rides above the Hilbert index in the key): for systems of ~10^5 atoms the
+ * per-frame sorts are launch-bound.  frames: device int[n_frames]; out: the packed array
+ * [n_frames][3][n_pad] (slab k receives frames[k]).  mdk_rdf_sort_batch_workspace returns the
+ * scratch size, or -1 when the batch is too large for this path (more than 2048 frames or 2^25
+ * atom-frames: use the per-frame call). */
+long long mdk_rdf_sort_batch_workspace(int max_atoms, int n_frames);
+int mdk_rdf_pack_sorted_batch(const float* traj, long long A_total, long long T,
+                              long long atom_first, int atom_count, const int* frames,
+                              int n_frames, float* out, long long n_pad, long long dst_first,
+                              int dst_span, const float* box, void* workspace,
+                              long long workspace_bytes, mdk_stream_t stream);
+
 /* Bounding boxes {min xyz, max xyz} of every MDK_RDF_SUBTILE-atom run of a packed frame array
  * (NaN padding ignored): bbox device float [n_frames][n_pad / MDK_RDF_SUBTILE][6].  Passed to
  * mdk_rdf_hist they let the kernel skip (row group, column sub-tile) blocks whose minimum-image

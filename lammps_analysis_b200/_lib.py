@@ -43,6 +43,8 @@ PROTOTYPES = {
     "mdk_rdf_tie_count": [_P, _LL, _LL, _P, _F, _F, _I, _P, _I, _P, _P],
     "mdk_rdf_sort_workspace": [_I],
     "mdk_rdf_pack_sorted": [_P, _LL, _LL, _LL, _I, _LL, _P, _LL, _LL, _I, _P, _P, _LL, _P],
+    "mdk_rdf_sort_batch_workspace": [_I, _I],
+    "mdk_rdf_pack_sorted_batch": [_P, _LL, _LL, _LL, _I, _P, _I, _P, _LL, _LL, _I, _P, _P, _LL, _P],
     "mdk_rdf_bbox": [_P, _I, _LL, _P, _P],
     "mdk_adf_workspace": [_LL, _I, _P, _F],
     "mdk_adf_hist": [_P, _I, _LL, _P, _I, _P, _F, _I, _D, _D, _I, _P, _P, _P, _P, _LL, _P],
@@ -77,7 +79,8 @@ def load():
     for name, argtypes in PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.argtypes = argtypes
-        fn.restype = _LL if name in ("mdk_rdf_sort_workspace", "mdk_adf_workspace") else _I
+        fn.restype = _LL if name in ("mdk_rdf_sort_workspace", "mdk_rdf_sort_batch_workspace",
+                                     "mdk_adf_workspace") else _I
     lib.mdk_last_error.argtypes = []
     lib.mdk_last_error.restype = C.c_char_p
     _lib = lib

@@ -51,7 +51,7 @@ class RdfEngine:
     # beyond the cutoff can be skipped; below it a tile spans too much of the box to gain
     TIE_ROWS = 1024
     TIE_PAIRS = 250_000_000
-    SORT_BATCH_FRAMES = 16
+    SORT_BATCH_FRAMES = 32
     SORT_MIN_ATOMS = 80_000    # measured on B200 (uniform-image kernel): -9 % at 50k atoms,
                                # +5 % at 100k, +24 % at 200k, +50 % at 10^6
 
@@ -130,9 +130,21 @@ class RdfEngine:
             self.add_packed(buf, len(sel), check_extent=check_extent, tuning=tuning, bbox=bbox)
 
     def pack_sorted(self, species_traj, frames, buf):
-        """Morton-ordered pack of the given frames (one sort per frame and species)."""
-        if self._work is None:
-            nbytes = K.rdf_sort_workspace(max(self.eff_counts))
+        """Hilbert-ordered pack of the given frames: one sort per species for the whole batch
+        when it is small enough (per-frame sorts of ~10^5 atoms are launch-bound), otherwise one
+        sort per frame and species."""
+        n_max = max(self.eff_counts)
+        need = K.rdf_sort_batch_workspace(n_max, len(frames)) if len(frames) > 1 else -1
+        if need >= 0:
+            if self._work is None or self._work.numel() < need:
+                self._work = torch.empty(need, dtype=torch.uint8, device=self.device)
+            fdev = torch.from_numpy(np.asarray(frames, dtype=np.int32)).to(self.device)
+            for s, traj in enumerate(species_traj):
+                K.rdf_pack_sorted_batch(traj, fdev, buf, self.layout, s, self.atom_first,
+                                        self.eff_counts[s], self.box, self._work)
+            return
+        nbytes = K.rdf_sort_workspace(n_max)
+        if self._work is None or self._work.numel() < nbytes:
             self._work = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         for k, f in enumerate(frames):
             for s, traj in enumerate(species_traj):

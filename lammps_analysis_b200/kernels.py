@@ -249,6 +249,36 @@ def rdf_pack_sorted(traj: torch.Tensor, frame: int, out: torch.Tensor, k: int, l
     _count(3)
 
 
+def rdf_sort_batch_workspace(max_atoms: int, n_frames: int) -> int:
+    """Scratch bytes of rdf_pack_sorted_batch, or -1 when the batch is too large for it."""
+    return int(_lib.load().mdk_rdf_sort_batch_workspace(int(max_atoms), int(n_frames)))
+
+
+def rdf_pack_sorted_batch(traj: torch.Tensor, frames: torch.Tensor, out: torch.Tensor,
+                          layout: RdfLayout, species_index: int, atom_first: int, atom_count: int,
+                          box, workspace: torch.Tensor):
+    """Hilbert-ordered pack of a batch of frames of one species (one radix sort for the batch)
+    into the slabs 0 .. len(frames) - 1 of ``out`` ([F][3][n_pad]).  frames: CUDA int32."""
+    _need_device_readable(traj, torch.float32, "rdf_pack_sorted_batch traj")
+    _need_cuda(out, torch.float32, "rdf_pack_sorted_batch out")
+    _need_cuda(frames, torch.int32, "rdf_pack_sorted_batch frames")
+    A, T, D = traj.shape
+    if D != 3:
+        raise MdkError("rdf_pack_sorted_batch: trajectory must be [A][T][3]")
+    lo = int(layout.sp_lo[species_index])
+    span = ((atom_count + layout.tile - 1) // layout.tile) * layout.tile
+    box32 = np.asarray(box, dtype=np.float32)
+    check(
+        _lib.load().mdk_rdf_pack_sorted_batch(
+            _ptr(traj), A, T, atom_first, atom_count, _ptr(frames), frames.numel(), _ptr(out),
+            layout.n_pad, lo, span, box32.ctypes.data_as(C.c_void_p), _ptr(workspace),
+            workspace.numel() * workspace.element_size(), _stream(),
+        ),
+        "mdk_rdf_pack_sorted_batch",
+    )
+    _count(3)
+
+
 def rdf_bbox(pos_soa: torch.Tensor, n_frames: int, layout: RdfLayout, bbox: torch.Tensor):
     """Bounding boxes [n_frames][n_pad / RDF_SUBTILE][6] of a packed frame array."""
     _need_cuda(pos_soa, torch.float32, "rdf_bbox pos")

@@ -749,6 +749,13 @@ def run_strong_leg(args, world, rank, dev, barrier):
         "rdf_pair_distances_per_s": pairs / t_rdf,
         "dynamics_atom_lag_updates_per_s": 2 * updates / (t_ein + t_gk),
         "h2d_bytes_this_rank": h2d, "setup_s": t_setup,
+        # the dynamics part is bound by the host link: 48 GB up (positions, velocities) and 24 GB
+        # down (unwrapped positions) over all ranks in t_einstein_s + t_green_kubo_s; compare
+        # with scripts/hostlink_probe.py (profiles/r02_hostlink_probe_*): 55 / 57 GB/s H2D / D2H
+        # for one rank, 227 / 115 GB/s aggregate for eight on the test box
+        "dynamics_host_link_GBps_aggregate": {
+            "h2d": 2 * 2 * n_sp * n_frames * 12 / (t_ein + t_gk) * 1e-9,
+            "d2h": 2 * n_sp * n_frames * 12 / (t_ein + t_gk) * 1e-9},
         "t_dynamics_first_pass_s": c_ein + c_gk,
         "D_A": ein["A"]["diffusion_coefficient"], "gk_D_A": gk["A"]["diffusion_coefficient"][0],
         "rdf_checksum": float(np.nansum(np.array(rdf["A_B"]["y"])[1:])),

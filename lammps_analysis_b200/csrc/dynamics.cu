@@ -504,6 +504,11 @@ msd_rw_kernel(const float* __restrict__ traj, long long T, long long a_lo, long 
 
   for (int k = lane; k < nl_pad * 32; k += 32) sacc[k] = 0.f;
   double total[4] = {0.0, 0.0, 0.0, 0.0};   // lane l keeps lags l + 32 r
+  // up to 12 lags per pass the register budget allows a second set of per-lane sums
+  constexpr bool RW_REG_ACC = NLP <= 12;
+  float racc[RW_REG_ACC ? NLP : 1];
+#pragma unroll
+  for (int k = 0; k < (RW_REG_ACC ? NLP : 1); ++k) racc[k] = 0.f;
 
   // a request copies the slab of chunk c: 16-byte copies up to the end of the row; the rest of
   // the slab (last chunks only) is zero-filled by 4-byte copies with source size 0
@@ -604,9 +609,22 @@ msd_rw_kernel(const float* __restrict__ traj, long long T, long long a_lo, long 
         float acc[NLP];
 #pragma unroll
         for (int k = 0; k < NLP; ++k) acc[k] = axy[k].x + axy[k].y;
-        float* __restrict__ sa = sacc + (size_t)g * NLP * 32 + lane;
+        if (RW_REG_ACC && n_pass == 1) {
+          // a single lag pass: the per-lane sums stay in registers for the whole atom
 #pragma unroll
-        for (int k = 0; k < NLP; ++k) sa[k * 32] += acc[k];
+          for (int k = 0; k < NLP; ++k) racc[k] += acc[k];
+        } else {
+          float* __restrict__ sa = sacc + (size_t)g * NLP * 32 + lane;
+#pragma unroll
+          for (int k = 0; k < NLP; ++k) sa[k * 32] += acc[k];
+        }
+      }
+    }
+    if (RW_REG_ACC && n_pass == 1) {
+#pragma unroll
+      for (int k = 0; k < NLP; ++k) {
+        sacc[k * 32 + lane] = racc[k];
+        racc[k] = 0.f;
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");

@@ -52,8 +52,9 @@ class RdfEngine:
     TIE_ROWS = 1024
     TIE_PAIRS = 250_000_000
     SORT_BATCH_FRAMES = 32
-    SORT_MIN_ATOMS = 80_000    # measured on B200 (uniform-image kernel): -9 % at 50k atoms,
-                               # +5 % at 100k, +24 % at 200k, +50 % at 10^6
+    SORT_MIN_ATOMS = 40_000    # measured on B200 (round 2: 32-atom boxes, one sort per batch):
+                               # -2 % at 30k atoms, +4 % at 50k, +10 % at 65k, +18 % at 100k,
+                               # +60 % at 10^6
 
     def __init__(self, counts, box, cutoff: float, nbins: int, drop_first: bool = True,
                  device=None, max_batch_bytes: int = 2 << 30, spatial_sort=None):
